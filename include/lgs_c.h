@@ -1,0 +1,224 @@
+/*
+ * lgs_c.h -- C ABI of the B200-native LiDAR front-end hot path (liblgs_b200.so).
+ *
+ * Drop-in boundary for RyuYamamoto/lidar_graph_slam: every entry point below replaces one call the
+ * reference makes through pcl::VoxelGrid / pcl::Registration.  Citations are
+ * file:line under the reference tree:
+ *   PPF = points_prefiltering/src/points_prefiltering.cpp
+ *   LSM = lidar_scan_matcher/src/lidar_scan_matcher.cpp
+ *   GBS = graph_based_slam/src/graph_based_slam.cpp
+ *   NDT.h / NDT = thirdparty/ndt_omp/include/pclomp/ndt_omp.h / ndt_omp_impl.hpp
+ *   VGC = thirdparty/ndt_omp/include/pclomp/voxel_grid_covariance_omp_impl.hpp
+ *   FG / FG.h = thirdparty/fast_gicp/include/fast_gicp/gicp/impl/fast_gicp_impl.hpp / fast_gicp.hpp
+ *   LSQ / LSQ.h = .../gicp/impl/lsq_registration_impl.hpp / lsq_registration.hpp
+ *
+ * Conventions
+ *   - plain C types only; every function returns LGS_OK (0) or a negative error code and never
+ *     throws; lgs_last_error() returns the thread's last message.
+ *   - all pointers are caller-owned HOST memory unless the parameter name ends in _dev.
+ *   - point clouds: `pts` + `n` + `stride_bytes`.  x,y,z are floats at byte offsets 0,4,8 of each
+ *     record; intensity is the float at offset 12 when stride_bytes == 16 (packed xyzi) and at offset
+ *     16 when stride_bytes >= 20 (pcl::PointXYZI, 32-byte records); absent (0) when stride_bytes == 12.
+ *   - 4x4 transforms are float[16] COLUMN-major (Eigen::Matrix4f memory order).
+ *   - handles are not thread-safe; use one lgs_ctx per host thread (the reference's registration
+ *     objects are stateful and non re-entrant as well, SURVEY.md section 8b "Threading").
+ *   - there is no CPU fallback: without a CUDA device every call fails with LGS_ERR_CUDA.
+ */
+#ifndef LGS_C_H_
+#define LGS_C_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_OK 0
+#define LGS_ERR_INVALID (-1)
+#define LGS_ERR_CUDA (-2)
+#define LGS_ERR_STATE (-3)
+
+/* ------------------------------------------------------------------------------------------- */
+/* context: one CUDA device + one stream + scratch arenas                                        */
+typedef struct lgs_ctx lgs_ctx;
+
+/* cuda_stream: a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
+ * let the context create its own non-blocking stream. */
+int lgs_ctx_create(int device, void* cuda_stream, lgs_ctx** out);
+void lgs_ctx_destroy(lgs_ctx* ctx);
+int lgs_ctx_synchronize(lgs_ctx* ctx);
+const char* lgs_last_error(void);
+const char* lgs_version(void);
+/* number of kernel launches issued through this context since creation (bench.py "gpu_launches") */
+int64_t lgs_ctx_launch_count(const lgs_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------- */
+/* prefilter: range crop + box crop + pcl::VoxelGrid                                             */
+/*   replaces PPF:102-112 (distance_filter), PPF:89-100 (crop), PPF:114-121 (downsample ->        */
+/*   VoxelGrid::setLeafSize/setInputCloud/filter) and the VoxelGrid calls at GBS:311-313,490-493 */
+#define LGS_VG_OK 0
+#define LGS_VG_REFUSED_OVERFLOW 1 /* dx*dy*dz > INT32_MAX: like pcl::VoxelGrid, output = cropped input */
+
+typedef struct lgs_voxelgrid_info {
+  int32_t status;    /* LGS_VG_OK or LGS_VG_REFUSED_OVERFLOW */
+  int32_t reserved;
+  int64_t n_kept;    /* points that survive the crop */
+  int64_t n_out;     /* output points (occupied voxels with >= min_points_per_voxel) */
+  int32_t min_b[3];  /* integer bounding box of the kept points, in leaf units */
+  int32_t max_b[3];
+  int32_t div_b[3];
+} lgs_voxelgrid_info;
+
+/* range_min < 0 disables the range test (keep iff range_min < |p|, strict, f32 norm as PPF:107-108);
+ * box6 = {min_x,max_x,min_y,max_y,min_z,max_z} or NULL (strict inequalities as PPF:93-96).
+ * out_pts: capacity n packed xyzi records (16 B each), centroids in ascending voxel-index order.
+ * out_voxel_idx[n]: per input point its voxel index (-1 if cropped); out_member_rank[n]: row of out_pts
+ * the point was averaged into (-1 if none).  Either may be NULL. */
+int lgs_voxelgrid_filter(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const float leaf[3],
+                         int32_t min_points_per_voxel, double range_min, const double* box6, float* out_pts,
+                         int32_t* out_voxel_idx, int32_t* out_member_rank, lgs_voxelgrid_info* info);
+
+/* Same, with the input cloud already resident in device memory as packed float4 xyzi and the three
+ * outputs written to device memory (any of them may be NULL).  info is still returned on the host. */
+int lgs_voxelgrid_filter_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, const float leaf[3],
+                             int32_t min_points_per_voxel, double range_min, const double* box6, float* out_pts_dev,
+                             int32_t* out_voxel_idx_dev, int32_t* out_member_rank_dev, lgs_voxelgrid_info* info);
+
+/* ------------------------------------------------------------------------------------------- */
+/* shared result of one registration (both methods)                                              */
+typedef struct lgs_align_result {
+  float T[16];               /* getFinalTransformation(), column-major */
+  double fitness;            /* filled by *_fitness / batch only; otherwise 0 */
+  double trans_probability;  /* NDT getTransformationProbability() (NDT:170); 0 for GICP */
+  int32_t iterations;        /* NDT getFinalNumIteration() / nr_iterations_ (LSQ:66 definition for GICP) */
+  int32_t converged;         /* hasConverged() */
+  int32_t evaluations;       /* derivative evaluations (NDT) / linearize calls (GICP) */
+  int32_t line_search_trials;/* NDT More-Thuente inner iterations / GICP compute_error calls */
+  int32_t hessian_recomputes;/* NDT computeHessian calls */
+  int32_t pair_id;           /* batch API: index of the pair this record belongs to */
+} lgs_align_result;
+
+/* ------------------------------------------------------------------------------------------- */
+/* NDT: pclomp::NormalDistributionsTransform behind pcl::Registration (NDT.h:71-502)             */
+typedef struct lgs_ndt lgs_ndt;
+
+#define LGS_NDT_KDTREE 0 /* enum order of ndt_omp.h:52-57; KDTREE is not supported (LGS_ERR_INVALID) */
+#define LGS_NDT_DIRECT26 1
+#define LGS_NDT_DIRECT7 2
+#define LGS_NDT_DIRECT1 3
+
+int lgs_ndt_create(lgs_ctx* ctx, lgs_ndt** out);
+void lgs_ndt_destroy(lgs_ndt* ndt);
+int lgs_ndt_set_resolution(lgs_ndt* ndt, float resolution);             /* NDT.h:132-142 setResolution */
+int lgs_ndt_set_step_size(lgs_ndt* ndt, double step_size);              /* NDT.h:162-166 setStepSize */
+int lgs_ndt_set_transformation_epsilon(lgs_ndt* ndt, double eps);       /* pcl::Registration::setTransformationEpsilon, LSM:58 */
+int lgs_ndt_set_maximum_iterations(lgs_ndt* ndt, int32_t n);            /* pcl::Registration::setMaximumIterations, LSM:66 */
+int lgs_ndt_set_outlier_ratio(lgs_ndt* ndt, double ratio);              /* NDT.h:180-184 setOutlierRatio */
+int lgs_ndt_set_search_method(lgs_ndt* ndt, int32_t method);            /* NDT.h:186-188 setNeighborhoodSearchMethod */
+/* setInputTarget (NDT.h:122-127): uploads and re-voxelises on EVERY call -- the scan matcher mutates
+ * the target cloud in place and passes the same pointer again (LSM:187-212). */
+int lgs_ndt_set_target(lgs_ndt* ndt, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_ndt_set_source(lgs_ndt* ndt, const void* pts, int64_t n, int32_t stride_bytes);   /* setInputSource, LSM:162 */
+/* device-resident variants (packed float4 xyzi already in HBM) */
+int lgs_ndt_set_target_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
+int lgs_ndt_set_source_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
+/* align (pcl::Registration::align + NDT:80-171, LSM:165, GBS:318).  guess may be NULL (identity).
+ * out_cloud: NULL or capacity n_source packed xyzi records = source transformed by the final T. */
+int lgs_ndt_align(lgs_ndt* ndt, const float* guess16, lgs_align_result* result, float* out_cloud);
+/* getFitnessScore(max_range) (PCL registration.hpp, GBS:321): exact 1-NN mean squared distance */
+int lgs_ndt_fitness(lgs_ndt* ndt, double max_range, double* fitness);
+/* calculateScore (NDT:934-982) of the source transformed by T */
+int lgs_ndt_calculate_score(lgs_ndt* ndt, const float* T16, double* score);
+
+/* parity hooks (SURVEY.md section 8b "export_voxels for parity tests") */
+typedef struct lgs_ndt_grid_info {
+  int32_t refused;   /* 1 when the target grid was refused (VGC:79-84) */
+  int32_t dense;     /* 1 dense cell table, 0 hashed cell table */
+  int64_t n_voxels;  /* occupied voxels (all leaves, including those with < 6 points) */
+  int64_t n_valid;   /* voxels usable by the lookup (n >= 6 and covariance checks passed) */
+  int32_t min_b[3];
+  int32_t max_b[3];
+  int32_t div_b[3];
+  int32_t reserved;
+} lgs_ndt_grid_info;
+int lgs_ndt_grid_info_get(lgs_ndt* ndt, lgs_ndt_grid_info* info);
+/* arrays of n_voxels entries, ascending idx: idx, nr_points (-1 when invalidated, VGC:339,363),
+ * mean[3], cov[9], icov[9] (row-major f64).  Any pointer may be NULL. */
+int lgs_ndt_export_voxels(lgs_ndt* ndt, int32_t* idx, int32_t* nr_points, double* mean, double* cov, double* icov);
+/* one derivative evaluation with the source transformed by T16 and the angle tables of p6:
+ * mode 0 = computeDerivatives(compute_hessian=true) (NDT:179-285), 1 = gradient only,
+ * mode 2 = computeHessian (f64, NDT:539-644).  Outputs: score, g[6], H[36] row-major. */
+int lgs_ndt_derivatives(lgs_ndt* ndt, const float* T16, const double* p6, int32_t mode, double* score, double* g6, double* H36);
+
+/* ------------------------------------------------------------------------------------------- */
+/* GICP: fast_gicp::FastGICP over LsqRegistration (FG.h:48-70, LSQ.h:48-60)                       */
+typedef struct lgs_gicp lgs_gicp;
+
+#define LGS_REG_NONE 0 /* enum order of gicp_settings.hpp:6 */
+#define LGS_REG_MIN_EIG 1
+#define LGS_REG_NORMALIZED_MIN_EIG 2
+#define LGS_REG_PLANE 3
+#define LGS_REG_FROBENIUS 4
+
+int lgs_gicp_create(lgs_ctx* ctx, lgs_gicp** out);
+void lgs_gicp_destroy(lgs_gicp* g);
+int lgs_gicp_set_correspondence_randomness(lgs_gicp* g, int32_t k);     /* FG:40-42 */
+int lgs_gicp_set_max_correspondence_distance(lgs_gicp* g, double d);    /* pcl::Registration, LSM:44 */
+int lgs_gicp_set_transformation_epsilon(lgs_gicp* g, double eps);
+int lgs_gicp_set_rotation_epsilon(lgs_gicp* g, double eps);             /* LSQ:28-30 */
+int lgs_gicp_set_maximum_iterations(lgs_gicp* g, int32_t n);
+int lgs_gicp_set_regularization_method(lgs_gicp* g, int32_t method);    /* FG:45-47 */
+int lgs_gicp_set_initial_lambda_factor(lgs_gicp* g, double f);          /* LSQ:33-35 */
+/* setInputSource / setInputTarget (FG:72-90).  Unlike the reference these never cache on pointer
+ * identity: each call uploads and invalidates the cloud's covariances. */
+int lgs_gicp_set_source(lgs_gicp* g, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_gicp_set_target(lgs_gicp* g, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_gicp_set_source_dev(lgs_gicp* g, const float* pts_dev, int64_t n);
+int lgs_gicp_set_target_dev(lgs_gicp* g, const float* pts_dev, int64_t n);
+int lgs_gicp_swap_source_and_target(lgs_gicp* g);                       /* FG:50-57 */
+int lgs_gicp_clear_source(lgs_gicp* g);                                 /* FG:60-63 */
+int lgs_gicp_clear_target(lgs_gicp* g);                                 /* FG:66-69 */
+int lgs_gicp_align(lgs_gicp* g, const float* guess16, lgs_align_result* result, float* out_cloud);
+int lgs_gicp_fitness(lgs_gicp* g, double max_range, double* fitness);
+int lgs_gicp_final_hessian(lgs_gicp* g, double* H36);                   /* LSQ:43-45 getFinalHessian */
+/* parity hooks: which = 0 source, 1 target; covs = n x 9 f64 row-major (computed on demand, FG:241-298) */
+int lgs_gicp_export_covariances(lgs_gicp* g, int32_t which, double* covs);
+/* evaluateCost / linearize at a row-major f64 4x4 (LSQ:48-50, FG:155-211): cost, H[36], b[6], and
+ * optionally the per-source-point correspondence index (-1 = none) */
+int lgs_gicp_linearize(lgs_gicp* g, const double* T16_rowmajor, double* cost, double* H36, double* b6, int32_t* correspondences);
+
+/* exact k-NN of `queries` in `pts` (the search behind FG:133 and FG:254); idx/d2 are m x k, ascending */
+int lgs_knn(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const void* queries, int64_t m, int32_t qstride_bytes,
+            int32_t k, int32_t* idx, float* d2);
+
+/* ------------------------------------------------------------------------------------------- */
+/* batched loop-closure verification: GBS:297-322 for a list of (scan, submap) pairs              */
+#define LGS_METHOD_NDT 0
+#define LGS_METHOD_GICP 1
+
+typedef struct lgs_batch_params {
+  int32_t method;                 /* LGS_METHOD_* */
+  int32_t max_iterations;         /* graph_based_slam.param.yaml */
+  double transformation_epsilon;
+  double max_correspondence_distance; /* GICP; <= 0 keeps FLT_MAX */
+  int32_t k_correspondences;      /* GICP */
+  float ndt_resolution;           /* NDT */
+  double ndt_step_size;
+  float submap_leaf;              /* VoxelGrid leaf applied to each submap before setInputTarget (GBS:61: 0.5); <= 0 disables */
+  double fitness_max_range;       /* getFitnessScore(max_range); <= 0 means DBL_MAX (GBS:321) */
+  int32_t n_workers;              /* concurrent pairs per GPU (each on its own stream); <= 0 picks a default */
+  int32_t reserved;
+} lgs_batch_params;
+
+/* Each pair i: scan = scans[i] (n_scan[i] points), submap = submaps[i] (n_submap[i] points), all with the
+ * same stride; guesses16 = n_pairs x 16 floats or NULL (identity, GBS:318).  records[n_pairs] receives
+ * (T, fitness, iterations, converged, pair_id = pair_id0 + i).  records_dev, when not NULL, is a device
+ * buffer of n_pairs records that receives the same data (the NCCL gather's send buffer). */
+int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
+                    const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
+                    const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGS_C_H_ */

@@ -1,0 +1,119 @@
+"""ctypes loader for liblgs_b200.so (the C-ABI declared in include/lgs_c.h).
+
+The library is the product: there is no Python or CPU fallback.  Importing this module without the built
+shared object, or calling into it on a box without a CUDA device, fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblgs_b200.so")
+
+LGS_OK = 0
+
+
+class LgsError(RuntimeError):
+    pass
+
+
+class VoxelGridInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("reserved", C.c_int32), ("n_kept", C.c_int64), ("n_out", C.c_int64),
+                ("min_b", C.c_int32 * 3), ("max_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3)]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("trans_probability", C.c_double), ("iterations", C.c_int32),
+                ("converged", C.c_int32), ("evaluations", C.c_int32), ("line_search_trials", C.c_int32),
+                ("hessian_recomputes", C.c_int32), ("pair_id", C.c_int32)]
+
+
+class NdtGridInfo(C.Structure):
+    _fields_ = [("refused", C.c_int32), ("dense", C.c_int32), ("n_voxels", C.c_int64), ("n_valid", C.c_int64),
+                ("min_b", C.c_int32 * 3), ("max_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3), ("reserved", C.c_int32)]
+
+
+class BatchParams(C.Structure):
+    _fields_ = [("method", C.c_int32), ("max_iterations", C.c_int32), ("transformation_epsilon", C.c_double),
+                ("max_correspondence_distance", C.c_double), ("k_correspondences", C.c_int32), ("ndt_resolution", C.c_float),
+                ("ndt_step_size", C.c_double), ("submap_leaf", C.c_float), ("fitness_max_range", C.c_double),
+                ("n_workers", C.c_int32), ("reserved", C.c_int32)]
+
+
+# every symbol include/lgs_c.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+SYMBOLS = {
+    "lgs_ctx_create": (_i32, [_i32, _vp, C.POINTER(_vp)]),
+    "lgs_ctx_destroy": (None, [_vp]),
+    "lgs_ctx_synchronize": (_i32, [_vp]),
+    "lgs_last_error": (C.c_char_p, []),
+    "lgs_version": (C.c_char_p, []),
+    "lgs_ctx_launch_count": (_i64, [_vp]),
+    "lgs_voxelgrid_filter": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
+    "lgs_voxelgrid_filter_dev": (_i32, [_vp, _vp, _i64, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
+    "lgs_ndt_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_ndt_destroy": (None, [_vp]),
+    "lgs_ndt_set_resolution": (_i32, [_vp, _f32]),
+    "lgs_ndt_set_step_size": (_i32, [_vp, _f64]),
+    "lgs_ndt_set_transformation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_ndt_set_maximum_iterations": (_i32, [_vp, _i32]),
+    "lgs_ndt_set_outlier_ratio": (_i32, [_vp, _f64]),
+    "lgs_ndt_set_search_method": (_i32, [_vp, _i32]),
+    "lgs_ndt_set_target": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_ndt_set_source": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_ndt_set_target_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_ndt_set_source_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_ndt_align": (_i32, [_vp, _vp, C.POINTER(AlignResult), _vp]),
+    "lgs_ndt_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
+    "lgs_ndt_calculate_score": (_i32, [_vp, _vp, C.POINTER(_f64)]),
+    "lgs_ndt_grid_info_get": (_i32, [_vp, C.POINTER(NdtGridInfo)]),
+    "lgs_ndt_export_voxels": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lgs_ndt_derivatives": (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_f64), _vp, _vp]),
+    "lgs_gicp_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_gicp_destroy": (None, [_vp]),
+    "lgs_gicp_set_correspondence_randomness": (_i32, [_vp, _i32]),
+    "lgs_gicp_set_max_correspondence_distance": (_i32, [_vp, _f64]),
+    "lgs_gicp_set_transformation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_gicp_set_rotation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_gicp_set_maximum_iterations": (_i32, [_vp, _i32]),
+    "lgs_gicp_set_regularization_method": (_i32, [_vp, _i32]),
+    "lgs_gicp_set_initial_lambda_factor": (_i32, [_vp, _f64]),
+    "lgs_gicp_set_source": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_gicp_set_target": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_gicp_set_source_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_gicp_set_target_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_gicp_swap_source_and_target": (_i32, [_vp]),
+    "lgs_gicp_clear_source": (_i32, [_vp]),
+    "lgs_gicp_clear_target": (_i32, [_vp]),
+    "lgs_gicp_align": (_i32, [_vp, _vp, C.POINTER(AlignResult), _vp]),
+    "lgs_gicp_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
+    "lgs_gicp_final_hessian": (_i32, [_vp, _vp]),
+    "lgs_gicp_export_covariances": (_i32, [_vp, _i32, _vp]),
+    "lgs_gicp_linearize": (_i32, [_vp, _vp, C.POINTER(_f64), _vp, _vp, _vp]),
+    "lgs_knn": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads liblgs_b200.so and binds every symbol of include/lgs_c.h.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise LgsError("%s is missing: build it with `python -m lidar_graph_slam_b200.build` (nvcc, sm_100a). "
+                       "There is no CPU fallback." % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != LGS_OK:
+        msg = load().lgs_last_error()
+        raise LgsError("liblgs_b200 error %d: %s" % (rc, msg.decode("utf-8", "replace") if msg else "?"))

@@ -1,0 +1,356 @@
+"""Host-side mirror of the reference's call surface for the LiDAR front-end hot path.
+
+Class and method names follow pcl::VoxelGrid / pcl::Registration as the reference uses them
+(SURVEY.md section 8b): `VoxelGrid.setLeafSize/setInputCloud/filter` (PPF:118-120, GBS:311-313),
+`NormalDistributionsTransform` (LSM:56-72) and `FastGICP` (LSM:38-54) with `setInputTarget / setInputSource /
+align / hasConverged / getFinalTransformation / getFitnessScore`.  Everything computes in liblgs_b200.so on the GPU.
+
+Clouds are numpy float32 arrays of shape (N, 4) [x, y, z, intensity] (16-byte records) or (N, 8) (the 32-byte
+pcl::PointXYZI layout), or CUDA torch tensors of shape (N, 4) for the device-resident variants.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AlignResult, BatchParams, NdtGridInfo, VoxelGridInfo, check
+
+NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
+REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = 0, 1, 2, 3, 4
+METHOD_NDT, METHOD_GICP = 0, 1
+VG_OK, VG_REFUSED_OVERFLOW = 0, 1
+DBL_MAX = float(np.finfo(np.float64).max)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _host_cloud(pts):
+    a = np.ascontiguousarray(pts, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4, 8):
+        raise ValueError("cloud must be (N,3), (N,4) xyzi or (N,8) PointXYZI float32")
+    return a, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1] * 4
+
+
+def _dev_cloud(t):
+    if not (t.is_cuda and t.dim() == 2 and t.shape[1] == 4 and t.is_contiguous() and str(t.dtype) == "torch.float32"):
+        raise ValueError("device cloud must be a contiguous CUDA float32 tensor of shape (N, 4)")
+    return C.c_void_p(t.data_ptr()), t.shape[0]
+
+
+def _mat_to_c(T):
+    if T is None:
+        return None, None
+    a = np.asarray(T, dtype=np.float32).reshape(4, 4).ravel(order="F").copy()
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _result_T(res):
+    return np.array(res.T, dtype=np.float32).reshape(4, 4, order="F")
+
+
+class Context:
+    """One CUDA device + one stream (include/lgs_c.h lgs_ctx).  stream: a raw cudaStream_t handle or None."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        check(self._L.lgs_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def synchronize(self):
+        check(self._L.lgs_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._L.lgs_ctx_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lgs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid<PointXYZI> plus the prefilter's crop predicates (PPF:89-121)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        self._leaf = np.array([0.01, 0.01, 0.01], np.float32)
+        self._min_pts = 0
+        self._range_min = -1.0
+        self._box = None
+        self._cloud = None
+        self.info = None
+        self.voxel_idx = None
+        self.member_rank = None
+
+    def setLeafSize(self, lx, ly=None, lz=None):
+        ly = lx if ly is None else ly
+        lz = lx if lz is None else lz
+        self._leaf = np.array([lx, ly, lz], dtype=np.float32)  # double -> float as VoxelGrid::setLeafSize(float,...)
+
+    def setMinimumPointsNumberPerVoxel(self, n):
+        self._min_pts = int(n)
+
+    def setRangeCrop(self, min_distance):
+        """distance_filter of the prefilter node (PPF:102-112); None disables."""
+        self._range_min = -1.0 if min_distance is None else float(min_distance)
+
+    def setBoxCrop(self, box6):
+        """crop of the prefilter node (PPF:89-100): (min_x, max_x, min_y, max_y, min_z, max_z) or None."""
+        self._box = None if box6 is None else np.asarray(box6, dtype=np.float64).copy()
+
+    def setInputCloud(self, cloud):
+        self._cloud = cloud
+
+    def filter(self, want_membership=True):
+        """Returns the downsampled cloud (M, 4).  Per-point voxel_idx / member_rank land in attributes."""
+        leaf_p = self._leaf.ctypes.data_as(C.c_void_p)
+        box_p = self._box.ctypes.data_as(C.c_void_p) if self._box is not None else None
+        info = VoxelGridInfo()
+        if _is_torch(self._cloud):
+            import torch
+            p, n = _dev_cloud(self._cloud)
+            out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self._cloud.device)
+            vidx = torch.empty(max(n, 1), dtype=torch.int32, device=self._cloud.device) if want_membership else None
+            rank = torch.empty(max(n, 1), dtype=torch.int32, device=self._cloud.device) if want_membership else None
+            check(self._L.lgs_voxelgrid_filter_dev(self.ctx._h, p, n, leaf_p, self._min_pts, self._range_min, box_p, C.c_void_p(out.data_ptr()),
+                                                   C.c_void_p(vidx.data_ptr()) if want_membership else None,
+                                                   C.c_void_p(rank.data_ptr()) if want_membership else None, C.byref(info)))
+            self.info = info
+            self.voxel_idx = vidx[:n] if want_membership else None
+            self.member_rank = rank[:n] if want_membership else None
+            return out[: info.n_out]
+        a, p, n, stride = _host_cloud(self._cloud)
+        out = np.empty((max(n, 1), 4), np.float32)
+        vidx = np.empty(max(n, 1), np.int32) if want_membership else None
+        rank = np.empty(max(n, 1), np.int32) if want_membership else None
+        check(self._L.lgs_voxelgrid_filter(self.ctx._h, p, n, stride, leaf_p, self._min_pts, self._range_min, box_p,
+                                           out.ctypes.data_as(C.c_void_p), vidx.ctypes.data_as(C.c_void_p) if want_membership else None,
+                                           rank.ctypes.data_as(C.c_void_p) if want_membership else None, C.byref(info)))
+        self.info = info
+        self.voxel_idx = vidx[:n] if want_membership else None
+        self.member_rank = rank[:n] if want_membership else None
+        return out[: info.n_out].copy()
+
+
+class _Registration:
+    """Shared pcl::Registration surface."""
+
+    _prefix = ""
+
+    def _fn(self, name):
+        return getattr(self._L, "lgs_%s_%s" % (self._prefix, name))
+
+    def _set_cloud(self, which, cloud):
+        if _is_torch(cloud):
+            p, n = _dev_cloud(cloud)
+            check(self._fn("set_%s_dev" % which)(self._h, p, n))
+        else:
+            _, p, n, stride = _host_cloud(cloud)
+            check(self._fn("set_%s" % which)(self._h, p, n, stride))
+        return n
+
+    def setInputTarget(self, cloud):
+        self._nt = self._set_cloud("target", cloud)
+
+    def setInputSource(self, cloud):
+        self._ns = self._set_cloud("source", cloud)
+
+    def align(self, guess=None, want_output=False):
+        """Runs the registration.  Returns the aligned source cloud when want_output, else None."""
+        keep, gp = _mat_to_c(guess)
+        res = AlignResult()
+        out = np.empty((max(self._ns, 1), 4), np.float32) if want_output else None
+        check(self._fn("align")(self._h, gp, C.byref(res), out.ctypes.data_as(C.c_void_p) if want_output else None))
+        self.result = res
+        self.final_transformation = _result_T(res)
+        return out[: self._ns] if want_output else None
+
+    def hasConverged(self):
+        return bool(self.result.converged)
+
+    def getFinalTransformation(self):
+        return self.final_transformation
+
+    def getFitnessScore(self, max_range=DBL_MAX):
+        f = C.c_double()
+        check(self._fn("fitness")(self._h, float(max_range), C.byref(f)))
+        return f.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._fn("destroy")(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class NormalDistributionsTransform(_Registration):
+    """pclomp::NormalDistributionsTransform (NDT.h:71-502)."""
+
+    _prefix = "ndt"
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_ndt_create(self.ctx._h, C.byref(h)))
+        self._h = h
+        self._ns = self._nt = 0
+        self._resolution, self._step, self._outlier = 1.0, 0.1, 0.55
+
+    def setResolution(self, r): check(self._L.lgs_ndt_set_resolution(self._h, float(r))); self._resolution = float(r)
+    def getResolution(self): return self._resolution
+    def setStepSize(self, s): check(self._L.lgs_ndt_set_step_size(self._h, float(s))); self._step = float(s)
+    def getStepSize(self): return self._step
+    def setOutlierRatio(self, o): check(self._L.lgs_ndt_set_outlier_ratio(self._h, float(o))); self._outlier = float(o)
+    def getOutlierRatio(self): return self._outlier
+    def setTransformationEpsilon(self, e): check(self._L.lgs_ndt_set_transformation_epsilon(self._h, float(e)))
+    def setMaximumIterations(self, n): check(self._L.lgs_ndt_set_maximum_iterations(self._h, int(n)))
+    def setNeighborhoodSearchMethod(self, m): check(self._L.lgs_ndt_set_search_method(self._h, int(m)))
+    def setNumThreads(self, n): pass  # OpenMP knob of the reference (NDT.h:113-115); meaningless on the GPU
+
+    def getTransformationProbability(self): return self.result.trans_probability
+    def getFinalNumIteration(self): return int(self.result.iterations)
+
+    def calculateScore(self, T):
+        keep, tp = _mat_to_c(T)
+        s = C.c_double()
+        check(self._L.lgs_ndt_calculate_score(self._h, tp, C.byref(s)))
+        return s.value
+
+    # parity hooks -------------------------------------------------------------------------------
+    def grid_info(self):
+        gi = NdtGridInfo()
+        check(self._L.lgs_ndt_grid_info_get(self._h, C.byref(gi)))
+        return gi
+
+    def export_voxels(self):
+        gi = self.grid_info()
+        v = int(gi.n_voxels)
+        idx, npts = np.empty(v, np.int32), np.empty(v, np.int32)
+        mean, cov, icov = np.empty((v, 3)), np.empty((v, 9)), np.empty((v, 9))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self._L.lgs_ndt_export_voxels(self._h, vp(idx), vp(npts), vp(mean), vp(cov), vp(icov)))
+        return dict(idx=idx, n=npts, mean=mean, cov=cov, icov=icov, min_b=np.array(gi.min_b), max_b=np.array(gi.max_b),
+                    div_b=np.array(gi.div_b), refused=bool(gi.refused), dense=bool(gi.dense), n_valid=int(gi.n_valid))
+
+    def derivatives(self, T, p, mode=0):
+        keep, tp = _mat_to_c(T)
+        p = np.asarray(p, np.float64).copy()
+        s = C.c_double()
+        g, H = np.zeros(6), np.zeros(36)
+        check(self._L.lgs_ndt_derivatives(self._h, tp, p.ctypes.data_as(C.c_void_p), int(mode), C.byref(s), g.ctypes.data_as(C.c_void_p),
+                                          H.ctypes.data_as(C.c_void_p)))
+        return s.value, g, H.reshape(6, 6)
+
+
+class FastGICP(_Registration):
+    """fast_gicp::FastGICP (fast_gicp.hpp:48-70 over lsq_registration.hpp:48-60)."""
+
+    _prefix = "gicp"
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_gicp_create(self.ctx._h, C.byref(h)))
+        self._h = h
+        self._ns = self._nt = 0
+
+    def setCorrespondenceRandomness(self, k): check(self._L.lgs_gicp_set_correspondence_randomness(self._h, int(k)))
+    def setMaxCorrespondenceDistance(self, d): check(self._L.lgs_gicp_set_max_correspondence_distance(self._h, float(d)))
+    def setTransformationEpsilon(self, e): check(self._L.lgs_gicp_set_transformation_epsilon(self._h, float(e)))
+    def setRotationEpsilon(self, e): check(self._L.lgs_gicp_set_rotation_epsilon(self._h, float(e)))
+    def setMaximumIterations(self, n): check(self._L.lgs_gicp_set_maximum_iterations(self._h, int(n)))
+    def setRegularizationMethod(self, m): check(self._L.lgs_gicp_set_regularization_method(self._h, int(m)))
+    def setInitialLambdaFactor(self, f): check(self._L.lgs_gicp_set_initial_lambda_factor(self._h, float(f)))
+    def setNumThreads(self, n): pass
+
+    def swapSourceAndTarget(self):
+        check(self._L.lgs_gicp_swap_source_and_target(self._h))
+        self._ns, self._nt = self._nt, self._ns
+
+    def clearSource(self): check(self._L.lgs_gicp_clear_source(self._h)); self._ns = 0
+    def clearTarget(self): check(self._L.lgs_gicp_clear_target(self._h)); self._nt = 0
+
+    def getFinalHessian(self):
+        H = np.empty(36)
+        check(self._L.lgs_gicp_final_hessian(self._h, H.ctypes.data_as(C.c_void_p)))
+        return H.reshape(6, 6)
+
+    def covariances(self, which):
+        n = self._ns if which == 0 else self._nt
+        c = np.empty((n, 9))
+        check(self._L.lgs_gicp_export_covariances(self._h, int(which), c.ctypes.data_as(C.c_void_p)))
+        return c.reshape(n, 3, 3)
+
+    def linearize(self, T):
+        Tr = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4))
+        cost = C.c_double()
+        H, b = np.zeros(36), np.zeros(6)
+        corr = np.empty(max(self._ns, 1), np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self._L.lgs_gicp_linearize(self._h, vp(Tr), C.byref(cost), vp(H), vp(b), vp(corr)))
+        return cost.value, H.reshape(6, 6), b, corr[: self._ns]
+
+
+def knn(pts, queries, k, ctx=None):
+    """Exact k-NN of `queries` in `pts` (the search behind FG:133 / FG:254).  Returns (idx (m,k) int32, d2 (m,k) f32)."""
+    ctx = ctx or default_context()
+    a, pa, n, sa = _host_cloud(pts)
+    q, pq, m, sq = _host_cloud(queries)
+    idx = np.empty((max(m, 1), k), np.int32)
+    d2 = np.empty((max(m, 1), k), np.float32)
+    check(ctx._L.lgs_knn(ctx._h, pa, n, sa, pq, m, sq, int(k), idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p)))
+    return idx[:m], d2[:m]
+
+
+def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stream=None, pair_id0=0, records_dev=None, max_iterations=100,
+                transformation_epsilon=0.01, max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0, ndt_step_size=0.1,
+                submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0):
+    """Batched loop-closure verification (GBS:297-322 for a list of pairs).  scans / submaps: lists of (N,4) float32
+    numpy arrays.  Returns a numpy structured view of lgs_align_result records."""
+    L = _lib.load()
+    n = len(scans)
+    assert len(submaps) == n
+    sc = [np.ascontiguousarray(s, np.float32) for s in scans]
+    sm = [np.ascontiguousarray(s, np.float32) for s in submaps]
+    sp = (C.c_void_p * n)(*[s.ctypes.data for s in sc])
+    mp = (C.c_void_p * n)(*[s.ctypes.data for s in sm])
+    ns = (C.c_int64 * n)(*[s.shape[0] for s in sc])
+    nm = (C.c_int64 * n)(*[s.shape[0] for s in sm])
+    g = None
+    if guesses is not None:
+        g = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).reshape(4, 4).ravel(order="F") for T in guesses]))
+    bp = BatchParams(method=method, max_iterations=max_iterations, transformation_epsilon=transformation_epsilon,
+                     max_correspondence_distance=max_correspondence_distance, k_correspondences=k_correspondences,
+                     ndt_resolution=ndt_resolution, ndt_step_size=ndt_step_size, submap_leaf=submap_leaf,
+                     fitness_max_range=fitness_max_range, n_workers=n_workers, reserved=0)
+    recs = (AlignResult * max(n, 1))()
+    check(L.lgs_batch_align(int(device), C.c_void_p(stream) if stream else None, C.byref(bp), n, sp, ns, mp, nm, 16,
+                            g.ctypes.data_as(C.c_void_p) if g is not None else None, int(pair_id0), recs,
+                            C.c_void_p(records_dev) if records_dev else None))
+    return [recs[i] for i in range(n)]

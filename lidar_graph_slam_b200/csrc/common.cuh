@@ -1,0 +1,156 @@
+// Shared plumbing of liblgs_b200.so: error handling, the context (device + stream + arenas), growable
+// device buffers and small device helpers.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lgs_c.h"
+
+namespace lgs {
+
+void set_error(const char* fmt, ...);
+
+#define LGS_CUDA(call)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t _e = (call);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      lgs::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));           \
+      return LGS_ERR_CUDA;                                                                                 \
+    }                                                                                                      \
+  } while (0)
+
+#define LGS_TRY(call)          \
+  do {                         \
+    int _r = (call);           \
+    if (_r != LGS_OK) return _r; \
+  } while (0)
+
+#define LGS_REQUIRE(cond, msg)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      lgs::set_error("%s: %s", __func__, msg); \
+      return LGS_ERR_INVALID;                  \
+    }                                          \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// Growable device allocation; never shrinks, so steady-state calls do not touch cudaMalloc.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return LGS_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      p = nullptr;
+      return LGS_ERR_CUDA;
+    }
+    cap = want;
+    return LGS_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// Pinned host staging (results, small parameter blocks).
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return LGS_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes + 256, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return LGS_ERR_CUDA;
+    }
+    cap = bytes + 256;
+    return LGS_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+}  // namespace lgs
+
+struct lgs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  lgs::DevBuf raw;       // AoS upload staging
+  lgs::DevBuf tmp[8];    // general scratch arenas (per-call meaning)
+  lgs::DevBuf cub_tmp;   // CUB temp storage
+  lgs::PinnedBuf pin;    // small D2H results
+  lgs::PinnedBuf pin_up; // small H2D parameter blocks
+  lgs::DevBuf vg_in, vg_out, vg_vidx, vg_rank;  // host-facing voxel-grid call: staged cloud + device-side outputs
+};
+
+namespace lgs {
+
+inline int use_device(const lgs_ctx* c) {
+  LGS_CUDA(cudaSetDevice(c->device));
+  return LGS_OK;
+}
+
+// Upload a host cloud with arbitrary record stride into packed float4 xyzi device storage.
+int upload_cloud(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, DevBuf* dst);
+// Copy an already packed device cloud into dst (device to device).
+int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst);
+
+inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+#ifdef __CUDACC__
+// order-preserving float <-> uint encoding for atomic min/max
+__device__ __forceinline__ unsigned enc_f(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_f_host(unsigned u) {
+  unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+
+// pcl::transformPointCloud order (PCL >= 1.10): c0*x + (c1*y + (c2*z + c3)), explicit rn ops so the
+// compiler can neither contract nor reassociate.  T column-major.
+__device__ __forceinline__ float3 transform_pcl(const float* __restrict__ T, float x, float y, float z) {
+  float3 r;
+  r.x = __fadd_rn(__fmul_rn(T[0], x), __fadd_rn(__fmul_rn(T[4], y), __fadd_rn(__fmul_rn(T[8], z), T[12])));
+  r.y = __fadd_rn(__fmul_rn(T[1], x), __fadd_rn(__fmul_rn(T[5], y), __fadd_rn(__fmul_rn(T[9], z), T[13])));
+  r.z = __fadd_rn(__fmul_rn(T[2], x), __fadd_rn(__fmul_rn(T[6], y), __fadd_rn(__fmul_rn(T[10], z), T[14])));
+  return r;
+}
+#endif
+
+}  // namespace lgs

@@ -1,0 +1,122 @@
+// Context, error reporting and cloud upload (host AoS records -> packed float4 xyzi in HBM).
+#include "common.cuh"
+
+namespace lgs {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+// One thread per point: gather x,y,z (+ intensity) from the strided record.  Reads are 4-byte but
+// consecutive lanes touch consecutive records, so every 32 B sector fetched is used for 32 B-stride
+// PointXYZI up to its padding; the store is a coalesced float4.
+__global__ void repack_kernel(const unsigned char* __restrict__ raw, int64_t n, int stride, int ioff, float4* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float* r = reinterpret_cast<const float*>(raw + i * stride);
+  float4 v;
+  v.x = r[0];
+  v.y = r[1];
+  v.z = r[2];
+  v.w = ioff >= 0 ? *reinterpret_cast<const float*>(raw + i * stride + ioff) : 0.0f;
+  out[i] = v;
+}
+
+int upload_cloud(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride, DevBuf* dst) {
+  LGS_REQUIRE(n >= 0, "negative point count");
+  LGS_REQUIRE(stride >= 12 && stride % 4 == 0, "stride_bytes must be a multiple of 4 and >= 12");
+  LGS_REQUIRE(n == 0 || pts != nullptr, "null cloud");
+  LGS_TRY(dst->reserve(static_cast<size_t>(n > 0 ? n : 1) * 16));
+  if (n == 0) return LGS_OK;
+  if (stride == 16) {
+    LGS_CUDA(cudaMemcpyAsync(dst->p, pts, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    return LGS_OK;
+  }
+  LGS_TRY(ctx->raw.reserve(static_cast<size_t>(n) * stride));
+  LGS_CUDA(cudaMemcpyAsync(ctx->raw.p, pts, static_cast<size_t>(n) * stride, cudaMemcpyHostToDevice, ctx->stream));
+  int ioff = stride >= 20 ? 16 : -1;
+  repack_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->raw.as<unsigned char>(), n, stride, ioff, dst->as<float4>());
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  return LGS_OK;
+}
+
+int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst) {
+  LGS_REQUIRE(n >= 0, "negative point count");
+  LGS_TRY(dst->reserve(static_cast<size_t>(n > 0 ? n : 1) * 16));
+  if (n) LGS_CUDA(cudaMemcpyAsync(dst->p, pts_dev, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+  return LGS_OK;
+}
+
+}  // namespace lgs
+
+extern "C" {
+
+const char* lgs_last_error(void) { return lgs::g_last_error.c_str(); }
+const char* lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }
+
+int lgs_ctx_create(int device, void* cuda_stream, lgs_ctx** out) {
+  if (!out) {
+    lgs::set_error("lgs_ctx_create: null out");
+    return LGS_ERR_INVALID;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    lgs::set_error("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return LGS_ERR_CUDA;
+  }
+  LGS_REQUIRE(device >= 0 && device < count, "device index out of range");
+  LGS_CUDA(cudaSetDevice(device));
+  lgs_ctx* c = new lgs_ctx;
+  c->device = device;
+  if (cuda_stream) {
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      lgs::set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+      delete c;
+      return LGS_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  *out = c;
+  return LGS_OK;
+}
+
+void lgs_ctx_destroy(lgs_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->raw.release();
+  for (auto& b : c->tmp) b.release();
+  c->cub_tmp.release();
+  c->pin.release();
+  c->pin_up.release();
+  c->vg_in.release();
+  c->vg_out.release();
+  c->vg_vidx.release();
+  c->vg_rank.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int lgs_ctx_synchronize(lgs_ctx* c) {
+  LGS_REQUIRE(c, "null ctx");
+  LGS_CUDA(cudaStreamSynchronize(c->stream));
+  return LGS_OK;
+}
+
+int64_t lgs_ctx_launch_count(const lgs_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// State of the GICP registration object (shared between gicp.cu and batch.cu).
+#pragma once
+#include <memory>
+
+#include "math.cuh"
+#include "nn.cuh"
+
+namespace lgs {
+
+// A cloud with everything fast_gicp keeps next to it: the search structure and the per-point covariances.
+// swapSourceAndTarget (FG:50-57) swaps these bundles, which is what makes covariance reuse work.
+struct GicpCloud {
+  DevBuf pts;
+  int64_t n = 0;
+  NNIndex nn;
+  bool nn_ready = false;
+  DevBuf covs;  // n x 9 f64, row-major 3x3 block of the reference's Matrix4d
+  bool covs_ready = false;
+  int covs_k = 0, covs_reg = -1;
+  int ensure_index(lgs_ctx* ctx);
+  int ensure_covariances(lgs_ctx* ctx, int k, int regularization);
+  ~GicpCloud() {
+    pts.release();
+    covs.release();
+    nn.release();
+  }
+};
+
+}  // namespace lgs
+
+struct lgs_gicp {
+  lgs_ctx* ctx = nullptr;
+  // defaults FG:16-20, LSQ:11-19
+  int k = 20;
+  double corr_dist_threshold = 3.4028234663852886e38;
+  int regularization = LGS_REG_PLANE;
+  int max_iterations = 64;
+  double rotation_eps = 2e-3, trans_eps = 5e-4;
+  int lm_max_iterations = 10;
+  double lm_init_lambda_factor = 1e-9, lm_lambda = -1.0;
+  std::shared_ptr<lgs::GicpCloud> source, target;
+  lgs::DevBuf corr, mahal, partials, result, out_cloud;
+  double final_hessian[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+  float final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  int linearize_calls = 0, error_calls = 0;
+};
+
+namespace lgs {
+int gicp_align_impl(lgs_gicp* g, const float* guess16, lgs_align_result* res);
+int gicp_fitness_impl(lgs_gicp* g, double max_range, double* fitness);
+}  // namespace lgs

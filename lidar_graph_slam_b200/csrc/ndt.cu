@@ -1,0 +1,1202 @@
+// NDT scan-to-map registration: pclomp::NormalDistributionsTransform behind the pcl::Registration surface.
+//
+//   set_target   -> VoxelGridCovariance::applyFilter (VGC:48-370): bbox, keys, stable radix sort, then one thread
+//                   per occupied voxel accumulates sum(x), sum(x x^T) in f64 in ascending point index (the
+//                   reference's serial order => bit-identical sums), finishes mean / covariance / eigen
+//                   regularisation / inverse, and publishes a 64-byte lookup record + a cell-table entry.
+//   derivatives  -> computeDerivatives (NDT:179-285) fused with transformPointCloud and getNeighborhoodAtPoint7
+//                   (VGC:373-433): float4 point load, on-the-fly f32 transform, <=27 cell-table probes,
+//                   f32 point terms (NDT:397-439,483-536), f64 accumulation, block reduction of 43 doubles,
+//                   last-block fixed-order final reduction (deterministic).
+//   hessian_f64  -> computeHessian / updateHessian (NDT:539-644) in f64.
+//   align        -> computeTransformation (NDT:80-171) + computeStepLengthMT (NDT:771-931) driven from the host;
+//                   each evaluation is one kernel launch + one 352-byte D2H.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "math.cuh"
+#include "nn.cuh"
+#include "voxel_common.cuh"
+
+namespace lgs {
+
+// 64-byte voxel record read by the derivative kernels (4 x 16-byte loads)
+struct __align__(16) VoxelRec {
+  double mean[3];
+  float icov[9];
+  int n;
+};
+static_assert(sizeof(VoxelRec) == 64, "VoxelRec must be 64 bytes");
+
+struct CellTable {
+  int dense;            // 1: table[lin] = record index or -1 ; 0: open-addressing hash
+  const int* table;     // dense table, or hash values
+  const int* hkeys;     // hash keys (-1 = empty)
+  unsigned hmask;
+  float leaf[3];
+  int min_b[3], max_b[3], mul[3];
+};
+
+__device__ __forceinline__ unsigned hash_u32(unsigned x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ int cell_lookup(const CellTable& ct, int lin) {
+  if (ct.dense) return __ldg(ct.table + lin);
+  unsigned h = hash_u32(static_cast<unsigned>(lin)) & ct.hmask;
+  while (true) {
+    int k = __ldg(ct.hkeys + h);
+    if (k == lin) return __ldg(ct.table + h);
+    if (k == -1) return -1;
+    h = (h + 1) & ct.hmask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// target voxelisation
+
+struct VoxelExport {  // f64 per-voxel data, ascending idx (parity hook + operands of the f64 Hessian path)
+  int* idx;
+  int* nr_points;
+  double* mean;  // 3
+  double* cov;   // 9
+  double* icov;  // 9
+};
+
+__global__ void __launch_bounds__(128) voxel_stats_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ keys,
+                                                         const unsigned* __restrict__ vals, const int* __restrict__ seg_start, int n_seg,
+                                                         int64_t n_pts, int min_pts, double eig_mult, VoxelExport ex, VoxelRec* __restrict__ recs,
+                                                         int* __restrict__ dense_table, int* __restrict__ hkeys, int* __restrict__ hvals,
+                                                         unsigned hmask, int* __restrict__ n_valid) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_seg) return;
+  const int b = seg_start[v];
+  const int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_pts);
+  const int key = static_cast<int>(keys[b]);
+  // pass 1 (VGC:233-237): mean_ += p ; cov_ += p p^T, f64, ascending point index
+  double s0 = 0, s1 = 0, s2 = 0, c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (int j = b; j < e; j++) {
+    float4 p = pts[vals[j]];
+    double x = p.x, y = p.y, z = p.z;
+    s0 += x; s1 += y; s2 += z;
+    c00 += x * x; c01 += x * y; c02 += x * z;
+    c11 += y * y; c12 += y * z; c22 += z * z;
+  }
+  int n = e - b;
+  double cov[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
+  double sum[3] = {s0, s1, s2};
+  double mean[3] = {s0 / n, s1 / n, s2 / n};  // VGC:293
+  double icov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int nr_points = n;
+  if (n >= min_pts) {
+    // VGC:329-330
+    const double dn = n;
+    for (int a = 0; a < 3; a++)
+      for (int c = 0; c < 3; c++) cov[a * 3 + c] = (cov[a * 3 + c] - 2 * (sum[a] * mean[c])) / dn + mean[a] * mean[c];
+    const double f = (n - 1.0) / n;
+    for (int k = 0; k < 9; k++) cov[k] *= f;
+    double ev[3], V[9];
+    m::eig_sym3(cov, ev, V);  // VGC:333-335
+    if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+      nr_points = -1;  // VGC:337-341
+    } else {
+      const double min_ev = eig_mult * ev[2];  // VGC:345-356
+      if (ev[0] < min_ev) {
+        ev[0] = min_ev;
+        if (ev[1] < min_ev) ev[1] = min_ev;
+        double D[9] = {ev[0], 0, 0, 0, ev[1], 0, 0, 0, ev[2]};
+        double Vi[9], VD[9];
+        m::inv3(V, Vi);
+        m::mul3(V, D, VD);
+        m::mul3(VD, Vi, cov);
+      }
+      m::inv3(cov, icov);  // VGC:359-364
+      double mxc = icov[0], mnc = icov[0];
+      for (int k = 1; k < 9; k++) {
+        mxc = fmax(mxc, icov[k]);
+        mnc = fmin(mnc, icov[k]);
+      }
+      const double finf = static_cast<double>(__int_as_float(0x7f800000));
+      if (mxc == finf || mnc == -finf) nr_points = -1;
+    }
+  }
+  ex.idx[v] = key;
+  ex.nr_points[v] = nr_points;
+  for (int a = 0; a < 3; a++) ex.mean[v * 3 + a] = mean[a];
+  for (int k = 0; k < 9; k++) {
+    ex.cov[v * 9 + k] = cov[k];
+    ex.icov[v * 9 + k] = icov[k];
+  }
+  if (nr_points >= min_pts) {  // visible to the lookup (VGC:395)
+    VoxelRec r;
+    for (int a = 0; a < 3; a++) r.mean[a] = mean[a];
+    for (int k = 0; k < 9; k++) r.icov[k] = static_cast<float>(icov[k]);  // c_inv.cast<float>() (NDT:493)
+    r.n = nr_points;
+    recs[v] = r;
+    if (dense_table) {
+      dense_table[key] = v;
+    } else {
+      unsigned h = hash_u32(static_cast<unsigned>(key)) & hmask;
+      while (true) {
+        int prev = atomicCAS(hkeys + h, -1, key);
+        if (prev == -1 || prev == key) {
+          hvals[h] = v;
+          break;
+        }
+        h = (h + 1) & hmask;
+      }
+    }
+    atomicAdd(n_valid, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// derivative evaluation
+
+struct EvalParams {
+  float T[16];          // column-major transform applied to the source points
+  float j_ang[8][3];    // NDT:339-346 (rows a..h), f32
+  float h_ang[15][3];   // NDT:373-392 (rows a2..f3), f32
+  double j_ang_d[8][3]; // f64 copies for computeHessian (NDT:329-336, 351-370)
+  double h_ang_d[15][3];
+  double gauss_d1, gauss_d2;
+  float gauss_d2f;
+  int n_offsets;
+  signed char off[27][3];
+};
+
+constexpr int kEvalBlock = 128;
+constexpr int kNumAcc = 44;  // score, g[6], H[36], pad
+
+// block-wide sum of K doubles held per thread -> partials[blockIdx][k]; the last block to finish adds the
+// per-block partials in block order (fixed tree => run-to-run reproducible) and writes result[k].
+template <int K>
+__device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double* __restrict__ partials, double* __restrict__ result,
+                                                       unsigned* __restrict__ counter) {
+  __shared__ double sm[kEvalBlock / 32][K];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < kEvalBlock / 32; w++) v += sm[w][threadIdx.x];
+    partials[static_cast<size_t>(blockIdx.x) * K + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < K) {
+      double v = 0;
+      for (unsigned b = 0; b < gridDim.x; b++) v += partials[static_cast<size_t>(b) * K + threadIdx.x];
+      result[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0;  // re-arm for the next launch on this stream
+  }
+}
+
+// f32 per-point tables (NDT:397-439): the 8 non-trivial point_gradient_ entries and vectors a..f
+struct PointTables {
+  float J13, J23, J04, J14, J24, J05, J15, J25;
+  float a1, a2, b1, b2, c1, c2;  // a,b,c = (0, ., .)
+  float d0, d1, d2, e0, e1, e2, f0, f1, f2;
+};
+
+template <bool HESS>
+__device__ __forceinline__ void point_tables(const EvalParams& P, float x, float y, float z, PointTables& t) {
+  // rows of (j_ang * x4) with x4 = (x,y,z,0): ((r0*x + r1*y) + r2*z) + 0
+#define LGS_ROW(M, r) __fadd_rn(__fadd_rn(__fmul_rn(M[r][0], x), __fmul_rn(M[r][1], y)), __fmul_rn(M[r][2], z))
+  t.J13 = LGS_ROW(P.j_ang, 0);
+  t.J23 = LGS_ROW(P.j_ang, 1);
+  t.J04 = LGS_ROW(P.j_ang, 2);
+  t.J14 = LGS_ROW(P.j_ang, 3);
+  t.J24 = LGS_ROW(P.j_ang, 4);
+  t.J05 = LGS_ROW(P.j_ang, 5);
+  t.J15 = LGS_ROW(P.j_ang, 6);
+  t.J25 = LGS_ROW(P.j_ang, 7);
+  if (HESS) {
+    t.a1 = LGS_ROW(P.h_ang, 0);  t.a2 = LGS_ROW(P.h_ang, 1);
+    t.b1 = LGS_ROW(P.h_ang, 2);  t.b2 = LGS_ROW(P.h_ang, 3);
+    t.c1 = LGS_ROW(P.h_ang, 4);  t.c2 = LGS_ROW(P.h_ang, 5);
+    t.d0 = LGS_ROW(P.h_ang, 6);  t.d1 = LGS_ROW(P.h_ang, 7);  t.d2 = LGS_ROW(P.h_ang, 8);
+    t.e0 = LGS_ROW(P.h_ang, 9);  t.e1 = LGS_ROW(P.h_ang, 10); t.e2 = LGS_ROW(P.h_ang, 11);
+    t.f0 = LGS_ROW(P.h_ang, 12); t.f1 = LGS_ROW(P.h_ang, 13); t.f2 = LGS_ROW(P.h_ang, 14);
+  }
+#undef LGS_ROW
+}
+
+// updateDerivatives (NDT:483-536) for one (point, cell) pair.  Products of the reference's padded 4x4 / 4x6
+// f32 matrices are written out with their structural zeros and ones removed; every surviving operation is
+// kept in the reference's order, so each f32 term is bit-identical to the full-matrix evaluation.
+template <bool HESS>
+__device__ __forceinline__ void accumulate_cell(const EvalParams& P, const PointTables& t, const VoxelRec& r, float xt, float yt, float zt,
+                                                double* __restrict__ acc) {
+  // x_trans = Vector3d(x_trans_pt) - mean  (f64), then cast to f32 (NDT:259-262,491)
+  const float x0 = static_cast<float>(static_cast<double>(xt) - r.mean[0]);
+  const float x1 = static_cast<float>(static_cast<double>(yt) - r.mean[1]);
+  const float x2 = static_cast<float>(static_cast<double>(zt) - r.mean[2]);
+  const float* C = r.icov;
+  // xC = x_trans4 * c_inv4
+  const float xC0 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[0]), __fmul_rn(x1, C[3])), __fmul_rn(x2, C[6]));
+  const float xC1 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[1]), __fmul_rn(x1, C[4])), __fmul_rn(x2, C[7]));
+  const float xC2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[2]), __fmul_rn(x1, C[5])), __fmul_rn(x2, C[8]));
+  const float q = __fadd_rn(__fadd_rn(__fmul_rn(x0, xC0), __fmul_rn(x1, xC1)), __fmul_rn(x2, xC2));
+  // exp of an f32 argument, evaluated in f64 and rounded (NDT:498)
+  float e = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(-P.gauss_d2f, q), 0.5f))));
+  const float score_inc = static_cast<float>(-P.gauss_d1 * static_cast<double>(e));
+  e = __fmul_rn(P.gauss_d2f, e);
+  if (e > 1.0f || e < 0.0f || e != e) return;  // NDT:505-506
+  e = static_cast<float>(static_cast<double>(e) * P.gauss_d1);
+  acc[0] += static_cast<double>(score_inc);
+
+  // CJ = c_inv4 * point_gradient4, columns 3..5 (columns 0..2 are the columns of C)
+  float CJ3[3], CJ4[3], CJ5[3];
+#pragma unroll
+  for (int rr = 0; rr < 3; rr++) {
+    CJ3[rr] = __fadd_rn(__fmul_rn(C[rr * 3 + 1], t.J13), __fmul_rn(C[rr * 3 + 2], t.J23));
+    CJ4[rr] = __fadd_rn(__fadd_rn(__fmul_rn(C[rr * 3 + 0], t.J04), __fmul_rn(C[rr * 3 + 1], t.J14)), __fmul_rn(C[rr * 3 + 2], t.J24));
+    CJ5[rr] = __fadd_rn(__fadd_rn(__fmul_rn(C[rr * 3 + 0], t.J05), __fmul_rn(C[rr * 3 + 1], t.J15)), __fmul_rn(C[rr * 3 + 2], t.J25));
+  }
+  float g[6];
+  g[0] = xC0;
+  g[1] = xC1;
+  g[2] = xC2;
+  g[3] = __fadd_rn(__fadd_rn(__fmul_rn(x0, CJ3[0]), __fmul_rn(x1, CJ3[1])), __fmul_rn(x2, CJ3[2]));
+  g[4] = __fadd_rn(__fadd_rn(__fmul_rn(x0, CJ4[0]), __fmul_rn(x1, CJ4[1])), __fmul_rn(x2, CJ4[2]));
+  g[5] = __fadd_rn(__fadd_rn(__fmul_rn(x0, CJ5[0]), __fmul_rn(x1, CJ5[1])), __fmul_rn(x2, CJ5[2]));
+#pragma unroll
+  for (int c = 0; c < 6; c++) acc[1 + c] += static_cast<double>(__fmul_rn(e, g[c]));
+
+  if (HESS) {
+    // CJ as a 3x6: CJm[r][c]
+    float CJm[3][6];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+      CJm[rr][0] = C[rr * 3 + 0];
+      CJm[rr][1] = C[rr * 3 + 1];
+      CJm[rr][2] = C[rr * 3 + 2];
+      CJm[rr][3] = CJ3[rr];
+      CJm[rr][4] = CJ4[rr];
+      CJm[rr][5] = CJ5[rr];
+    }
+    // xCH[i][j] = x_trans4_x_c_inv4 * point_hessian_ block (i,j), i,j in 3..5
+    const float xa = __fadd_rn(__fmul_rn(xC1, t.a1), __fmul_rn(xC2, t.a2));
+    const float xb = __fadd_rn(__fmul_rn(xC1, t.b1), __fmul_rn(xC2, t.b2));
+    const float xc = __fadd_rn(__fmul_rn(xC1, t.c1), __fmul_rn(xC2, t.c2));
+    const float xd = __fadd_rn(__fadd_rn(__fmul_rn(xC0, t.d0), __fmul_rn(xC1, t.d1)), __fmul_rn(xC2, t.d2));
+    const float xe = __fadd_rn(__fadd_rn(__fmul_rn(xC0, t.e0), __fmul_rn(xC1, t.e1)), __fmul_rn(xC2, t.e2));
+    const float xf = __fadd_rn(__fadd_rn(__fmul_rn(xC0, t.f0), __fmul_rn(xC1, t.f1)), __fmul_rn(xC2, t.f2));
+    const float xCH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
+    const float nd2 = -P.gauss_d2f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const float ngi = __fmul_rn(nd2, g[i]);
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        // JCJ(j,i) = point_gradient4.col(j) . CJ.col(i)
+        float jcj;
+        if (j < 3) {
+          jcj = CJm[j][i];
+        } else if (j == 3) {
+          jcj = __fadd_rn(__fmul_rn(t.J13, CJm[1][i]), __fmul_rn(t.J23, CJm[2][i]));
+        } else if (j == 4) {
+          jcj = __fadd_rn(__fadd_rn(__fmul_rn(t.J04, CJm[0][i]), __fmul_rn(t.J14, CJm[1][i])), __fmul_rn(t.J24, CJm[2][i]));
+        } else {
+          jcj = __fadd_rn(__fadd_rn(__fmul_rn(t.J05, CJm[0][i]), __fmul_rn(t.J15, CJm[1][i])), __fmul_rn(t.J25, CJm[2][i]));
+        }
+        float inner = __fmul_rn(ngi, g[j]);
+        if (i >= 3 && j >= 3) inner = __fadd_rn(inner, xCH[i - 3][j - 3]);
+        inner = __fadd_rn(inner, jcj);
+        acc[7 + i * 6 + j] += static_cast<double>(__fmul_rn(e, inner));
+      }
+    }
+  }
+}
+
+template <bool HESS>
+__global__ void __launch_bounds__(kEvalBlock) ndt_derivatives_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
+                                                                   const VoxelRec* __restrict__ recs, double* __restrict__ partials,
+                                                                   double* __restrict__ result, unsigned* __restrict__ counter) {
+  constexpr int K = HESS ? 43 : 7;
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = 0.0;
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = src[i];
+    const float3 xt = transform_pcl(P.T, p.x, p.y, p.z);
+    // getNeighborhoodAtPoint (VGC:379-381): ijk = floor(x / leaf) with an IEEE f32 division
+    const int ix = static_cast<int>(floorf(__fdiv_rn(xt.x, ct.leaf[0])));
+    const int iy = static_cast<int>(floorf(__fdiv_rn(xt.y, ct.leaf[1])));
+    const int iz = static_cast<int>(floorf(__fdiv_rn(xt.z, ct.leaf[2])));
+    PointTables t;
+    bool have_tables = false;
+    for (int o = 0; o < P.n_offsets; o++) {
+      const int cx = ix + P.off[o][0], cy = iy + P.off[o][1], cz = iz + P.off[o][2];
+      if (cx < ct.min_b[0] || cx > ct.max_b[0] || cy < ct.min_b[1] || cy > ct.max_b[1] || cz < ct.min_b[2] || cz > ct.max_b[2]) continue;
+      const int lin = (cx - ct.min_b[0]) * ct.mul[0] + (cy - ct.min_b[1]) * ct.mul[1] + (cz - ct.min_b[2]) * ct.mul[2];
+      const int slot = cell_lookup(ct, lin);
+      if (slot < 0) continue;
+      if (!have_tables) {
+        point_tables<HESS>(P, p.x, p.y, p.z, t);
+        have_tables = true;
+      }
+      VoxelRec r;
+      const uint4* rp = reinterpret_cast<const uint4*>(recs + slot);
+      uint4* rw = reinterpret_cast<uint4*>(&r);
+      rw[0] = __ldg(rp + 0);
+      rw[1] = __ldg(rp + 1);
+      rw[2] = __ldg(rp + 2);
+      rw[3] = __ldg(rp + 3);
+      accumulate_cell<HESS>(P, t, r, xt.x, xt.y, xt.z, acc);
+    }
+  }
+  block_reduce_and_finish<K>(acc, partials, result, counter);
+}
+
+// computeHessian / updateHessian (NDT:539-644) with the f64 point derivatives (NDT:443-480)
+__global__ void __launch_bounds__(kEvalBlock) ndt_hessian_f64_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
+                                                                   const double* __restrict__ vmean, const double* __restrict__ vicov,
+                                                                   double* __restrict__ partials, double* __restrict__ result,
+                                                                   unsigned* __restrict__ counter) {
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.0;
+  auto s3 = [](double a, double b, double c) { return a + (b + c); };  // Eigen's unrolled 3-element reduction order
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = src[i];
+    const float3 xt = transform_pcl(P.T, p.x, p.y, p.z);
+    const int ix = static_cast<int>(floorf(__fdiv_rn(xt.x, ct.leaf[0])));
+    const int iy = static_cast<int>(floorf(__fdiv_rn(xt.y, ct.leaf[1])));
+    const int iz = static_cast<int>(floorf(__fdiv_rn(xt.z, ct.leaf[2])));
+    const double x[3] = {p.x, p.y, p.z};
+    double J[3][6];
+    double vec[6][3];
+    bool have = false;
+    for (int o = 0; o < P.n_offsets; o++) {
+      const int cx = ix + P.off[o][0], cy = iy + P.off[o][1], cz = iz + P.off[o][2];
+      if (cx < ct.min_b[0] || cx > ct.max_b[0] || cy < ct.min_b[1] || cy > ct.max_b[1] || cz < ct.min_b[2] || cz > ct.max_b[2]) continue;
+      const int lin = (cx - ct.min_b[0]) * ct.mul[0] + (cy - ct.min_b[1]) * ct.mul[1] + (cz - ct.min_b[2]) * ct.mul[2];
+      const int slot = cell_lookup(ct, lin);
+      if (slot < 0) continue;
+      if (!have) {
+        have = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) J[a][c] = (a == c) ? 1.0 : 0.0;
+#define LGS_DJ(r) s3(x[0] * P.j_ang_d[r][0], x[1] * P.j_ang_d[r][1], x[2] * P.j_ang_d[r][2])
+#define LGS_DH(r) s3(x[0] * P.h_ang_d[r][0], x[1] * P.h_ang_d[r][1], x[2] * P.h_ang_d[r][2])
+        J[1][3] = LGS_DJ(0); J[2][3] = LGS_DJ(1);
+        J[0][4] = LGS_DJ(2); J[1][4] = LGS_DJ(3); J[2][4] = LGS_DJ(4);
+        J[0][5] = LGS_DJ(5); J[1][5] = LGS_DJ(6); J[2][5] = LGS_DJ(7);
+        vec[0][0] = 0; vec[0][1] = LGS_DH(0); vec[0][2] = LGS_DH(1);
+        vec[1][0] = 0; vec[1][1] = LGS_DH(2); vec[1][2] = LGS_DH(3);
+        vec[2][0] = 0; vec[2][1] = LGS_DH(4); vec[2][2] = LGS_DH(5);
+        vec[3][0] = LGS_DH(6); vec[3][1] = LGS_DH(7); vec[3][2] = LGS_DH(8);
+        vec[4][0] = LGS_DH(9); vec[4][1] = LGS_DH(10); vec[4][2] = LGS_DH(11);
+        vec[5][0] = LGS_DH(12); vec[5][1] = LGS_DH(13); vec[5][2] = LGS_DH(14);
+#undef LGS_DJ
+#undef LGS_DH
+      }
+      const double* mean = vmean + static_cast<size_t>(slot) * 3;
+      const double* C = vicov + static_cast<size_t>(slot) * 9;
+      const double xx[3] = {static_cast<double>(xt.x) - mean[0], static_cast<double>(xt.y) - mean[1], static_cast<double>(xt.z) - mean[2]};
+      double Cx[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) Cx[r] = s3(C[r * 3] * xx[0], C[r * 3 + 1] * xx[1], C[r * 3 + 2] * xx[2]);
+      double e = P.gauss_d2 * exp(-P.gauss_d2 * s3(xx[0] * Cx[0], xx[1] * Cx[1], xx[2] * Cx[2]) / 2);
+      if (e > 1 || e < 0 || e != e) continue;
+      e *= P.gauss_d1;
+      double CJ[6][3], xCJ[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) CJ[c][r] = s3(C[r * 3] * J[0][c], C[r * 3 + 1] * J[1][c], C[r * 3 + 2] * J[2][c]);
+        xCJ[c] = s3(xx[0] * CJ[c][0], xx[1] * CJ[c][1], xx[2] * CJ[c][2]);
+      }
+      const int blk[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+      for (int ii = 0; ii < 6; ii++) {
+#pragma unroll
+        for (int jj = 0; jj < 6; jj++) {
+          double hv[3] = {0, 0, 0};
+          if (ii >= 3 && jj >= 3) {
+            const double* vv = vec[blk[ii - 3][jj - 3]];
+            hv[0] = vv[0]; hv[1] = vv[1]; hv[2] = vv[2];
+          }
+          double Ch[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) Ch[r] = s3(C[r * 3] * hv[0], C[r * 3 + 1] * hv[1], C[r * 3 + 2] * hv[2]);
+          const double xCH = s3(xx[0] * Ch[0], xx[1] * Ch[1], xx[2] * Ch[2]);
+          const double jcj = s3(J[0][jj] * CJ[ii][0], J[1][jj] * CJ[ii][1], J[2][jj] * CJ[ii][2]);
+          acc[ii * 6 + jj] += e * (-P.gauss_d2 * xCJ[ii] * xCJ[jj] + xCH + jcj);
+        }
+      }
+    }
+  }
+  block_reduce_and_finish<36>(acc, partials, result, counter);
+}
+
+// calculateScore (NDT:934-982)
+__global__ void __launch_bounds__(kEvalBlock) ndt_score_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
+                                                             const double* __restrict__ vmean, const double* __restrict__ vicov, double gauss_d3,
+                                                             double* __restrict__ partials, double* __restrict__ result, unsigned* __restrict__ counter) {
+  double acc[1] = {0.0};
+  auto s3 = [](double a, double b, double c) { return a + (b + c); };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = src[i];
+    const float3 xt = transform_pcl(P.T, p.x, p.y, p.z);
+    const int ix = static_cast<int>(floorf(__fdiv_rn(xt.x, ct.leaf[0])));
+    const int iy = static_cast<int>(floorf(__fdiv_rn(xt.y, ct.leaf[1])));
+    const int iz = static_cast<int>(floorf(__fdiv_rn(xt.z, ct.leaf[2])));
+    int slots[27];
+    int cnt = 0;
+    for (int o = 0; o < P.n_offsets; o++) {
+      const int cx = ix + P.off[o][0], cy = iy + P.off[o][1], cz = iz + P.off[o][2];
+      if (cx < ct.min_b[0] || cx > ct.max_b[0] || cy < ct.min_b[1] || cy > ct.max_b[1] || cz < ct.min_b[2] || cz > ct.max_b[2]) continue;
+      const int lin = (cx - ct.min_b[0]) * ct.mul[0] + (cy - ct.min_b[1]) * ct.mul[1] + (cz - ct.min_b[2]) * ct.mul[2];
+      const int slot = cell_lookup(ct, lin);
+      if (slot >= 0) slots[cnt++] = slot;
+    }
+    for (int k = 0; k < cnt; k++) {
+      const double* mean = vmean + static_cast<size_t>(slots[k]) * 3;
+      const double* C = vicov + static_cast<size_t>(slots[k]) * 9;
+      const double xx[3] = {static_cast<double>(xt.x) - mean[0], static_cast<double>(xt.y) - mean[1], static_cast<double>(xt.z) - mean[2]};
+      double Cx[3];
+      for (int r = 0; r < 3; r++) Cx[r] = s3(C[r * 3] * xx[0], C[r * 3 + 1] * xx[1], C[r * 3 + 2] * xx[2]);
+      double e = exp(-P.gauss_d2 * s3(xx[0] * Cx[0], xx[1] * Cx[1], xx[2] * Cx[2]) / 2);
+      double score_inc = -P.gauss_d1 * e - gauss_d3;
+      acc[0] += score_inc / cnt;
+    }
+  }
+  block_reduce_and_finish<1>(acc, partials, result, counter);
+}
+
+__global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __restrict__ src, int64_t n, EvalParams P, float4* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float4 p = src[i];
+  float3 t = transform_pcl(P.T, p.x, p.y, p.z);
+  out[i] = make_float4(t.x, t.y, t.z, p.w);
+}
+
+}  // namespace lgs
+
+// =============================================================================================
+// host side
+
+using namespace lgs;
+
+struct lgs_ndt {
+  lgs_ctx* ctx = nullptr;
+  // parameters, defaults NDT:49-51,71-75
+  float resolution = 1.0f;
+  double step_size = 0.1, outlier_ratio = 0.55, trans_eps = 0.1;
+  int max_iter = 35;
+  int search = LGS_NDT_DIRECT7;
+  // clouds
+  DevBuf target, source, out_cloud;
+  int64_t n_target = 0, n_source = 0;
+  bool have_target = false, have_source = false;
+  // voxel structure
+  bool grid_ready = false, refused = false;
+  int dense = 1;
+  int64_t n_voxels = 0, n_valid = 0;
+  int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
+  DevBuf table, hkeys, recs, ex_idx, ex_n, ex_mean, ex_cov, ex_icov, small;
+  unsigned hmask = 0;
+  // reduction scratch
+  DevBuf partials, result;
+  // nearest-neighbour structure over the target for getFitnessScore (lazy)
+  NNIndex nn;
+  bool nn_ready = false;
+  // state of the last align
+  float final_T[16];
+  double gauss_d1 = 0, gauss_d2 = 0, gauss_d3 = 0;
+  EvalParams P;
+  int evals = 0, trials = 0, hess_recomputes = 0;
+};
+
+namespace {
+
+constexpr uint64_t kDenseCellLimit = uint64_t(1) << 26;  // 64 Mi cells (256 MiB of int32) before switching to the hash
+
+void identity16(float* T) {
+  for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+}
+
+// Eigen::AngleAxis<float>(angle, Unit{X,Y,Z}).toRotationMatrix(): note (1-c)*1 + c on the axis diagonal
+void angle_axis_unit(float angle, int axis, float* R) {
+  float ax[3] = {0, 0, 0};
+  ax[axis] = 1.0f;
+  const float s = std::sin(angle), c = std::cos(angle);
+  const float sa[3] = {s * ax[0], s * ax[1], s * ax[2]};
+  const float ca[3] = {(1.0f - c) * ax[0], (1.0f - c) * ax[1], (1.0f - c) * ax[2]};
+  float tmp = ca[0] * ax[1];
+  R[1] = tmp - sa[2];
+  R[3] = tmp + sa[2];
+  tmp = ca[0] * ax[2];
+  R[2] = tmp + sa[1];
+  R[6] = tmp - sa[1];
+  tmp = ca[1] * ax[2];
+  R[5] = tmp - sa[0];
+  R[7] = tmp + sa[0];
+  for (int a = 0; a < 3; a++) R[a * 4] = ca[a] * ax[a] + c;
+}
+
+void mul3f(const float* a, const float* b, float* c) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c[i * 3 + j] = (a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j];
+}
+
+// NDT.h:214-231: Translation * AngleAxis(X) * AngleAxis(Y) * AngleAxis(Z) in f32, column-major out
+void pose_to_matrix(const double x[6], float* T) {
+  float Rx[9], Ry[9], Rz[9], Rxy[9], R[9];
+  angle_axis_unit(static_cast<float>(x[3]), 0, Rx);
+  angle_axis_unit(static_cast<float>(x[4]), 1, Ry);
+  angle_axis_unit(static_cast<float>(x[5]), 2, Rz);
+  mul3f(Rx, Ry, Rxy);
+  mul3f(Rxy, Rz, R);
+  identity16(T);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) T[c * 4 + r] = R[r * 3 + c];
+  T[12] = static_cast<float>(x[0]);
+  T[13] = static_cast<float>(x[1]);
+  T[14] = static_cast<float>(x[2]);
+}
+
+// p = [translation, eulerAngles(0,1,2)] of an Affine3f (NDT:103-111): rotation() is the polar factor
+// U V^T of the linear part (f32 Jacobi SVD), then Eigen's eulerAngles branch convention.
+void matrix_to_pose(const float* T, double p[6]) {
+  float L[9], U[9], S[3], V[9], UVt[9], R[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) L[r * 3 + c] = T[c * 4 + r];
+  m::svd_jacobi<3, float>(L, U, S, V);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) UVt[i * 3 + j] = (U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1]) + U[i * 3 + 2] * V[j * 3 + 2];
+  float det = UVt[0] * (UVt[4] * UVt[8] - UVt[5] * UVt[7]) - UVt[1] * (UVt[3] * UVt[8] - UVt[5] * UVt[6]) +
+              UVt[2] * (UVt[3] * UVt[7] - UVt[4] * UVt[6]);
+  float sgn = det < 0.0f ? -1.0f : 1.0f;
+  for (int r = 0; r < 3; r++) U[r * 3 + 2] *= sgn;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i * 3 + j] = (U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1]) + U[i * 3 + 2] * V[j * 3 + 2];
+  const float pi = static_cast<float>(M_PI);
+  float r0 = std::atan2(R[1 * 3 + 2], R[2 * 3 + 2]);
+  float c2 = std::sqrt(R[0] * R[0] + R[1] * R[1]);
+  float r1;
+  if (r0 > 0.0f) {
+    r0 -= pi;
+    r1 = std::atan2(-R[2], -c2);
+  } else {
+    r1 = std::atan2(-R[2], c2);
+  }
+  float s1 = std::sin(r0), c1 = std::cos(r0);
+  float r2 = std::atan2(s1 * R[2 * 3 + 0] - c1 * R[1 * 3 + 0], c1 * R[1 * 3 + 1] - s1 * R[2 * 3 + 1]);
+  p[0] = T[12];
+  p[1] = T[13];
+  p[2] = T[14];
+  p[3] = -r0;
+  p[4] = -r1;
+  p[5] = -r2;
+}
+
+void compute_gauss(lgs_ndt* n) {  // NDT:86-93
+  double c1 = 10 * (1 - n->outlier_ratio);
+  double c2 = n->outlier_ratio / std::pow(static_cast<double>(n->resolution), 3);
+  n->gauss_d3 = -std::log(c2);
+  n->gauss_d1 = -std::log(c1 + c2) - n->gauss_d3;
+  n->gauss_d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - n->gauss_d3) / n->gauss_d1);
+}
+
+// computeAngleDerivatives (NDT:288-394)
+void angle_derivatives(const double p[6], EvalParams* P) {
+  double cx, cy, cz, sx, sy, sz;
+  if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
+  if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
+  if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
+  const double J[8][3] = {{(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
+                          {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
+                          {(-sy * cz), sy * sz, cy},
+                          {sx * cy * cz, (-sx * cy * sz), sx * sy},
+                          {(-cx * cy * cz), cx * cy * sz, (-cx * sy)},
+                          {(-cy * sz), (-cy * cz), 0},
+                          {(cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0},
+                          {(sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0}};
+  const double H[15][3] = {{(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy},
+                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy)},
+                           {(cx * cy * cz), (-cx * cy * sz), (cx * sy)},
+                           {(sx * cy * cz), (-sx * cy * sz), (sx * sy)},
+                           {(-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0},
+                           {(cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0},
+                           {(-cy * cz), (cy * sz), (sy)},
+                           {(-sx * sy * cz), (sx * sy * sz), (sx * cy)},
+                           {(cx * sy * cz), (-cx * sy * sz), (-cx * cy)},
+                           {(sy * sz), (sy * cz), 0},
+                           {(-sx * cy * sz), (-sx * cy * cz), 0},
+                           {(cx * cy * sz), (cx * cy * cz), 0},
+                           {(-cy * cz), (cy * sz), 0},
+                           {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},
+                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 3; c++) {
+      P->j_ang_d[r][c] = J[r][c];
+      P->j_ang[r][c] = static_cast<float>(J[r][c]);
+    }
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 3; c++) {
+      P->h_ang_d[r][c] = H[r][c];
+      P->h_ang[r][c] = static_cast<float>(H[r][c]);
+    }
+}
+
+void fill_offsets(int method, EvalParams* P) {
+  static const signed char off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};  // VGC:423-430
+  if (method == LGS_NDT_DIRECT1) {
+    P->n_offsets = 1;
+    P->off[0][0] = P->off[0][1] = P->off[0][2] = 0;
+  } else if (method == LGS_NDT_DIRECT26) {
+    // pcl::getAllNeighborCellIndices: 13 half offsets then their negations (no centre cell)
+    int c = 0;
+    signed char half[13][3];
+    for (int i = -1; i < 2; i++)
+      for (int j = -1; j < 2; j++) {
+        half[c][0] = i; half[c][1] = j; half[c][2] = -1; c++;
+      }
+    for (int i = -1; i < 2; i++) {
+      half[c][0] = i; half[c][1] = -1; half[c][2] = 0; c++;
+    }
+    half[c][0] = -1; half[c][1] = 0; half[c][2] = 0;
+    for (int t = 0; t < 13; t++)
+      for (int a = 0; a < 3; a++) {
+        P->off[t][a] = half[t][a];
+        P->off[13 + t][a] = -half[t][a];
+      }
+    P->n_offsets = 26;
+  } else {
+    P->n_offsets = 7;
+    for (int t = 0; t < 7; t++)
+      for (int a = 0; a < 3; a++) P->off[t][a] = off7[t][a];
+  }
+}
+
+CellTable make_cell_table(const lgs_ndt* n) {
+  CellTable ct;
+  ct.dense = n->dense;
+  ct.table = n->table.as<int>();
+  ct.hkeys = n->hkeys.as<int>();
+  ct.hmask = n->hmask;
+  for (int a = 0; a < 3; a++) {
+    ct.leaf[a] = n->resolution;
+    ct.min_b[a] = n->min_b[a];
+    ct.max_b[a] = n->max_b[a];
+  }
+  ct.mul[0] = 1;
+  ct.mul[1] = n->div_b[0];
+  ct.mul[2] = n->div_b[0] * n->div_b[1];
+  return ct;
+}
+
+int eval_grid(int64_t n) { return std::max(1, std::min(grid_for(n, kEvalBlock), kNumSMs * 4)); }
+
+// init() (NDT.h:276-283): (re)voxelise the target at the current resolution
+int build_grid(lgs_ndt* n) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  n->grid_ready = false;
+  n->refused = false;
+  n->n_voxels = n->n_valid = 0;
+  if (!n->have_target) return LGS_OK;
+  const float leaf[3] = {n->resolution, n->resolution, n->resolution};
+  SortedVoxels sv;
+  LGS_TRY(build_sorted_voxels(ctx, n->target.as<float4>(), n->n_target, leaf, -1.0, nullptr, nullptr, nullptr, &sv));
+  if (n->n_target == 0 || sv.status == LGS_VG_REFUSED_OVERFLOW) {  // VGC:79-84: grid cleared, every lookup misses
+    n->refused = true;
+    n->grid_ready = true;
+    return LGS_OK;
+  }
+  for (int a = 0; a < 3; a++) {
+    n->min_b[a] = sv.min_b[a];
+    n->max_b[a] = sv.max_b[a];
+    n->div_b[a] = sv.div_b[a];
+  }
+  const int V = sv.n_seg;
+  n->n_voxels = V;
+  n->dense = sv.total_cells <= kDenseCellLimit ? 1 : 0;
+  LGS_TRY(n->recs.reserve(static_cast<size_t>(V) * sizeof(VoxelRec)));
+  LGS_TRY(n->ex_idx.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(n->ex_n.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(n->ex_mean.reserve(static_cast<size_t>(V) * 24));
+  LGS_TRY(n->ex_cov.reserve(static_cast<size_t>(V) * 72));
+  LGS_TRY(n->ex_icov.reserve(static_cast<size_t>(V) * 72));
+  LGS_TRY(n->small.reserve(64));
+  LGS_CUDA(cudaMemsetAsync(n->small.p, 0, 64, st));
+  if (n->dense) {
+    LGS_TRY(n->table.reserve(sv.total_cells * 4));
+    LGS_CUDA(cudaMemsetAsync(n->table.p, 0xFF, sv.total_cells * 4, st));
+    n->hmask = 0;
+  } else {
+    uint64_t cap = 1024;
+    while (cap < static_cast<uint64_t>(V) * 2) cap <<= 1;
+    n->hmask = static_cast<unsigned>(cap - 1);
+    LGS_TRY(n->table.reserve(cap * 4));
+    LGS_TRY(n->hkeys.reserve(cap * 4));
+    LGS_CUDA(cudaMemsetAsync(n->hkeys.p, 0xFF, cap * 4, st));
+  }
+  VoxelExport ex{n->ex_idx.as<int>(), n->ex_n.as<int>(), n->ex_mean.as<double>(), n->ex_cov.as<double>(), n->ex_icov.as<double>()};
+  voxel_stats_kernel<<<grid_for(V, 128), 128, 0, st>>>(n->target.as<float4>(), sv.keys, sv.vals, sv.seg_start, V, sv.n_kept, 6, 0.01, ex,
+                                                      n->recs.as<VoxelRec>(), n->dense ? n->table.as<int>() : nullptr, n->hkeys.as<int>(),
+                                                      n->table.as<int>(), n->hmask, n->small.as<int>());
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  LGS_TRY(ctx->pin.reserve(256));
+  int* h = ctx->pin.as<int>();
+  LGS_CUDA(cudaMemcpyAsync(h, n->small.p, 4, cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  n->n_valid = h[0];
+  n->grid_ready = true;
+  return LGS_OK;
+}
+
+// one computeDerivatives / computeHessian evaluation.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian
+int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* score, double* g, double* H) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  EvalParams& P = n->P;
+  memcpy(P.T, T, sizeof(float) * 16);
+  if (mode != 2 || p) angle_derivatives(p, &P);
+  P.gauss_d1 = n->gauss_d1;
+  P.gauss_d2 = n->gauss_d2;
+  P.gauss_d2f = static_cast<float>(n->gauss_d2);
+  fill_offsets(n->search, &P);
+  const int K = mode == 0 ? 43 : (mode == 1 ? 7 : 36);
+  if (score) *score = 0;
+  if (g) std::fill(g, g + 6, 0.0);
+  if (H) std::fill(H, H + 36, 0.0);
+  if (mode == 2) n->hess_recomputes++; else n->evals++;
+  if (n->n_source == 0 || n->refused || n->n_valid == 0) return LGS_OK;
+  const int grid = eval_grid(n->n_source);
+  LGS_TRY(n->partials.reserve(static_cast<size_t>(grid) * kNumAcc * sizeof(double)));
+  if (!n->result.p) {
+    LGS_TRY(n->result.reserve(kNumAcc * sizeof(double) + 64));
+    LGS_CUDA(cudaMemsetAsync(n->result.p, 0, kNumAcc * sizeof(double) + 64, st));
+  }
+  double* result = n->result.as<double>();
+  unsigned* counter = reinterpret_cast<unsigned*>(result + kNumAcc);
+  CellTable ct = make_cell_table(n);
+  const float4* src = n->source.as<float4>();
+  const int ns = static_cast<int>(n->n_source);
+  if (mode == 0)
+    ndt_derivatives_kernel<true><<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->partials.as<double>(), result, counter);
+  else if (mode == 1)
+    ndt_derivatives_kernel<false><<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->partials.as<double>(), result, counter);
+  else
+    ndt_hessian_f64_kernel<<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->partials.as<double>(),
+                                                       result, counter);
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  LGS_TRY(ctx->pin.reserve(kNumAcc * sizeof(double)));
+  double* h = ctx->pin.as<double>();
+  LGS_CUDA(cudaMemcpyAsync(h, result, K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  if (mode == 2) {
+    memcpy(H, h, 36 * sizeof(double));
+  } else {
+    *score = h[0];
+    memcpy(g, h + 1, 6 * sizeof(double));
+    if (mode == 0) memcpy(H, h + 7, 36 * sizeof(double));
+  }
+  return LGS_OK;
+}
+
+inline double dot6(const double* a, const double* b) {
+  double s = 0;
+  for (int i = 0; i < 6; i++) s += a[i] * b[i];
+  return s;
+}
+
+// updateIntervalMT (NDT:647-685)
+bool update_interval(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t) {
+  if (f_t > f_l) {
+    a_u = a_t; f_u = f_t; g_u = g_t;
+    return false;
+  }
+  if (g_t * (a_l - a_t) > 0) {
+    a_l = a_t; f_l = f_t; g_l = g_t;
+    return false;
+  }
+  if (g_t * (a_l - a_t) < 0) {
+    a_u = a_l; f_u = f_l; g_u = g_l;
+    a_l = a_t; f_l = f_t; g_l = g_t;
+    return false;
+  }
+  return true;
+}
+
+// trialValueSelectionMT (NDT:688-768)
+double trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
+  auto cubic = [](double a0, double f0, double g0, double a1, double f1, double g1) {
+    double z = 3 * (f1 - f0) / (a1 - a0) - g1 - g0;
+    double w = std::sqrt(z * z - g1 * g0);
+    return a0 + (a1 - a0) * (w - g0 - z) / (g1 - g0 + 2 * w);
+  };
+  if (f_t > f_l) {
+    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
+    double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+    return std::fabs(a_c - a_l) < std::fabs(a_q - a_l) ? a_c : 0.5 * (a_q + a_c);
+  }
+  if (g_t * g_l < 0) {
+    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    return std::fabs(a_c - a_t) >= std::fabs(a_s - a_t) ? a_c : a_s;
+  }
+  if (std::fabs(g_t) <= std::fabs(g_l)) {
+    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    double a_next = std::fabs(a_c - a_t) < std::fabs(a_s - a_t) ? a_c : a_s;
+    return a_t > a_l ? std::min(a_t + 0.66 * (a_u - a_t), a_next) : std::max(a_t + 0.66 * (a_u - a_t), a_next);
+  }
+  return cubic(a_u, f_u, g_u, a_t, f_t, g_t);
+}
+
+// computeStepLengthMT (NDT:771-931)
+int step_length_mt(lgs_ndt* n, const double x[6], double dir[6], double step_init, double step_max, double step_min, double& score, double g[6],
+                   double H[36], double* step_out) {
+  const double phi_0 = -score;
+  double d_phi_0 = -dot6(g, dir);
+  if (d_phi_0 >= 0) {
+    if (d_phi_0 == 0) {
+      *step_out = 0;
+      return LGS_OK;
+    }
+    d_phi_0 *= -1;
+    for (int i = 0; i < 6; i++) dir[i] *= -1;
+  }
+  const int max_step_iterations = 10;
+  int step_iterations = 0;
+  const double mu = 1.e-4, nu = 0.9;
+  double a_l = 0, a_u = 0;
+  double f_l = phi_0 - phi_0 - mu * d_phi_0 * a_l;  // auxiliaryFunction_PsiMT (NDT.h:430-436)
+  double g_l = d_phi_0 - mu * d_phi_0;              // auxiliaryFunction_dPsiMT (NDT.h:438-447)
+  double f_u = phi_0 - phi_0 - mu * d_phi_0 * a_u;
+  double g_u = d_phi_0 - mu * d_phi_0;
+  bool interval_converged = (step_max - step_min) < 0, open_interval = true;
+  double a_t = std::max(std::min(step_init, step_max), step_min);
+  double x_t[6];
+  for (int i = 0; i < 6; i++) x_t[i] = x[i] + dir[i] * a_t;
+  pose_to_matrix(x_t, n->final_T);
+  LGS_TRY(evaluate(n, n->final_T, x_t, 0, &score, g, H));
+  double phi_t = -score;
+  double d_phi_t = -dot6(g, dir);
+  double psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
+  double d_psi_t = d_phi_t - mu * d_phi_0;
+  while (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
+    n->trials++;
+    if (open_interval)
+      a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+    else
+      a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+    a_t = std::max(std::min(a_t, step_max), step_min);
+    for (int i = 0; i < 6; i++) x_t[i] = x[i] + dir[i] * a_t;
+    pose_to_matrix(x_t, n->final_T);
+    LGS_TRY(evaluate(n, n->final_T, x_t, 1, &score, g, H));  // compute_hessian = false: H is zeroed
+    phi_t = -score;
+    d_phi_t = -dot6(g, dir);
+    psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
+    d_psi_t = d_phi_t - mu * d_phi_0;
+    if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+      open_interval = false;
+      f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
+      g_l = g_l + mu * d_phi_0;
+      f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
+      g_u = g_u + mu * d_phi_0;
+    }
+    if (open_interval)
+      interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+    else
+      interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+    step_iterations++;
+  }
+  if (step_iterations) LGS_TRY(evaluate(n, n->final_T, nullptr, 2, nullptr, nullptr, H));  // NDT:927-928 (angle tables of x_t are current)
+  *step_out = a_t;
+  return LGS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgs_ndt_create(lgs_ctx* ctx, lgs_ndt** out) {
+  LGS_REQUIRE(ctx && out, "null argument");
+  lgs_ndt* n = new lgs_ndt;
+  n->ctx = ctx;
+  identity16(n->final_T);
+  memset(&n->P, 0, sizeof(n->P));
+  compute_gauss(n);
+  *out = n;
+  return LGS_OK;
+}
+
+void lgs_ndt_destroy(lgs_ndt* n) {
+  if (!n) return;
+  cudaSetDevice(n->ctx->device);
+  cudaStreamSynchronize(n->ctx->stream);
+  for (DevBuf* b : {&n->target, &n->source, &n->out_cloud, &n->table, &n->hkeys, &n->recs, &n->ex_idx, &n->ex_n, &n->ex_mean, &n->ex_cov, &n->ex_icov,
+                    &n->small, &n->partials, &n->result})
+    b->release();
+  n->nn.release();
+  delete n;
+}
+
+int lgs_ndt_set_resolution(lgs_ndt* n, float r) {  // NDT.h:132-142: re-init only when the value changes and a source is set
+  LGS_REQUIRE(n && r > 0, "bad argument");
+  if (n->resolution != r) {
+    n->resolution = r;
+    n->grid_ready = false;
+    if (n->have_source && n->have_target) {
+      LGS_TRY(use_device(n->ctx));
+      LGS_TRY(build_grid(n));
+    }
+  }
+  return LGS_OK;
+}
+int lgs_ndt_set_step_size(lgs_ndt* n, double s) { LGS_REQUIRE(n, "null"); n->step_size = s; return LGS_OK; }
+int lgs_ndt_set_transformation_epsilon(lgs_ndt* n, double e) { LGS_REQUIRE(n, "null"); n->trans_eps = e; return LGS_OK; }
+int lgs_ndt_set_maximum_iterations(lgs_ndt* n, int32_t it) { LGS_REQUIRE(n, "null"); n->max_iter = it; return LGS_OK; }
+int lgs_ndt_set_outlier_ratio(lgs_ndt* n, double o) { LGS_REQUIRE(n, "null"); n->outlier_ratio = o; return LGS_OK; }
+int lgs_ndt_set_search_method(lgs_ndt* n, int32_t m) {
+  LGS_REQUIRE(n, "null");
+  LGS_REQUIRE(m == LGS_NDT_DIRECT1 || m == LGS_NDT_DIRECT7 || m == LGS_NDT_DIRECT26, "only DIRECT1/7/26 are supported (KDTREE radius search is not)");
+  n->search = m;
+  return LGS_OK;
+}
+
+static int after_target(lgs_ndt* n) {
+  n->have_target = true;
+  n->nn_ready = false;
+  return build_grid(n);
+}
+
+int lgs_ndt_set_target(lgs_ndt* n, const void* pts, int64_t cnt, int32_t stride) {
+  LGS_REQUIRE(n, "null");
+  LGS_TRY(use_device(n->ctx));
+  LGS_TRY(upload_cloud(n->ctx, pts, cnt, stride, &n->target));
+  n->n_target = cnt;
+  return after_target(n);
+}
+int lgs_ndt_set_target_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
+  LGS_REQUIRE(n, "null");
+  LGS_TRY(use_device(n->ctx));
+  LGS_TRY(adopt_cloud_dev(n->ctx, pts_dev, cnt, &n->target));
+  n->n_target = cnt;
+  return after_target(n);
+}
+int lgs_ndt_set_source(lgs_ndt* n, const void* pts, int64_t cnt, int32_t stride) {
+  LGS_REQUIRE(n, "null");
+  LGS_TRY(use_device(n->ctx));
+  LGS_TRY(upload_cloud(n->ctx, pts, cnt, stride, &n->source));
+  n->n_source = cnt;
+  n->have_source = true;
+  return LGS_OK;
+}
+int lgs_ndt_set_source_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
+  LGS_REQUIRE(n, "null");
+  LGS_TRY(use_device(n->ctx));
+  LGS_TRY(adopt_cloud_dev(n->ctx, pts_dev, cnt, &n->source));
+  n->n_source = cnt;
+  n->have_source = true;
+  return LGS_OK;
+}
+
+// pcl::Registration::align shell + computeTransformation (NDT:80-171)
+int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
+  LGS_REQUIRE(n && res, "null argument");
+  memset(res, 0, sizeof(*res));
+  if (!n->have_target || !n->have_source) {
+    set_error("lgs_ndt_align: setInputTarget and setInputSource must be called first");
+    return LGS_ERR_STATE;
+  }
+  LGS_TRY(use_device(n->ctx));
+  if (!n->grid_ready) LGS_TRY(build_grid(n));
+  n->evals = n->trials = n->hess_recomputes = 0;
+  int nr_iterations = 0;
+  bool converged = false;
+  compute_gauss(n);
+  float guess[16];
+  identity16(guess);
+  if (guess16) memcpy(guess, guess16, sizeof(guess));
+  identity16(n->final_T);
+  bool is_identity = true;
+  for (int i = 0; i < 16; i++)
+    if (guess[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) is_identity = false;
+  if (!is_identity) memcpy(n->final_T, guess, sizeof(guess));  // NDT:95-101; the evaluation transforms by final_T on the fly
+
+  double p[6], delta_p[6], g[6], H[36], score = 0;
+  matrix_to_pose(n->final_T, p);  // NDT:103-111
+  LGS_TRY(evaluate(n, n->final_T, p, 0, &score, g, H));  // NDT:119
+  const double n_in = static_cast<double>(n->n_source);
+  double trans_probability = 0;
+  bool early_exit = false;
+  while (!converged) {
+    double neg_g[6];
+    for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
+    m::svd_solve<6>(H, neg_g, delta_p);  // NDT:127-129
+    double delta_p_norm = std::sqrt(dot6(delta_p, delta_p));
+    if (delta_p_norm == 0 || delta_p_norm != delta_p_norm) {  // NDT:134-139
+      trans_probability = score / n_in;
+      converged = delta_p_norm == delta_p_norm;
+      early_exit = true;
+      break;
+    }
+    for (int i = 0; i < 6; i++) delta_p[i] /= delta_p_norm;
+    double step = 0;
+    LGS_TRY(step_length_mt(n, p, delta_p, delta_p_norm, n->step_size, n->trans_eps / 2, score, g, H, &step));
+    delta_p_norm = step;
+    for (int i = 0; i < 6; i++) delta_p[i] *= delta_p_norm;
+    for (int i = 0; i < 6; i++) p[i] = p[i] + delta_p[i];
+    if (nr_iterations > n->max_iter || (nr_iterations && (std::fabs(delta_p_norm) < n->trans_eps))) converged = true;  // NDT:158-162
+    nr_iterations++;
+  }
+  if (!early_exit) trans_probability = score / n_in;  // NDT:170
+  memcpy(res->T, n->final_T, sizeof(float) * 16);
+  res->trans_probability = trans_probability;
+  res->iterations = nr_iterations;
+  res->converged = converged ? 1 : 0;
+  res->evaluations = n->evals;
+  res->line_search_trials = n->trials;
+  res->hessian_recomputes = n->hess_recomputes;
+  if (out_cloud && n->n_source) {
+    cudaStream_t st = n->ctx->stream;
+    LGS_TRY(n->out_cloud.reserve(static_cast<size_t>(n->n_source) * 16));
+    memcpy(n->P.T, n->final_T, sizeof(float) * 16);
+    transform_cloud_kernel<<<grid_for(n->n_source, 256), 256, 0, st>>>(n->source.as<float4>(), n->n_source, n->P, n->out_cloud.as<float4>());
+    n->ctx->launches++;
+    LGS_CUDA(cudaMemcpyAsync(out_cloud, n->out_cloud.p, static_cast<size_t>(n->n_source) * 16, cudaMemcpyDeviceToHost, st));
+    LGS_CUDA(cudaStreamSynchronize(st));
+  }
+  return LGS_OK;
+}
+
+int lgs_ndt_fitness(lgs_ndt* n, double max_range, double* fitness) {
+  LGS_REQUIRE(n && fitness, "null argument");
+  if (!n->have_target || !n->have_source) {
+    set_error("lgs_ndt_fitness: target and source must be set");
+    return LGS_ERR_STATE;
+  }
+  LGS_TRY(use_device(n->ctx));
+  if (!n->nn_ready) {
+    LGS_TRY(n->nn.build(n->ctx, n->target.as<float4>(), n->n_target));
+    n->nn_ready = true;
+  }
+  return nn_fitness(n->ctx, n->nn, n->source.as<float4>(), n->n_source, n->final_T, max_range, fitness);
+}
+
+int lgs_ndt_calculate_score(lgs_ndt* n, const float* T16, double* score) {
+  LGS_REQUIRE(n && T16 && score, "null argument");
+  LGS_TRY(use_device(n->ctx));
+  if (!n->grid_ready) LGS_TRY(build_grid(n));
+  compute_gauss(n);
+  *score = 0;
+  if (n->n_source == 0) return LGS_OK;
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  EvalParams& P = n->P;
+  memcpy(P.T, T16, sizeof(float) * 16);
+  P.gauss_d1 = n->gauss_d1;
+  P.gauss_d2 = n->gauss_d2;
+  fill_offsets(n->search, &P);
+  if (!(n->refused || n->n_valid == 0)) {
+    const int grid = eval_grid(n->n_source);
+    LGS_TRY(n->partials.reserve(static_cast<size_t>(grid) * kNumAcc * sizeof(double)));
+    if (!n->result.p) {
+      LGS_TRY(n->result.reserve(kNumAcc * sizeof(double) + 64));
+      LGS_CUDA(cudaMemsetAsync(n->result.p, 0, kNumAcc * sizeof(double) + 64, st));
+    }
+    double* result = n->result.as<double>();
+    unsigned* counter = reinterpret_cast<unsigned*>(result + kNumAcc);
+    ndt_score_kernel<<<grid, kEvalBlock, 0, st>>>(n->source.as<float4>(), static_cast<int>(n->n_source), P, make_cell_table(n),
+                                                 n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->gauss_d3, n->partials.as<double>(), result, counter);
+    ctx->launches++;
+    LGS_TRY(ctx->pin.reserve(64));
+    LGS_CUDA(cudaMemcpyAsync(ctx->pin.p, result, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LGS_CUDA(cudaStreamSynchronize(st));
+    *score = ctx->pin.as<double>()[0];
+  }
+  *score /= static_cast<double>(n->n_source);
+  return LGS_OK;
+}
+
+int lgs_ndt_grid_info_get(lgs_ndt* n, lgs_ndt_grid_info* info) {
+  LGS_REQUIRE(n && info, "null argument");
+  memset(info, 0, sizeof(*info));
+  if (n->have_target && !n->grid_ready) {
+    LGS_TRY(use_device(n->ctx));
+    LGS_TRY(build_grid(n));
+  }
+  info->refused = n->refused ? 1 : 0;
+  info->dense = n->dense;
+  info->n_voxels = n->n_voxels;
+  info->n_valid = n->n_valid;
+  for (int a = 0; a < 3; a++) {
+    info->min_b[a] = n->min_b[a];
+    info->max_b[a] = n->max_b[a];
+    info->div_b[a] = n->div_b[a];
+  }
+  return LGS_OK;
+}
+
+int lgs_ndt_export_voxels(lgs_ndt* n, int32_t* idx, int32_t* nr_points, double* mean, double* cov, double* icov) {
+  LGS_REQUIRE(n, "null argument");
+  LGS_TRY(use_device(n->ctx));
+  if (n->have_target && !n->grid_ready) LGS_TRY(build_grid(n));
+  const size_t V = static_cast<size_t>(n->n_voxels);
+  if (V == 0) return LGS_OK;
+  cudaStream_t st = n->ctx->stream;
+  if (idx) LGS_CUDA(cudaMemcpyAsync(idx, n->ex_idx.p, V * 4, cudaMemcpyDeviceToHost, st));
+  if (nr_points) LGS_CUDA(cudaMemcpyAsync(nr_points, n->ex_n.p, V * 4, cudaMemcpyDeviceToHost, st));
+  if (mean) LGS_CUDA(cudaMemcpyAsync(mean, n->ex_mean.p, V * 24, cudaMemcpyDeviceToHost, st));
+  if (cov) LGS_CUDA(cudaMemcpyAsync(cov, n->ex_cov.p, V * 72, cudaMemcpyDeviceToHost, st));
+  if (icov) LGS_CUDA(cudaMemcpyAsync(icov, n->ex_icov.p, V * 72, cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  return LGS_OK;
+}
+
+int lgs_ndt_derivatives(lgs_ndt* n, const float* T16, const double* p6, int32_t mode, double* score, double* g6, double* H36) {
+  LGS_REQUIRE(n && T16 && p6 && H36, "null argument");
+  LGS_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  if (!n->have_target || !n->have_source) {
+    set_error("lgs_ndt_derivatives: target and source must be set");
+    return LGS_ERR_STATE;
+  }
+  LGS_TRY(use_device(n->ctx));
+  if (!n->grid_ready) LGS_TRY(build_grid(n));
+  compute_gauss(n);
+  double s = 0, g[6];
+  LGS_TRY(evaluate(n, T16, p6, mode, &s, g, H36));
+  if (score) *score = s;
+  if (g6) memcpy(g6, g, sizeof(g));
+  return LGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+// Prefilter: range/box crop + pcl::VoxelGrid downsampling on the GPU.
+//
+// Replaces PPF:102-112 (distance_filter), PPF:89-100 (crop) and pcl::VoxelGrid::filter as called at
+// PPF:114-121 and GBS:311-313,490-493 (index arithmetic restated in-tree at VGC:67-103,218-223).
+//
+// Pipeline (all on ctx->stream):
+//   K1 crop_bbox      16 B/pt read : crop predicate, bbox of the kept points (block reduce + 6 atomics)
+//   -- 32-byte D2H of the bbox; the host derives min_b/div_b/divb_mul with the reference's f32 arithmetic
+//   K2 voxel_key      16 B/pt read, 12 B/pt write: key = ijk . divb_mul (explicit IEEE f32 ops), value = point index
+//   K3 radix sort     (key,value) pairs, only the bits the grid needs (stable => members stay in index order)
+//   K4 segment heads  + select => start offset of every occupied voxel
+//   K5 centroid       one thread per voxel: sequential f32 sums in ascending point index (the oracle's order),
+//                     scatter of the per-point membership rank
+// Integer outputs (voxel idx, occupancy, membership, order) are bit-exact by construction: no FMA
+// contraction or reassociation can reach the key arithmetic because it is written with __f*_rn intrinsics.
+#include <cub/cub.cuh>
+
+#include <cfloat>
+#include <cmath>
+#include <limits>
+
+#include "voxel_common.cuh"
+
+namespace lgs {
+
+struct BBoxAcc {  // device-side accumulator
+  unsigned mn[3];
+  unsigned mx[3];
+  unsigned long long kept;
+};
+
+__global__ void bbox_init_kernel(BBoxAcc* acc) {
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 3; a++) {
+      acc->mn[a] = 0xFFFFFFFFu;
+      acc->mx[a] = 0u;
+    }
+    acc->kept = 0ull;
+  }
+}
+
+__device__ __forceinline__ bool crop_keep(const float4& p, const CropParams& cp) {
+  bool keep = true;
+  if (cp.range_min >= 0.0) {
+    // Eigen Vector3f::norm(): sqrt(x*x + (y*y + z*z)) in f32 (unrolled 3-element redux), compared in f64
+    float n2 = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
+    float nrm = __fsqrt_rn(n2);
+    keep = cp.range_min < static_cast<double>(nrm);
+  }
+  if (cp.use_box) {
+    keep = keep && (cp.box[0] < p.x && p.x < cp.box[1]) && (cp.box[2] < p.y && p.y < cp.box[3]) && (cp.box[4] < p.z && p.z < cp.box[5]);
+  }
+  return keep;
+}
+
+// grid-stride, float4 loads; per-thread min/max -> warp shuffle -> one atomic set per block
+__global__ void __launch_bounds__(256) crop_bbox_kernel(const float4* __restrict__ pts, int64_t n, CropParams cp, unsigned char* __restrict__ keep,
+                                                       BBoxAcc* __restrict__ acc) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  unsigned cnt = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 p = pts[i];
+    bool k = crop_keep(p, cp);
+    if (keep) keep[i] = k ? 1 : 0;
+    if (k) {
+      cnt++;
+      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    for (int a = 0; a < 3; a++) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  __shared__ float smn[8][3], smx[8][3];
+  __shared__ unsigned scnt[8];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    for (int a = 0; a < 3; a++) {
+      smn[w][a] = mn[a];
+      smx[w][a] = mx[a];
+    }
+    scnt[w] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned total = 0;
+    for (int ww = 0; ww < (blockDim.x >> 5); ww++) {
+      total += scnt[ww];
+      for (int a = 0; a < 3; a++) {
+        mn[a] = fminf(mn[a], smn[ww][a]);
+        mx[a] = fmaxf(mx[a], smx[ww][a]);
+      }
+    }
+    if (total) {
+      for (int a = 0; a < 3; a++) {
+        atomicMin(&acc->mn[a], enc_f(mn[a]));
+        atomicMax(&acc->mx[a], enc_f(mx[a]));
+      }
+      atomicAdd(&acc->kept, static_cast<unsigned long long>(total));
+    }
+  }
+}
+
+// VGC:218-223 / pcl::VoxelGrid: ijk = int(floor(x * inv) - float(min_b)); idx = ijk . divb_mul
+__device__ __forceinline__ int voxel_index(const float4& p, const GridParams& g) {
+  int ijk0 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.x, g.inv[0])), static_cast<float>(g.min_b[0])));
+  int ijk1 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.y, g.inv[1])), static_cast<float>(g.min_b[1])));
+  int ijk2 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.z, g.inv[2])), static_cast<float>(g.min_b[2])));
+  return ijk0 * g.mul[0] + ijk1 * g.mul[1] + ijk2 * g.mul[2];
+}
+
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ pts, const unsigned char* __restrict__ keep, int64_t n, GridParams g,
+                                                       unsigned* __restrict__ keys, unsigned* __restrict__ vals, int* __restrict__ voxel_idx,
+                                                       int* __restrict__ member_rank) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  unsigned key = g.sentinel;
+  int vi = -1;
+  if (!keep || keep[i]) {
+    vi = voxel_index(pts[i], g);
+    key = static_cast<unsigned>(vi);
+  }
+  keys[i] = key;
+  vals[i] = static_cast<unsigned>(i);
+  if (voxel_idx) voxel_idx[i] = vi;
+  if (member_rank) member_rank[i] = -1;
+}
+
+__global__ void __launch_bounds__(256) head_flag_kernel(const unsigned* __restrict__ keys, int64_t n_kept, unsigned char* __restrict__ flags) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_kept) return;
+  flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// qualifies[v] = 1 if the voxel holds >= min_pts points
+__global__ void __launch_bounds__(256) qualify_kernel(const int* __restrict__ seg_start, int n_seg, int64_t n_kept, int min_pts, int* __restrict__ qual) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_seg) return;
+  int b = seg_start[v];
+  int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_kept);
+  qual[v] = (e - b >= min_pts) ? 1 : 0;
+}
+
+// One thread per occupied voxel.  CentroidPoint<PointXYZI> (PCL): f32 accumulators for xyz and
+// intensity, divided by the point count; members are visited in ascending point index.
+__global__ void __launch_bounds__(128) centroid_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ vals, const int* __restrict__ seg_start,
+                                                      const int* __restrict__ out_rank, const int* __restrict__ qual, int n_seg, int64_t n_kept,
+                                                      float4* __restrict__ out_pts, int* __restrict__ member_rank) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_seg) return;
+  if (qual && !qual[v]) return;
+  int b = seg_start[v];
+  int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_kept);
+  int r = out_rank ? out_rank[v] : v;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  for (int j = b; j < e; j++) {
+    unsigned pi = vals[j];
+    float4 p = pts[pi];
+    sx = __fadd_rn(sx, p.x);
+    sy = __fadd_rn(sy, p.y);
+    sz = __fadd_rn(sz, p.z);
+    si = __fadd_rn(si, p.w);
+    if (member_rank) member_rank[pi] = r;
+  }
+  float c = static_cast<float>(e - b);
+  if (out_pts) out_pts[r] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+}
+
+static int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b) != 0) b++;
+  return b;
+}
+
+// Shared front half: crop, bbox, keys, sort, segment heads.
+int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float leaf[3], double range_min, const double* box6,
+                        int* voxel_idx_dev, int* member_rank_dev, SortedVoxels* out) {
+  *out = SortedVoxels();
+  LGS_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "point count out of range");
+  LGS_REQUIRE(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0, "leaf size must be positive");
+  if (n == 0) return LGS_OK;
+  cudaStream_t st = ctx->stream;
+  const bool cropping = range_min >= 0.0 || box6 != nullptr;
+
+  // arenas: tmp0 keep flags | tmp1 keys | tmp2 vals | tmp3 keys_alt | tmp4 vals_alt | tmp5 head flags, seg_start | tmp6 small
+  if (cropping) LGS_TRY(ctx->tmp[0].reserve(n));
+  LGS_TRY(ctx->tmp[6].reserve(sizeof(BBoxAcc) + 64));
+  LGS_TRY(ctx->pin.reserve(256));
+  unsigned char* keep = cropping ? ctx->tmp[0].as<unsigned char>() : nullptr;
+  out->keep = keep;
+  BBoxAcc* acc = ctx->tmp[6].as<BBoxAcc>();
+
+  CropParams cp;
+  cp.range_min = range_min;
+  cp.use_box = box6 ? 1 : 0;
+  for (int a = 0; a < 6; a++) cp.box[a] = box6 ? box6[a] : 0.0;
+
+  bbox_init_kernel<<<1, 32, 0, st>>>(acc);
+  int blocks = std::min(grid_for(n, 256), kNumSMs * 8);
+  crop_bbox_kernel<<<blocks, 256, 0, st>>>(pts, n, cp, keep, acc);
+  ctx->launches += 2;
+  BBoxAcc* hacc = ctx->pin.as<BBoxAcc>();
+  LGS_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+
+  const int64_t n_kept = static_cast<int64_t>(hacc->kept);
+  out->n_kept = n_kept;
+  if (n_kept == 0) {
+    if (voxel_idx_dev) LGS_CUDA(cudaMemsetAsync(voxel_idx_dev, 0xFF, n * sizeof(int), st));
+    if (member_rank_dev) LGS_CUDA(cudaMemsetAsync(member_rank_dev, 0xFF, n * sizeof(int), st));
+    return LGS_OK;
+  }
+  float mn[3], mx[3], inv[3];
+  for (int a = 0; a < 3; a++) {
+    mn[a] = dec_f_host(hacc->mn[a]);
+    mx[a] = dec_f_host(hacc->mx[a]);
+    inv[a] = 1.0f / leaf[a];  // VoxelGrid::setLeafSize: inverse_leaf_size_ = 1 / leaf_size_ (f32)
+  }
+  // overflow refusal (PCL voxel_grid.hpp; same test at VGC:75-84)
+  int64_t d[3];
+  for (int a = 0; a < 3; a++) d[a] = static_cast<int64_t>((mx[a] - mn[a]) * inv[a]) + 1;
+  if (d[0] * d[1] * d[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+    out->status = LGS_VG_REFUSED_OVERFLOW;
+    if (voxel_idx_dev) LGS_CUDA(cudaMemsetAsync(voxel_idx_dev, 0xFF, n * sizeof(int), st));
+    if (member_rank_dev) LGS_CUDA(cudaMemsetAsync(member_rank_dev, 0xFF, n * sizeof(int), st));
+    return LGS_OK;
+  }
+  GridParams g;
+  for (int a = 0; a < 3; a++) {
+    out->min_b[a] = static_cast<int>(std::floor(mn[a] * inv[a]));
+    out->max_b[a] = static_cast<int>(std::floor(mx[a] * inv[a]));
+    out->div_b[a] = out->max_b[a] - out->min_b[a] + 1;
+    g.inv[a] = inv[a];
+    g.min_b[a] = out->min_b[a];
+  }
+  g.mul[0] = 1;
+  g.mul[1] = out->div_b[0];
+  g.mul[2] = out->div_b[0] * out->div_b[1];
+  const uint64_t total_cells = static_cast<uint64_t>(out->div_b[0]) * out->div_b[1] * out->div_b[2];
+  out->total_cells = total_cells;
+  g.sentinel = static_cast<unsigned>(total_cells);  // <= 2^31 - 1, larger than any real index
+  const int end_bit = bits_for(total_cells);
+
+  LGS_TRY(ctx->tmp[1].reserve(n * 4));
+  LGS_TRY(ctx->tmp[2].reserve(n * 4));
+  LGS_TRY(ctx->tmp[3].reserve(n * 4));
+  LGS_TRY(ctx->tmp[4].reserve(n * 4));
+  cub::DoubleBuffer<unsigned> dkeys(ctx->tmp[1].as<unsigned>(), ctx->tmp[3].as<unsigned>());
+  cub::DoubleBuffer<unsigned> dvals(ctx->tmp[2].as<unsigned>(), ctx->tmp[4].as<unsigned>());
+  voxel_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, keep, n, g, dkeys.Current(), dvals.Current(), voxel_idx_dev, member_rank_dev);
+  ctx->launches++;
+  {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, dkeys, dvals, static_cast<int>(n), 0, end_bit, st);
+    LGS_TRY(ctx->cub_tmp.reserve(tb));
+    cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, dkeys, dvals, static_cast<int>(n), 0, end_bit, st);
+    ctx->launches += (end_bit + 7) / 8 + 2;
+  }
+  out->keys = dkeys.Current();
+  out->vals = dvals.Current();
+
+  // segment heads -> start offsets
+  LGS_TRY(ctx->tmp[5].reserve(static_cast<size_t>(n_kept) * (1 + 4) + 64));
+  unsigned char* flags = ctx->tmp[5].as<unsigned char>();
+  int* seg_start = reinterpret_cast<int*>(flags + ((n_kept + 15) / 16) * 16);
+  int* d_nseg = reinterpret_cast<int*>(reinterpret_cast<char*>(acc) + 48);
+  head_flag_kernel<<<grid_for(n_kept, 256), 256, 0, st>>>(out->keys, n_kept, flags);
+  {
+    size_t tb = 0;
+    cub::CountingInputIterator<int> it(0);
+    cub::DeviceSelect::Flagged(nullptr, tb, it, flags, seg_start, d_nseg, static_cast<int>(n_kept), st);
+    LGS_TRY(ctx->cub_tmp.reserve(tb));
+    cub::DeviceSelect::Flagged(ctx->cub_tmp.p, tb, it, flags, seg_start, d_nseg, static_cast<int>(n_kept), st);
+    ctx->launches += 3;
+  }
+  int* h_small = ctx->pin.as<int>() + 32;
+  LGS_CUDA(cudaMemcpyAsync(h_small, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  out->n_seg = h_small[0];
+  out->seg_start = seg_start;
+  return LGS_OK;
+}
+
+// Prefilter core: everything device-side.  Outputs may be null.  out_pts in ascending voxel-index order.
+int voxelgrid_device(lgs_ctx* ctx, const float4* pts, int64_t n, const float leaf[3], int min_pts, double range_min, const double* box6,
+                     float4* out_pts_dev, int* voxel_idx_dev, int* member_rank_dev, lgs_voxelgrid_info* info) {
+  memset(info, 0, sizeof(*info));
+  SortedVoxels sv;
+  LGS_TRY(build_sorted_voxels(ctx, pts, n, leaf, range_min, box6, voxel_idx_dev, member_rank_dev, &sv));
+  cudaStream_t st = ctx->stream;
+  info->status = sv.status;
+  info->n_kept = sv.n_kept;
+  for (int a = 0; a < 3; a++) {
+    info->min_b[a] = sv.min_b[a];
+    info->max_b[a] = sv.max_b[a];
+    info->div_b[a] = sv.div_b[a];
+  }
+  if (sv.n_kept == 0) return LGS_OK;
+  if (sv.status == LGS_VG_REFUSED_OVERFLOW) {
+    info->n_out = sv.n_kept;
+    if (out_pts_dev) {  // pcl::VoxelGrid: output = input (here: the cropped input, original order)
+      if (!sv.keep) {
+        LGS_CUDA(cudaMemcpyAsync(out_pts_dev, pts, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToDevice, st));
+      } else {
+        size_t tb = 0;
+        LGS_TRY(ctx->tmp[5].reserve(sizeof(int)));
+        cub::DeviceSelect::Flagged(nullptr, tb, pts, sv.keep, out_pts_dev, ctx->tmp[5].as<int>(), static_cast<int>(n), st);
+        LGS_TRY(ctx->cub_tmp.reserve(tb));
+        cub::DeviceSelect::Flagged(ctx->cub_tmp.p, tb, pts, sv.keep, out_pts_dev, ctx->tmp[5].as<int>(), static_cast<int>(n), st);
+        ctx->launches += 2;
+      }
+      LGS_CUDA(cudaGetLastError());
+    }
+    return LGS_OK;
+  }
+  const int n_seg = sv.n_seg;
+  const int64_t n_kept = sv.n_kept;
+  int* h_small = ctx->pin.as<int>() + 32;
+  int* qual = nullptr;
+  int* out_rank = nullptr;
+  int64_t n_out = n_seg;
+  if (min_pts > 1) {
+    LGS_TRY(ctx->tmp[7].reserve(static_cast<size_t>(n_seg) * 8 + 64));
+    qual = ctx->tmp[7].as<int>();
+    out_rank = qual + n_seg;
+    qualify_kernel<<<grid_for(n_seg, 256), 256, 0, st>>>(sv.seg_start, n_seg, n_kept, min_pts, qual);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, qual, out_rank, n_seg, st);
+    LGS_TRY(ctx->cub_tmp.reserve(tb));
+    cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, qual, out_rank, n_seg, st);
+    ctx->launches += 3;
+    LGS_CUDA(cudaMemcpyAsync(h_small, qual + n_seg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LGS_CUDA(cudaMemcpyAsync(h_small + 1, out_rank + n_seg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LGS_CUDA(cudaStreamSynchronize(st));
+    n_out = h_small[0] + h_small[1];
+  }
+  info->n_out = n_out;
+  centroid_kernel<<<grid_for(n_seg, 128), 128, 0, st>>>(pts, sv.vals, sv.seg_start, out_rank, qual, n_seg, n_kept, out_pts_dev, member_rank_dev);
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  return LGS_OK;
+}
+
+}  // namespace lgs
+
+extern "C" {
+
+int lgs_voxelgrid_filter_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, const float leaf[3], int32_t min_points_per_voxel, double range_min,
+                             const double* box6, float* out_pts_dev, int32_t* out_voxel_idx_dev, int32_t* out_member_rank_dev,
+                             lgs_voxelgrid_info* info) {
+  LGS_REQUIRE(ctx && info && leaf, "null argument");
+  LGS_TRY(lgs::use_device(ctx));
+  return lgs::voxelgrid_device(ctx, reinterpret_cast<const float4*>(pts_dev), n, leaf, min_points_per_voxel, range_min, box6,
+                               reinterpret_cast<float4*>(out_pts_dev), out_voxel_idx_dev, out_member_rank_dev, info);
+}
+
+int lgs_voxelgrid_filter(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const float leaf[3], int32_t min_points_per_voxel,
+                         double range_min, const double* box6, float* out_pts, int32_t* out_voxel_idx, int32_t* out_member_rank,
+                         lgs_voxelgrid_info* info) {
+  LGS_REQUIRE(ctx && info && leaf, "null argument");
+  LGS_TRY(lgs::use_device(ctx));
+  struct Arena {
+    lgs::DevBuf &in, &out, &vidx, &rank;
+  } arena{ctx->vg_in, ctx->vg_out, ctx->vg_vidx, ctx->vg_rank};
+  Arena* A = &arena;
+  LGS_TRY(lgs::upload_cloud(ctx, pts, n, stride_bytes, &A->in));
+  const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+  LGS_TRY(A->out.reserve(nn * 16));
+  if (out_voxel_idx) LGS_TRY(A->vidx.reserve(nn * 4));
+  if (out_member_rank) LGS_TRY(A->rank.reserve(nn * 4));
+  LGS_TRY(lgs::voxelgrid_device(ctx, A->in.as<float4>(), n, leaf, min_points_per_voxel, range_min, box6, A->out.as<float4>(),
+                                out_voxel_idx ? A->vidx.as<int>() : nullptr, out_member_rank ? A->rank.as<int>() : nullptr, info));
+  cudaStream_t st = ctx->stream;
+  if (out_pts && info->n_out) LGS_CUDA(cudaMemcpyAsync(out_pts, A->out.p, static_cast<size_t>(info->n_out) * 16, cudaMemcpyDeviceToHost, st));
+  if (out_voxel_idx && n) LGS_CUDA(cudaMemcpyAsync(out_voxel_idx, A->vidx.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+  if (out_member_rank && n) LGS_CUDA(cudaMemcpyAsync(out_member_rank, A->rank.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  return LGS_OK;
+}
+
+}  // extern "C"

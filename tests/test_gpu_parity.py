@@ -1,0 +1,399 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star / SURVEY.md section 8d): voxel indices, occupancy, membership and output order are
+bit-exact; voxel mean / inverse covariance rel 1e-9; final transforms within 1e-4 m / 1e-4 rad; fitness and
+transformation probability within 1e-5 relative; identical iteration counts and convergence flags."""
+import numpy as np
+import pytest
+
+from conftest import pose_error
+
+pytestmark = pytest.mark.gpu
+
+T_TOL_M, R_TOL_RAD, FIT_RTOL = 1e-4, 1e-4, 1e-5
+
+
+def _vg(api, pts, leaf, **kw):
+    vg = api.VoxelGrid()
+    vg.setLeafSize(leaf)
+    if "range_min" in kw:
+        vg.setRangeCrop(kw["range_min"])
+    if "box" in kw:
+        vg.setBoxCrop(kw["box"])
+    if "min_pts" in kw:
+        vg.setMinimumPointsNumberPerVoxel(kw["min_pts"])
+    vg.setInputCloud(pts)
+    out = vg.filter()
+    return vg, out
+
+
+def _check_vg(api, oracle, pts, leaf, **kw):
+    vg, out = _vg(api, pts, leaf, **kw)
+    ref = oracle.voxel_grid(pts, leaf, min_points_per_voxel=kw.get("min_pts", 0), range_min=kw.get("range_min", -1.0), box=kw.get("box"))
+    assert vg.info.status == ref["status"]
+    assert vg.info.n_kept == ref["n_kept"]
+    assert out.shape[0] == ref["points"].shape[0]
+    if ref["status"] == 0 and ref["n_kept"] > 0:
+        assert list(vg.info.min_b) == list(ref["min_b"]) and list(vg.info.div_b) == list(ref["div_b"])
+    assert np.array_equal(vg.voxel_idx, ref["voxel_idx"])        # per-point voxel index: bit-exact
+    assert np.array_equal(vg.member_rank, ref["member_rank"])    # membership: bit-exact
+    # centroids: same f32 summation order as the oracle => expected bit-exact; the contract is rel 1e-5
+    np.testing.assert_allclose(out, ref["points"], rtol=1e-5, atol=1e-6)
+    return out, ref
+
+
+def test_voxelgrid_velodyne_bit_exact(api, oracle, velodyne_pair):
+    for leaf in (0.1, 0.2, 0.5):
+        out, ref = _check_vg(api, oracle, velodyne_pair["target"], leaf)
+        assert np.array_equal(out, ref["points"])  # stronger than the contract: identical bits
+    _check_vg(api, oracle, velodyne_pair["source"], 0.2, range_min=1.0)
+    _check_vg(api, oracle, velodyne_pair["source"], 0.1, range_min=2.5, box=[-20, 30, -15, 15, -2, 4])
+    _check_vg(api, oracle, velodyne_pair["source"], 0.5, min_pts=3)
+
+
+def test_voxelgrid_cfg1_synthetic_128_beam(api, oracle):
+    """BASELINE configs[1]: VoxelGrid 0.2 m + min-range crop of 128-beam 262 144-point sweeps, bit-exact membership."""
+    from lidar_graph_slam_b200 import synth
+    for sweep in synth.prefilter_sweeps(2):
+        assert sweep.shape == (262144, 4)
+        for leaf in (0.2, 0.1):
+            out, ref = _check_vg(api, oracle, sweep, leaf, range_min=1.0)
+            assert np.array_equal(out, ref["points"])
+
+
+def test_voxelgrid_pcl_point_layout_and_edge_cases(api, oracle, velodyne_pair):
+    pts = velodyne_pair["target"][:5000]
+    aos = np.zeros((len(pts), 8), np.float32)  # pcl::PointXYZI: x y z pad | intensity pad pad pad
+    aos[:, :3] = pts[:, :3]
+    aos[:, 4] = pts[:, 3]
+    vg = api.VoxelGrid()
+    vg.setLeafSize(0.3)
+    vg.setInputCloud(aos)
+    out32 = vg.filter()
+    ref = oracle.voxel_grid(pts, 0.3)
+    assert np.array_equal(out32, ref["points"])
+    # empty, single, all-cropped, overflow refusal
+    for cloud, kw in ((np.zeros((0, 4), np.float32), {}), (np.array([[1, 2, 3, 4]], np.float32), {}),
+                      (np.array([[1, 2, 3, 4]], np.float32), {"range_min": 100.0})):
+        _check_vg(api, oracle, cloud, 0.2, **kw)
+    far = np.array([[0, 0, 0, 1], [5000, 5000, 5000, 2]], np.float32)
+    vg, out = _vg(api, far, 0.01)
+    assert vg.info.status == api.VG_REFUSED_OVERFLOW and np.array_equal(out, far)
+
+
+def test_voxelgrid_idempotent_at_full_size(api):
+    """Size-independent property at BASELINE size: filtering the centroids again with the same leaf keeps one point
+    per voxel, and membership counts sum to the kept points."""
+    from lidar_graph_slam_b200 import synth
+    sweep = synth.prefilter_sweeps(1)[0]
+    vg, out = _vg(api, sweep, 0.2, range_min=1.0)
+    counts = np.bincount(vg.member_rank[vg.member_rank >= 0], minlength=len(out))
+    assert counts.sum() == vg.info.n_kept and counts.min() >= 1
+    assert np.all(np.diff(vg.voxel_idx[np.argsort(vg.member_rank, kind="stable")][vg.member_rank[np.argsort(vg.member_rank, kind="stable")] >= 0]) >= 0)
+    vg2, out2 = _vg(api, out, 0.2)
+    assert len(out2) <= len(out) and len(out2) >= 0.95 * len(out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _ndt_pair(api, oracle, tgt, src, res=1.0, eps=0.01, it=64, method=None):
+    g = api.NormalDistributionsTransform()
+    o = oracle.NDT()
+    for n in (g, o):
+        n.setResolution(res)
+        n.setTransformationEpsilon(eps)
+        n.setMaximumIterations(it)
+        n.setStepSize(0.1)
+        if method is not None:
+            n.setNeighborhoodSearchMethod(method)
+        n.setInputTarget(tgt)
+        n.setInputSource(src)
+    return g, o
+
+
+def _compare_voxels(g, o):
+    vg, vo = g.export_voxels(), o.export_voxels()
+    assert np.array_equal(vg["idx"], vo["idx"])          # occupancy: bit-exact
+    assert np.array_equal(vg["n"], vo["n"])              # counts and validity flags: bit-exact
+    assert list(vg["min_b"]) == list(vo["min_b"]) and list(vg["div_b"]) == list(vo["div_b"])
+    valid = vo["n"] >= 6
+    assert vg["n_valid"] == valid.sum()
+    np.testing.assert_allclose(vg["mean"], vo["mean"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(vg["icov"][valid], vo["icov"][valid], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(vg["cov"][valid], vo["cov"][valid], rtol=1e-9, atol=1e-12)
+    return vo, valid
+
+
+def _compare_align(g, o, guess=None):
+    g.align(guess)
+    o.align(guess)
+    r = g.result
+    assert (r.iterations, bool(r.converged)) == (o.nr_iterations, o.converged)
+    assert (r.evaluations, r.line_search_trials, r.hessian_recomputes) == (o.stats["derivative_evals"], o.stats["line_search_trials"],
+                                                                         o.stats["hessian_recomputes"])
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD
+    assert g.getTransformationProbability() == pytest.approx(o.trans_probability, rel=FIT_RTOL)
+    assert g.getFitnessScore() == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+
+
+def test_ndt_velodyne_voxels_and_derivatives(api, oracle, velodyne_pair):
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.1)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.1)["points"]
+    for res in (1.0, 2.0, 0.5):
+        g, o = _ndt_pair(api, oracle, td, sd, res=res)
+        _compare_voxels(g, o)
+        for p in (np.zeros(6), np.array([0.45, 0.12, -0.02, 0.004, -0.008, 0.011])):
+            T = oracle.ndt_convert_transform(p)
+            for mode in (0, 1, 2):
+                so, go, Ho = o.derivatives(T, p, mode)
+                sg, gg, Hg = g.derivatives(T, p, mode)
+                scale = np.abs(Ho).max() if mode != 1 else 1.0
+                if mode != 2:
+                    assert sg == pytest.approx(so, rel=1e-12)
+                    np.testing.assert_allclose(gg, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+                if mode != 1:
+                    np.testing.assert_allclose(Hg, Ho, rtol=1e-9, atol=1e-11 * scale)
+
+
+def test_ndt_velodyne_align_parity(api, oracle, velodyne_pair):
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.1)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.1)["points"]
+    for res, eps, it in ((1.0, 0.01, 64), (1.0, 0.1, 35), (2.0, 0.01, 64)):
+        g, o = _ndt_pair(api, oracle, td, sd, res=res, eps=eps, it=it)
+        _compare_align(g, o)
+    g, o = _ndt_pair(api, oracle, td, sd)
+    t_err, r_err = None, None
+    _compare_align(g, o)
+    t_err, r_err = pose_error(velodyne_pair["relative"], g.getFinalTransformation())
+    assert t_err < 0.05 and np.degrees(r_err) < 1.0  # the reference's own acceptance band
+    # non-identity guess (LSM:165 passes the previous pose), DIRECT1 and DIRECT26 neighbourhoods
+    guess = velodyne_pair["relative"].astype(np.float32).copy()
+    guess[:3, 3] += np.array([0.2, -0.15, 0.03], np.float32)
+    _compare_align(g, o, guess)
+    for method in (api.NDT_DIRECT1, api.NDT_DIRECT26):
+        g, o = _ndt_pair(api, oracle, td, sd, method=method)
+        _compare_align(g, o)
+
+
+def test_ndt_cfg0_synthetic_scan_to_map(api, oracle):
+    """BASELINE configs[0]: 120 000-point 64-beam sweep against a 1 000 000-point local map, DIRECT7, 1.0 m."""
+    from lidar_graph_slam_b200 import synth
+    d = synth.ndt_scan_to_map()
+    assert d["source"].shape == (120000, 4) and d["target"].shape == (1000000, 4)
+    g, o = _ndt_pair(api, oracle, d["target"], d["source"])
+    _compare_voxels(g, o)
+    _compare_align(g, o, d["guess"])
+    t_err, r_err = pose_error(d["T_true"], g.getFinalTransformation())
+    assert t_err < 0.05 and r_err < np.radians(0.5)
+    # calculateScore (NDT:934-982)
+    assert g.calculateScore(g.getFinalTransformation()) == pytest.approx(o.calculateScore(o.final_transformation), rel=1e-9)
+
+
+def test_ndt_hash_table_path_and_refusal(api, oracle):
+    """A sparse, very wide target forces the hashed cell table; results must equal the dense-table oracle semantics.
+    A grid above INT32_MAX cells is refused like VGC:79-84 (every lookup misses, align returns the guess)."""
+    rs = np.random.RandomState(3)
+    centers = rs.uniform(-3000, 3000, size=(300, 3)).astype(np.float32)
+    centers[:, 2] = rs.uniform(-300, 300, size=300)
+    tgt = (centers[:, None, :] + rs.normal(0, 0.25, size=(300, 40, 3))).reshape(-1, 3).astype(np.float32)
+    tgt = np.concatenate([tgt, np.zeros((len(tgt), 1), np.float32)], 1)
+    src = tgt[::3].copy()
+    src[:, :3] += np.array([0.05, -0.04, 0.02], np.float32)
+    g, o = _ndt_pair(api, oracle, tgt, src, res=2.0)
+    vo, valid = _compare_voxels(g, o)
+    assert not g.export_voxels()["dense"]
+    _compare_align(g, o)
+    big = np.array([[0, 0, 0, 0], [40000, 40000, 4000, 0]], np.float32)
+    g, o = _ndt_pair(api, oracle, np.concatenate([tgt, big]), src, res=0.5)
+    assert g.export_voxels()["refused"] and o.export_voxels()["refused"]
+    _compare_align(g, o)
+
+
+def test_ndt_set_target_always_rebuilds(api, oracle, velodyne_pair):
+    """LSM:187-212 mutates the target cloud in place and re-submits the same pointer: every call must re-voxelise."""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"].copy()
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _ndt_pair(api, oracle, td, sd)
+    td[:, 0] += 0.37  # in-place mutation of the same buffer
+    g.setInputTarget(td)
+    o.setInputTarget(td)
+    _compare_voxels(g, o)
+    _compare_align(g, o)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_knn_exact(api, oracle, velodyne_pair):
+    pts = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    q = oracle.voxel_grid(velodyne_pair["source"], 0.4)["points"]
+    for k in (1, 20):
+        ig, dg = api.knn(pts, q, k)
+        io, do = oracle.knn(pts, q, k)
+        assert np.array_equal(dg, do)   # f32 squared distances: identical bits
+        assert np.array_equal(ig, io)   # same tie rule => identical indices
+    # far-away queries and duplicates
+    qq = np.array([[500, -300, 40, 0], [0, 0, 0, 0]], np.float32)
+    dup = np.concatenate([pts[:100], pts[:100]])
+    ig, dg = api.knn(dup, qq, 3)
+    io, do = oracle.knn(dup, qq, 3)
+    assert np.array_equal(ig, io) and np.array_equal(dg, do)
+
+
+def _gicp_pair(api, oracle, tgt, src, max_corr=None, it=64, eps=5e-4):
+    g, o = api.FastGICP(), oracle.FastGICP()
+    for x in (g, o):
+        x.setMaximumIterations(it)
+        x.setTransformationEpsilon(eps)
+        if max_corr is not None:
+            x.setMaxCorrespondenceDistance(max_corr)
+        x.setInputTarget(tgt)
+        x.setInputSource(src)
+    return g, o
+
+
+def _compare_gicp_align(g, o, guess=None):
+    g.align(guess)
+    o.align(guess)
+    r = g.result
+    assert (r.iterations, bool(r.converged)) == (o.nr_iterations, o.converged)
+    assert (r.evaluations, r.line_search_trials) == (o.stats["linearize_calls"], o.stats["error_calls"])
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD
+    assert g.getFitnessScore() == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+    np.testing.assert_allclose(g.getFinalHessian(), o.getFinalHessian(), rtol=1e-6, atol=1e-6 * np.abs(o.getFinalHessian()).max())
+
+
+def test_gicp_covariances_and_linearize(api, oracle, velodyne_pair):
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _gicp_pair(api, oracle, t2, s2)
+    for which in (0, 1):
+        np.testing.assert_allclose(g.covariances(which), o.covariances(which), rtol=1e-6, atol=1e-9)
+    T = velodyne_pair["relative"].copy()
+    T[:3, 3] += [0.1, -0.05, 0.02]
+    cg, Hg, bg, corrg = g.linearize(T)
+    co, Ho, bo, corro = o.linearize(T)
+    assert np.array_equal(corrg, corro)
+    assert cg == pytest.approx(co, rel=1e-10)
+    np.testing.assert_allclose(Hg, Ho, rtol=1e-9, atol=1e-9 * np.abs(Ho).max())
+    np.testing.assert_allclose(bg, bo, rtol=1e-9, atol=1e-9 * np.abs(bo).max())
+    for reg in (api.REG_NONE, api.REG_MIN_EIG, api.REG_NORMALIZED_MIN_EIG, api.REG_FROBENIUS):
+        g.setRegularizationMethod(reg)
+        o.setRegularizationMethod(reg)
+        g.setInputSource(s2[:3000])
+        o.setInputSource(s2[:3000])
+        cg_, co_ = g.covariances(0), o.covariances(0)
+        np.testing.assert_allclose(cg_, co_, rtol=1e-6, atol=1e-7 * np.abs(co_).max())
+
+
+def test_gicp_velodyne_align_parity(api, oracle, velodyne_pair):
+    """fast_gicp gtest recipe (gicp_test.cpp:55-65,147-201) + the four set/swap orderings."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _gicp_pair(api, oracle, t2, s2)
+    _compare_gicp_align(g, o)
+    t_err, r_err = pose_error(velodyne_pair["relative"], g.getFinalTransformation())
+    assert t_err < 0.05 and np.degrees(r_err) < 1.0 and g.hasConverged()
+    # backward
+    g, o = _gicp_pair(api, oracle, s2, t2)
+    _compare_gicp_align(g, o)
+    t_err, r_err = pose_error(velodyne_pair["relative"], np.linalg.inv(g.getFinalTransformation().astype(np.float64)))
+    assert t_err < 0.05 and np.degrees(r_err) < 1.0
+    # swap and set source
+    g, o = api.FastGICP(), oracle.FastGICP()
+    for x in (g, o):
+        x.setInputSource(t2)
+        x.swapSourceAndTarget()
+        x.setInputSource(s2)
+    _compare_gicp_align(g, o)
+    # swap and set target
+    g, o = api.FastGICP(), oracle.FastGICP()
+    for x in (g, o):
+        x.setInputTarget(s2)
+        x.swapSourceAndTarget()
+        x.setInputTarget(t2)
+    _compare_gicp_align(g, o)
+    # product parameters (lidar_scan_matcher.param.yaml: max_corr 2.0, eps 0.01) with a non-identity guess
+    g, o = _gicp_pair(api, oracle, t2, s2, max_corr=2.0, eps=0.01)
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.3, 0.0, 0.0]
+    _compare_gicp_align(g, o, guess)
+
+
+def test_gicp_cfg2_synthetic_odometry(api, oracle):
+    """BASELINE configs[2] in miniature: scan-to-scan GICP over consecutive synthetic 64-beam sweeps, VoxelGrid 0.25 m
+    (kitti.cpp:80-82), covariance reuse through swapSourceAndTarget (kitti.cpp:115-125)."""
+    from lidar_graph_slam_b200 import synth
+    sweeps, poses = synth.odometry_sequence(4)
+    ds = [oracle.voxel_grid(s, 0.25, range_min=1.0)["points"] for s in sweeps]
+    g, o = api.FastGICP(), oracle.FastGICP()
+    for x in (g, o):
+        x.setMaxCorrespondenceDistance(1.0)
+        x.setInputTarget(ds[0])
+    for k in range(1, len(ds)):
+        for x in (g, o):
+            x.setInputSource(ds[k])
+        _compare_gicp_align(g, o)
+        rel_true = np.linalg.inv(poses[k - 1]) @ poses[k]
+        t_err, r_err = pose_error(rel_true, g.getFinalTransformation())
+        assert t_err < 0.1 and r_err < np.radians(1.0)
+        for x in (g, o):
+            x.swapSourceAndTarget()
+
+
+def test_batch_loop_closure_matches_single_pair_runs(api, oracle):
+    """BASELINE configs[4] in miniature: the batch API equals per-pair runs of the oracle (VoxelGrid 0.5 m on the
+    submap, FastGICP with graph_based_slam.param.yaml parameters, fitness), independent of worker count."""
+    from lidar_graph_slam_b200 import synth
+    scans, submaps, corrections = synth.loop_pairs(n_pairs=4, n_keyframes=9, n_unique=2)
+    recs1 = api.batch_align(scans, submaps, method=api.METHOD_GICP, n_workers=1)
+    recs3 = api.batch_align(scans, submaps, method=api.METHOD_GICP, n_workers=3, pair_id0=100)
+    for i, (r1, r3) in enumerate(zip(recs1, recs3)):
+        assert list(r1.T) == list(r3.T) and r1.fitness == r3.fitness and r1.iterations == r3.iterations  # bitwise
+        assert r1.pair_id == i and r3.pair_id == 100 + i
+        o = oracle.FastGICP()
+        o.setMaximumIterations(100)
+        o.setTransformationEpsilon(0.01)
+        o.setMaxCorrespondenceDistance(2.0)
+        o.setInputTarget(oracle.voxel_grid(submaps[i], 0.5)["points"])
+        o.setInputSource(scans[i])
+        o.align()
+        T = np.array(r1.T, np.float32).reshape(4, 4, order="F")
+        t_err, r_err = pose_error(o.final_transformation, T)
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD
+        assert (r1.iterations, bool(r1.converged)) == (o.nr_iterations, o.converged)
+        assert r1.fitness == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+        t_err, r_err = pose_error(corrections[i], T)
+        assert t_err < 0.1 and r_err < np.radians(0.5)
+    recs_ndt = api.batch_align(scans[:2], submaps[:2], method=api.METHOD_NDT, n_workers=2)
+    for i, r in enumerate(recs_ndt):
+        o = oracle.NDT()
+        o.setMaximumIterations(100)
+        o.setTransformationEpsilon(0.01)
+        o.setInputTarget(oracle.voxel_grid(submaps[i], 0.5)["points"])
+        o.setInputSource(scans[i])
+        o.align()
+        T = np.array(r.T, np.float32).reshape(4, 4, order="F")
+        t_err, r_err = pose_error(o.final_transformation, T)
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD and r.iterations == o.nr_iterations
+        assert r.fitness == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+
+
+def test_device_resident_inputs(api, oracle, velodyne_pair):
+    """_dev entry points: clouds already in HBM (torch tensors) give the same results as host uploads."""
+    import torch
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g1 = api.NormalDistributionsTransform()
+    g2 = api.NormalDistributionsTransform()
+    g1.setInputTarget(td)
+    g1.setInputSource(sd)
+    g2.setInputTarget(torch.from_numpy(td).cuda())
+    g2.setInputSource(torch.from_numpy(sd).cuda())
+    g1.align()
+    g2.align()
+    assert np.array_equal(g1.getFinalTransformation(), g2.getFinalTransformation())
+    vg = api.VoxelGrid()
+    vg.setLeafSize(0.2)
+    vg.setInputCloud(torch.from_numpy(velodyne_pair["target"]).cuda())
+    out = vg.filter().cpu().numpy()
+    assert np.array_equal(out, td)
