@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LiDAR front-end hot path (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): NDT scan-to-map aligns per second, 120 000-point 64-beam sweep against a 1 000 000-point
+local map (configs[0]: DIRECT7, 1.0 m, step 0.1, eps 0.01, max_iter 64), synthetic data.
+One step = one align of one sweep against the resident map.  At N > 1 every rank runs its own sequence against its
+own map ("offline multi-sequence odometry", the north_star's partitioning of odometry): weak scaling, no data-path
+collective; the loop-closure batch (configs[4]) is measured next to it with its NCCL result gather and reported
+under "loop_closure".
+
+  value  aligns/s, sweeps already resident in HBM (set_source_dev + align), per-step CUDA events, L2 flushed
+         between steps outside the event pairs
+  e2e    aligns/s through the reference-facing call sequence with HOST buffers: setInputSource(pinned host sweep)
+         -> align -> getFinalTransformation, H2D of the sweep and D2H of the result inside the timed region
+  roofline  the dominant kernel (ndt_derivatives_kernel<true>): algorithmic bytes / CUDA-event duration
+  cpu_baseline  the oracle (CPU restatement of the reference's OpenMP path) on this box's host cores, bounded sample
+
+--impl reference times the reference's CPU path (the oracle port: the reference cannot be compiled here) on the
+same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "cfg0: NDT DIRECT7 res 1.0 m, 120000-pt 64-beam sweep -> 1000000-pt local map (20 keyframes, 0.2 m filtered)"
+NDT_PARAMS = dict(resolution=1.0, step=0.1, eps=0.01, max_iter=64)
+N_SWEEP_POOL = 6
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_workload(rank):
+    """Target map + a pool of source sweeps with perturbed guesses, distinct per rank (multi-sequence)."""
+    from lidar_graph_slam_b200 import synth
+    d = synth.ndt_scan_to_map(perturb_seed=1 + rank, seed=synth.SEED + 7919 * rank)
+    sweeps, guesses = [d["source"]], [d["guess"]]
+    rs = np.random.RandomState(100 + rank)
+    # further "scans" of the sequence: the same sweep geometry re-observed with fresh noise is not available without
+    # re-casting, so the pool perturbs the initial guess (what changes from scan to scan for the optimiser) and
+    # rotates through physically re-cast sweeps when present
+    for k in range(1, N_SWEEP_POOL):
+        dd = np.array([0.3, 0.3, 0.05, np.radians(0.5), np.radians(0.5), np.radians(2.0)]) * rs.uniform(-1, 1, 6)
+        P = synth.pose_matrix(dd[0], dd[1], dd[5], z=dd[2], roll=dd[3], pitch=dd[4])
+        sweeps.append(d["source"])
+        guesses.append((d["T_true"] @ P).astype(np.float32))
+    return d["target"], sweeps, guesses, d["T_true"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(target, sweeps, guesses, budget_s=20.0, threads=0):
+    """The oracle (kind 'port': CPU restatement of the reference's ndt_omp path) on the host cores, bounded sample."""
+    from oracle import pyoracle as O
+    nthreads = threads or O.max_threads()
+    n = O.NDT()
+    n.setNumThreads(nthreads)
+    n.setResolution(NDT_PARAMS["resolution"])
+    n.setStepSize(NDT_PARAMS["step"])
+    n.setTransformationEpsilon(NDT_PARAMS["eps"])
+    n.setMaximumIterations(NDT_PARAMS["max_iter"])
+    t0 = time.perf_counter()
+    n.setInputTarget(target)
+    t_build = time.perf_counter() - t0
+    done, t_align = 0, 0.0
+    while done < len(sweeps) and (done == 0 or t_align < budget_s):
+        n.setInputSource(sweeps[done])
+        t0 = time.perf_counter()
+        n.align(guesses[done])
+        t_align += time.perf_counter() - t0
+        done += 1
+    return dict(value=done / t_align, unit="aligns/s", cores=nthreads, kind="port",
+                sample="%d aligns of the cfg0 workload (oracle NDT, %d OpenMP threads); target build %.3f s not included" % (done, nthreads, t_build),
+                target_build_s=t_build, iterations_last=n.nr_iterations)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores, all threads, same workload."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+    target, sweeps, guesses, _ = make_workload(0)
+    nthreads = O.max_threads()
+    n = O.NDT()
+    n.setNumThreads(nthreads)
+    n.setResolution(NDT_PARAMS["resolution"])
+    n.setStepSize(NDT_PARAMS["step"])
+    n.setTransformationEpsilon(NDT_PARAMS["eps"])
+    n.setMaximumIterations(NDT_PARAMS["max_iter"])
+    n.setInputTarget(target)
+    n.setInputSource(sweeps[0])
+    t0 = time.perf_counter()
+    n.align(guesses[0])
+    t_one = time.perf_counter() - t0
+    # bound the whole run to a few minutes: a step is one align; cap the step count by a time budget
+    budget = float(os.environ.get("LGS_REF_BUDGET_S", 150))
+    warm = min(args.warmup, 1 if t_one > 5 else args.warmup)
+    steps = int(max(1, min(args.steps, budget / max(t_one, 1e-3))))
+    for w in range(max(0, warm - 1)):
+        n.setInputSource(sweeps[w % len(sweeps)])
+        n.align(guesses[w % len(sweeps)])
+    t0 = time.perf_counter()
+    for s in range(steps):
+        n.setInputSource(sweeps[s % len(sweeps)])
+        n.align(guesses[s % len(sweeps)])
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    line = {"impl": "reference", "metric": "ndt_scan_to_map_aligns_per_sec", "value": val, "unit": "aligns/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 terms / f64 accumulation",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "impl_note": "oracle port of pclomp::NDT (reference needs PCL/Eigen, unbuildable here)"},
+            "cpu_baseline": {"value": val, "unit": "aligns/s", "cores": nthreads, "kind": "port",
+                             "sample": "%d aligns of the cfg0 workload, %d OpenMP threads" % (steps, nthreads)},
+            "e2e": {"value": val, "unit": "aligns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def loop_closure_bench(rank, world, device, pairs_per_rank):
+    """configs[4] in miniature at N GPUs: GICP verification of (scan, submap) candidates, sharded by size, one NCCL
+    gather of the result records.  Returns pairs/s over all ranks (max-over-ranks time)."""
+    import torch
+    import torch.distributed as dist
+    from lidar_graph_slam_b200 import api, synth
+    from lidar_graph_slam_b200.distributed import gather_records, partition_pairs, records_to_array
+    n_total = pairs_per_rank * world
+    scans, submaps, _ = synth.loop_pairs(n_pairs=n_total, n_keyframes=41, n_azimuth=900, n_unique=2)
+    sizes = [len(a) + len(b) for a, b in zip(scans, submaps)]
+    mine = partition_pairs(sizes, rank, world)
+    my_scans, my_subs = [scans[i] for i in mine], [submaps[i] for i in mine]
+    api.batch_align(my_scans[:1], my_subs[:1], n_workers=1, device=device)  # warm-up (allocations, module load)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    recs = api.batch_align(my_scans, my_subs, method=api.METHOD_GICP, device=device, n_workers=4, pair_id0=0)
+    local = torch.from_numpy(records_to_array(recs)).cuda(device)
+    gathered = gather_records(local, n_total, torch.tensor(mine, dtype=torch.int64), rank, world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    conv = int(gathered[:, 19].sum().item())
+    return {"pairs_per_sec": n_total / tmax.item(), "n_pairs": n_total, "converged": conv, "method": "FastGICP k=20, max_corr 2.0, submap VoxelGrid 0.5 m",
+            "gather": "all_gather of %d x 26 f32 records (%s)" % (n_total, "nccl" if world > 1 else "single rank"),
+            "mean_scan_pts": float(np.mean([len(s) for s in scans])), "mean_submap_pts": float(np.mean([len(s) for s in submaps]))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 8), help="loop-closure pairs per rank (0 disables)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lidar_graph_slam_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    target, sweeps, guesses, T_true = make_workload(rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ctx = api.Context(local_rank, stream.cuda_stream)
+    ndt = api.NormalDistributionsTransform(ctx)
+    ndt.setResolution(NDT_PARAMS["resolution"])
+    ndt.setStepSize(NDT_PARAMS["step"])
+    ndt.setTransformationEpsilon(NDT_PARAMS["eps"])
+    ndt.setMaximumIterations(NDT_PARAMS["max_iter"])
+    ndt.setNeighborhoodSearchMethod(api.NDT_DIRECT7)
+
+    # target build (timed separately: setInputTarget = H2D of 1M points + voxelisation)
+    tgt_pinned = torch.from_numpy(target).pin_memory()
+    ndt.setInputTarget(tgt_pinned.numpy())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    ndt.setInputTarget(tgt_pinned.numpy())
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    target_build_ms = ev0.elapsed_time(ev1)
+    gi = ndt.grid_info()
+
+    sweeps_pinned = [torch.from_numpy(s).pin_memory() for s in sweeps]
+    sweeps_dev = [t.cuda(local_rank, non_blocking=True) for t in sweeps_pinned]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local_rank)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        ndt.setInputSource(sweeps_dev[i % len(sweeps_dev)])
+        ndt.align(guesses[i % len(guesses)])
+
+    def step_host(i):
+        ndt.setInputSource(sweeps_pinned[i % len(sweeps_pinned)].numpy())
+        ndt.align(guesses[i % len(guesses)])
+        return ndt.getFinalTransformation()
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        l0 = ctx.launch_count
+        evals = 0
+        for i in range(steps):
+            flush.zero_()  # L2 flush, outside the event pair
+            starts[i].record(stream)
+            fn(i)
+            stops[i].record(stream)
+            evals += ndt.result.evaluations + ndt.result.hessian_recomputes
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+        return ms, ctx.launch_count - l0, evals
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, evals_dev = timed(step_dev, K, W)
+    ms_host, _, evals_host = timed(step_host, K, W)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # accuracy sanity of the timed workload (not a parity test: those live in tests/)
+    E = np.linalg.inv(T_true) @ ndt.getFinalTransformation().astype(np.float64)
+    t_err = float(np.linalg.norm(E[:3, 3]))
+
+    # per-kernel timing pass for the roofline (CUDA events around every evaluation launch, same stream)
+    ndt.profile(True)
+    for i in range(min(K, 20)):
+        step_dev(i)
+    prof = ndt.profile(False)
+    n_src = prof["n_source"]
+    terms = prof["terms_last_eval"]
+    hbar = terms / max(n_src, 1)
+    alg_bytes = n_src * (16 + 7 * 8) + 40.0 * terms  # point float4 + 7 (key,slot) probes + h voxel records of 40 B
+    kern_ms = prof["hess_ms"] / max(prof["hess_launches"], 1)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    peak, peak_src = measured_peak_hbm()
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device="cuda:%d" % local_rank)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_host_max = t.tolist()
+    total_steps = K * world
+
+    loop = None
+    if args.loop_pairs > 0:
+        try:
+            loop = loop_closure_bench(rank, world, local_rank, args.loop_pairs)
+        except Exception as e:  # the headline line must still be printed
+            loop = {"error": repr(e)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(target, sweeps, guesses)
+
+    if rank == 0:
+        line = {
+            "metric": "ndt_scan_to_map_aligns_per_sec", "value": total_steps / (ms_dev_max * 1e-3), "unit": "aligns/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 terms / f64 accumulation", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ndt": NDT_PARAMS, "n_source": int(n_src), "n_target": int(target.shape[0]),
+                       "voxels": int(gi.n_voxels), "valid_voxels": int(gi.n_valid), "cell_table": "dense" if gi.dense else "hash",
+                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pairs); within an align the 1.9 MB sweep and the voxel table are re-read from L2 by design",
+                       "parallelism": "1 sequence per GPU (replicas, no collective)" if world > 1 else "single GPU",
+                       "evaluations_per_align": evals_dev / K, "target_build_ms": target_build_ms, "pose_error_m": t_err},
+            "e2e": {"value": total_steps / (ms_host_max * 1e-3), "unit": "aligns/s", "h2d_bytes_per_step": int(n_src) * 16 + 64,
+                    "d2h_bytes_per_step": int(round(evals_host / K * 44 * 8))},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "ndt_derivatives_kernel<true>", "kernel_ms": kern_ms, "launches_timed": prof["hess_launches"],
+                         "algorithmic_bytes": alg_bytes, "h_bar": hbar, "peak_source": peak_src,
+                         "other_kernels_ms": {"ndt_derivatives_kernel<false>": prof["grad_ms"] / max(prof["grad_launches"], 1),
+                                              "ndt_hessian_f64_kernel": prof["h64_ms"] / max(prof["h64_launches"], 1)}},
+            "cpu_baseline": cpu, "clocks": clocks, "loop_closure": loop,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

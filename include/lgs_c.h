@@ -150,6 +150,12 @@ int lgs_ndt_export_voxels(lgs_ndt* ndt, int32_t* idx, int32_t* nr_points, double
  * mode 2 = computeHessian (f64, NDT:539-644).  Outputs: score, g[6], H[36] row-major. */
 int lgs_ndt_derivatives(lgs_ndt* ndt, const float* T16, const double* p6, int32_t mode, double* score, double* g6, double* H36);
 
+/* measurement hook (bench.py roofline): returns and clears the CUDA-event timings gathered since the last
+ * call, then enables (1) / disables (0) per-launch timing of the evaluation kernels.  out8 = {launches, ms} for
+ * computeDerivatives with Hessian, gradient-only, and the f64 computeHessian kernel, then the number of accepted
+ * (point, voxel) terms of the last evaluation and the source size.  out8 may be NULL. */
+int lgs_ndt_profile(lgs_ndt* ndt, int32_t enable, double* out8);
+
 /* ------------------------------------------------------------------------------------------- */
 /* GICP: fast_gicp::FastGICP over LsqRegistration (FG.h:48-70, LSQ.h:48-60)                       */
 typedef struct lgs_gicp lgs_gicp;

@@ -241,6 +241,13 @@ class NormalDistributionsTransform(_Registration):
         check(self._L.lgs_ndt_calculate_score(self._h, tp, C.byref(s)))
         return s.value
 
+    def profile(self, enable):
+        """Measurement hook: returns the per-kernel CUDA-event timings gathered so far and (re)arms / disarms timing."""
+        out = np.zeros(8)
+        check(self._L.lgs_ndt_profile(self._h, 1 if enable else 0, out.ctypes.data_as(C.c_void_p)))
+        return dict(hess_launches=int(out[0]), hess_ms=out[1], grad_launches=int(out[2]), grad_ms=out[3], h64_launches=int(out[4]),
+                    h64_ms=out[5], terms_last_eval=out[6], n_source=int(out[7]))
+
     # parity hooks -------------------------------------------------------------------------------
     def grid_info(self):
         gi = NdtGridInfo()

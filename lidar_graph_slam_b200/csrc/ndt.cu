@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <utility>
+#include <vector>
 
 #include "math.cuh"
 #include "nn.cuh"
@@ -174,7 +176,7 @@ struct EvalParams {
 };
 
 constexpr int kEvalBlock = 128;
-constexpr int kNumAcc = 44;  // score, g[6], H[36], pad
+constexpr int kNumAcc = 44;  // score, g[6], H[36], term count
 
 // block-wide sum of K doubles held per thread -> partials[blockIdx][k]; the last block to finish adds the
 // per-block partials in block order (fixed tree => run-to-run reproducible) and writes result[k].
@@ -269,6 +271,7 @@ __device__ __forceinline__ void accumulate_cell(const EvalParams& P, const Point
   if (e > 1.0f || e < 0.0f || e != e) return;  // NDT:505-506
   e = static_cast<float>(static_cast<double>(e) * P.gauss_d1);
   acc[0] += static_cast<double>(score_inc);
+  acc[HESS ? 43 : 7] += 1.0;  // accepted (point, cell) terms: measurement only (algorithmic-bytes accounting)
 
   // CJ = c_inv4 * point_gradient4, columns 3..5 (columns 0..2 are the columns of C)
   float CJ3[3], CJ4[3], CJ5[3];
@@ -338,7 +341,7 @@ template <bool HESS>
 __global__ void __launch_bounds__(kEvalBlock) ndt_derivatives_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
                                                                    const VoxelRec* __restrict__ recs, double* __restrict__ partials,
                                                                    double* __restrict__ result, unsigned* __restrict__ counter) {
-  constexpr int K = HESS ? 43 : 7;
+  constexpr int K = HESS ? 44 : 8;
   double acc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = 0.0;
@@ -537,6 +540,10 @@ struct lgs_ndt {
   double gauss_d1 = 0, gauss_d2 = 0, gauss_d3 = 0;
   EvalParams P;
   int evals = 0, trials = 0, hess_recomputes = 0;
+  double last_terms = 0;
+  // optional per-kernel timing (bench.py roofline): CUDA event pairs around each evaluation launch
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];
 };
 
 namespace {
@@ -790,7 +797,7 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   P.gauss_d2 = n->gauss_d2;
   P.gauss_d2f = static_cast<float>(n->gauss_d2);
   fill_offsets(n->search, &P);
-  const int K = mode == 0 ? 43 : (mode == 1 ? 7 : 36);
+  const int K = mode == 0 ? 44 : (mode == 1 ? 8 : 36);
   if (score) *score = 0;
   if (g) std::fill(g, g + 6, 0.0);
   if (H) std::fill(H, H + 36, 0.0);
@@ -807,6 +814,12 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   CellTable ct = make_cell_table(n);
   const float4* src = n->source.as<float4>();
   const int ns = static_cast<int>(n->n_source);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (n->profiling) {
+    LGS_CUDA(cudaEventCreate(&ev0));
+    LGS_CUDA(cudaEventCreate(&ev1));
+    LGS_CUDA(cudaEventRecord(ev0, st));
+  }
   if (mode == 0)
     ndt_derivatives_kernel<true><<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->partials.as<double>(), result, counter);
   else if (mode == 1)
@@ -814,6 +827,10 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   else
     ndt_hessian_f64_kernel<<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->partials.as<double>(),
                                                        result, counter);
+  if (n->profiling) {
+    LGS_CUDA(cudaEventRecord(ev1, st));
+    n->prof_events[mode].emplace_back(ev0, ev1);
+  }
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   LGS_TRY(ctx->pin.reserve(kNumAcc * sizeof(double)));
@@ -826,6 +843,7 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     *score = h[0];
     memcpy(g, h + 1, 6 * sizeof(double));
     if (mode == 0) memcpy(H, h + 7, 36 * sizeof(double));
+    n->last_terms = h[mode == 0 ? 43 : 7];
   }
   return LGS_OK;
 }
@@ -1179,6 +1197,35 @@ int lgs_ndt_export_voxels(lgs_ndt* n, int32_t* idx, int32_t* nr_points, double* 
   if (cov) LGS_CUDA(cudaMemcpyAsync(cov, n->ex_cov.p, V * 72, cudaMemcpyDeviceToHost, st));
   if (icov) LGS_CUDA(cudaMemcpyAsync(icov, n->ex_icov.p, V * 72, cudaMemcpyDeviceToHost, st));
   LGS_CUDA(cudaStreamSynchronize(st));
+  return LGS_OK;
+}
+
+int lgs_ndt_profile(lgs_ndt* n, int32_t enable, double* out8) {
+  LGS_REQUIRE(n, "null argument");
+  LGS_TRY(use_device(n->ctx));
+  LGS_CUDA(cudaStreamSynchronize(n->ctx->stream));
+  if (out8) {
+    for (int m = 0; m < 3; m++) {
+      double ms = 0;
+      for (auto& pr : n->prof_events[m]) {
+        float t = 0;
+        cudaEventElapsedTime(&t, pr.first, pr.second);
+        ms += t;
+      }
+      out8[2 * m] = static_cast<double>(n->prof_events[m].size());
+      out8[2 * m + 1] = ms;
+    }
+    out8[6] = n->last_terms;
+    out8[7] = static_cast<double>(n->n_source);
+  }
+  for (int m = 0; m < 3; m++) {
+    for (auto& pr : n->prof_events[m]) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    n->prof_events[m].clear();
+  }
+  n->profiling = enable != 0;
   return LGS_OK;
 }
 

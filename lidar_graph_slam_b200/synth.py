@@ -140,8 +140,9 @@ def cast_sweep(world, pose, frame, n_beams=64, n_azimuth=1875, elev=(-24.8, 2.0)
             tt = tc[np.arange(m), j]
             upd = tt < tb
             # incidence: normal is radial in xy
-            hx = o[0] + tt * d[:, 0] - cc[j, 0]
-            hy = o[1] + tt * d[:, 1] - cc[j, 1]
+            tsafe = np.where(np.isfinite(tt), tt, 0.0)
+            hx = o[0] + tsafe * d[:, 0] - cc[j, 0]
+            hy = o[1] + tsafe * d[:, 1] - cc[j, 1]
             with np.errstate(divide="ignore", invalid="ignore"):
                 cosc = np.abs(hx * d[:, 0] + hy * d[:, 1]) / np.maximum(np.hypot(hx, hy), 1e-9)
             tb = np.where(upd, tt, tb)
