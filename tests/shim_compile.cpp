@@ -1,0 +1,39 @@
+// Compile-and-link check of the header-only C++ shim (include/lgs/registration.hpp) against liblgs_b200.so.
+// Mirrors the reference's call sequence (LSM:149,162-172; PPF:118-120).  Runs the calls only when a GPU exists.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "lgs/registration.hpp"
+
+int main(int argc, char** argv) {
+  const bool run = argc > 1 && std::strcmp(argv[1], "--run") == 0;
+  if (!run) {
+    std::printf("shim compiled; version %s\n", lgs_version());
+    return 0;
+  }
+  auto cloud = std::make_shared<lgs::PointCloud>();
+  for (int i = 0; i < 4000; i++) {
+    float a = 0.01f * i;
+    cloud->push_back(lgs::PointXYZI{10.0f * std::cos(a), 10.0f * std::sin(a), 0.001f * (i % 97), 1.0f, float(i % 255), 0, 0, 0});
+  }
+  lgs::VoxelGrid vg;
+  vg.setLeafSize(0.2f, 0.2f, 0.2f);
+  vg.setInputCloud(cloud);
+  lgs::PointCloud filtered;
+  vg.filter(filtered);
+  std::shared_ptr<lgs::Registration> registration = std::make_shared<lgs::NormalDistributionsTransform>();
+  auto ndt = std::static_pointer_cast<lgs::NormalDistributionsTransform>(registration);
+  ndt->setTransformationEpsilon(0.01);
+  ndt->setStepSize(0.1);
+  ndt->setResolution(1.0f);
+  ndt->setMaximumIterations(64);
+  ndt->setNeighborhoodSearchMethod(lgs::DIRECT7);
+  registration->setInputTarget(cloud);
+  registration->setInputSource(std::make_shared<lgs::PointCloud>(filtered));
+  lgs::PointCloud aligned;
+  registration->align(aligned);
+  std::printf("filtered %zu -> converged %d, iterations %d, fitness %.6f\n", filtered.size(), int(registration->hasConverged()),
+              ndt->getFinalNumIteration(), registration->getFitnessScore());
+  return registration->hasConverged() ? 0 : 1;
+}

@@ -397,3 +397,12 @@ def test_device_resident_inputs(api, oracle, velodyne_pair):
     vg.setInputCloud(torch.from_numpy(velodyne_pair["target"]).cuda())
     out = vg.filter().cpu().numpy()
     assert np.array_equal(out, td)
+
+
+def test_cpp_shim_runs_reference_call_sequence(api, tmp_path):
+    """The header-only C++ shim drives VoxelGrid + NDT through the reference's call order on the GPU."""
+    import subprocess
+    from test_oracle_cpu import _build_shim
+    exe = _build_shim(tmp_path)
+    out = subprocess.check_output([exe, "--run"]).decode()
+    assert "converged 1" in out, out

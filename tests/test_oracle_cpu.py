@@ -321,3 +321,22 @@ def test_gather_records_world2_gloo():
         p.join(60)
     for rank, col in got:
         assert col == [float(i) for i in range(13)], (rank, col)
+
+
+def _build_shim(tmpdir):
+    import subprocess
+    exe = os.path.join(str(tmpdir), "shim_test")
+    libdir = os.path.join(ROOT, "lidar_graph_slam_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "shim_compile.cpp"),
+                           "-o", exe, "-L" + libdir, "-l:liblgs_b200.so", "-Wl,-rpath," + libdir, "-ldl", "-lpthread", "-lrt"])
+    return exe
+
+
+def test_cpp_shim_compiles_and_links(tmp_path):
+    """include/lgs/registration.hpp (PCL method names over the C-ABI) builds against liblgs_b200.so with plain g++."""
+    import subprocess
+    from lidar_graph_slam_b200 import _lib
+    _lib.load()
+    exe = _build_shim(tmp_path)
+    out = subprocess.check_output([exe]).decode()
+    assert "shim compiled" in out
