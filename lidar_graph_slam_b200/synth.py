@@ -112,9 +112,12 @@ def cast_sweep(world, pose, frame, n_beams=64, n_azimuth=1875, elev=(-24.8, 2.0)
                 t1 = (bmax[None, :, :] - o[None, None, :]) * inv[:, None, :]
             tn = np.minimum(t0, t1)
             tf = np.maximum(t0, t1)
-            axis = np.argmax(tn, axis=2)
-            tnear = np.max(tn, axis=2)
-            tfar = np.min(tf, axis=2)
+            # reductions over the 3 slab axes written out (numpy's axis=2 reduce over a length-3 axis is very slow)
+            m01 = np.maximum(tn[:, :, 0], tn[:, :, 1])
+            tnear = np.maximum(m01, tn[:, :, 2])
+            axis = np.where(tn[:, :, 1] > tn[:, :, 0], 1, 0)
+            axis = np.where(tn[:, :, 2] > m01, 2, axis)
+            tfar = np.minimum(np.minimum(tf[:, :, 0], tf[:, :, 1]), tf[:, :, 2])
             hit = (tnear <= tfar) & (tnear > 1e-6)
             tnear = np.where(hit, tnear, np.inf)
             j = np.argmin(tnear, axis=1)
