@@ -23,7 +23,7 @@ COMMON = [
     # (thirdparty/ndt_omp/CMakeLists.txt:5-6).  Kernels that want FMA opt in with explicit fmaf().
     "-fmad=false",
     "-Xcompiler", "-fPIC", "-ccbin", CCBIN,
-]
+] + os.environ.get("LGS_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _stale(target, deps):

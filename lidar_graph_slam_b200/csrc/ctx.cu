@@ -1,4 +1,6 @@
 // Context, error reporting and cloud upload (host AoS records -> packed float4 xyzi in HBM).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace lgs {
@@ -55,6 +57,47 @@ int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst) 
   return LGS_OK;
 }
 
+int mailbox_next(lgs_ctx* ctx, Mailbox* mb) {
+  if (!ctx->mbox) {
+    void* p = nullptr;
+    LGS_CUDA(cudaHostAlloc(&p, sizeof(MailboxHost), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, sizeof(MailboxHost));
+    ctx->mbox = static_cast<MailboxHost*>(p);
+  }
+  void* dv = nullptr;
+  LGS_CUDA(cudaHostGetDevicePointer(&dv, ctx->mbox, 0));
+  MailboxHost* d = static_cast<MailboxHost*>(dv);
+  mb->v = d->v;
+  mb->seq = &d->seq;
+  mb->token = ++ctx->mbox_token;
+  return LGS_OK;
+}
+
+int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb) {
+  volatile unsigned long long* seq = &ctx->mbox->seq;
+  unsigned spins = 0;
+  while (*seq != mb.token) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0x3fffu) == 0) {
+      // a failed or finished-without-publishing launch must not hang the caller
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaErrorNotReady) continue;
+      if (e != cudaSuccess) {
+        set_error("kernel failed while waiting for its result: %s", cudaGetErrorString(e));
+        return LGS_ERR_CUDA;
+      }
+      if (*seq != mb.token) {
+        set_error("stream drained but the result mailbox was not written (token %llu)", mb.token);
+        return LGS_ERR_CUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return LGS_OK;
+}
+
 }  // namespace lgs
 
 extern "C" {
@@ -107,6 +150,7 @@ void lgs_ctx_destroy(lgs_ctx* c) {
   c->vg_out.release();
   c->vg_vidx.release();
   c->vg_rank.release();
+  if (c->mbox) cudaFreeHost(c->mbox);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }

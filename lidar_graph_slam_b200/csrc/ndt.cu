@@ -182,7 +182,7 @@ constexpr int kNumAcc = 44;  // score, g[6], H[36], term count
 // per-block partials in block order (fixed tree => run-to-run reproducible) and writes result[k].
 template <int K>
 __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double* __restrict__ partials, double* __restrict__ result,
-                                                       unsigned* __restrict__ counter) {
+                                                       unsigned* __restrict__ counter, const Mailbox& mb) {
   __shared__ double sm[kEvalBlock / 32][K];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -209,275 +209,33 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double
   __syncthreads();
   if (is_last) {
     __threadfence();
+    double v = 0;
     if (threadIdx.x < K) {
-      double v = 0;
-      for (unsigned b = 0; b < gridDim.x; b++) v += partials[static_cast<size_t>(b) * K + threadIdx.x];
+      for (unsigned b0 = 0; b0 < gridDim.x; b0 += 8) {  // eight independent loads in flight, added in block order
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = b0 + u < gridDim.x ? __ldcg(partials + static_cast<size_t>(b0 + u) * K + threadIdx.x) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) v += t[u];
+      }
       result[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *counter = 0;  // re-arm for the next launch on this stream
+    mailbox_publish<K>(mb, v);
   }
 }
 
-// ---- ndt_derivatives_kernel ----------------------------------------------------------------------------------
-// Persistent grid: one CTA of kDerivThreads per SM, every warp owns a contiguous, equally sized range of source
-// points (balanced to +-1 point, so there is no wave quantisation and no tail).  A warp walks its range in chunks of
-// 32 points:
-//   phase 1 (lane = point)      float4 load, f32 transform, voxel coordinates, up to 7 independent cell-table probes
-//                               per batch, per-point derivative tables (NDT:397-439) staged in shared memory;
-//   compaction                  the valid (point, voxel) pairs of the chunk are packed into a shared-memory list with a
-//                               warp prefix sum, so that
-//   phase 2 (lane = pair)       every lane evaluates one updateDerivatives term (NDT:483-536): no lane idles because
-//                               its point has fewer neighbours than another lane's.
-// Accumulators are f64 registers (score, g[6], upper triangle of H[21], term count); one warp-shuffle + shared-memory
-// reduction per CTA at the end, then the last CTA adds the per-CTA partials in CTA order with coalesced row loads.
-// Every step is a fixed function of (n, grid), so sums are run-to-run reproducible.
-constexpr int kDerivThreads = 384;
-constexpr int kDerivWarps = kDerivThreads / 32;
-constexpr int kBatch = 7;          // cell probes per point per pass (DIRECT7 = one pass, DIRECT26 = four)
-constexpr int kRow = 32;           // padded row length of the partials matrix
-constexpr int kTab = 26;           // floats staged per point: xt[3] + 8 gradient entries + 15 Hessian entries
+}  // namespace lgs
 
-struct DerivScratch {
-  float tab[kDerivWarps][kTab][32];       // [warp][field][lane]: conflict-free (bank = lane), broadcast for equal lanes
-  int pair_slot[kDerivWarps][kBatch * 32];
-  unsigned char pair_lane[kDerivWarps][kBatch * 32];
-};
+#include "ndt_deriv.cuh"
 
-// index of (i,j), i <= j, in the packed upper triangle
-__host__ __device__ constexpr int tri(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
-
-// updateDerivatives (NDT:483-536) for one (point, voxel) pair.  Products of the reference's padded 4x4 / 4x6 f32
-// matrices are written out with their structural zeros and ones removed; every surviving operation keeps the
-// reference's order, so each f32 term is bit-identical to the full-matrix evaluation.  Only the upper triangle of
-// the Hessian is formed (entry (i,j), i <= j, exactly as the reference forms it); the host mirrors it.  The
-// reference's (j,i) entry differs from its (i,j) entry by f32 rounding only (~1e-7 per term, ~1e-9 after the sum).
-template <bool HESS>
-__device__ __forceinline__ void accumulate_term(const EvalParams& P, const float (*__restrict__ tab)[32], int pl, const VoxelRec& r,
-                                                double* __restrict__ acc) {
-  const float xt = tab[0][pl], yt = tab[1][pl], zt = tab[2][pl];
-  // x_trans = Vector3d(x_trans_pt) - mean (f64), then cast to f32 (NDT:259-262,491)
-  const float x0 = static_cast<float>(static_cast<double>(xt) - r.mean[0]);
-  const float x1 = static_cast<float>(static_cast<double>(yt) - r.mean[1]);
-  const float x2 = static_cast<float>(static_cast<double>(zt) - r.mean[2]);
-  const float* C = r.icov;
-  const float xC0 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[0]), __fmul_rn(x1, C[3])), __fmul_rn(x2, C[6]));
-  const float xC1 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[1]), __fmul_rn(x1, C[4])), __fmul_rn(x2, C[7]));
-  const float xC2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, C[2]), __fmul_rn(x1, C[5])), __fmul_rn(x2, C[8]));
-  const float q = __fadd_rn(__fadd_rn(__fmul_rn(x0, xC0), __fmul_rn(x1, xC1)), __fmul_rn(x2, xC2));
-  // exp of an f32 argument, evaluated in f64 and rounded (NDT:498)
-  float e = static_cast<float>(exp(static_cast<double>(__fmul_rn(__fmul_rn(-P.gauss_d2f, q), 0.5f))));
-  const float score_inc = static_cast<float>(-P.gauss_d1 * static_cast<double>(e));
-  e = __fmul_rn(P.gauss_d2f, e);
-  if (e > 1.0f || e < 0.0f || e != e) return;  // NDT:505-506
-  e = static_cast<float>(static_cast<double>(e) * P.gauss_d1);
-  acc[0] += static_cast<double>(score_inc);
-  acc[HESS ? 28 : 7] += 1.0;  // accepted terms: measurement only (algorithmic-bytes accounting)
-
-  const float J13 = tab[3][pl], J23 = tab[4][pl], J04 = tab[5][pl], J14 = tab[6][pl], J24 = tab[7][pl];
-  const float J05 = tab[8][pl], J15 = tab[9][pl], J25 = tab[10][pl];
-  // CJ = c_inv4 * point_gradient4: columns 0..2 are the columns of C, columns 3..5 below
-  float CJ[3][6];
-#pragma unroll
-  for (int rr = 0; rr < 3; rr++) {
-    CJ[rr][0] = C[rr * 3 + 0];
-    CJ[rr][1] = C[rr * 3 + 1];
-    CJ[rr][2] = C[rr * 3 + 2];
-    CJ[rr][3] = __fadd_rn(__fmul_rn(C[rr * 3 + 1], J13), __fmul_rn(C[rr * 3 + 2], J23));
-    CJ[rr][4] = __fadd_rn(__fadd_rn(__fmul_rn(C[rr * 3 + 0], J04), __fmul_rn(C[rr * 3 + 1], J14)), __fmul_rn(C[rr * 3 + 2], J24));
-    CJ[rr][5] = __fadd_rn(__fadd_rn(__fmul_rn(C[rr * 3 + 0], J05), __fmul_rn(C[rr * 3 + 1], J15)), __fmul_rn(C[rr * 3 + 2], J25));
-  }
-  float g[6];
-  g[0] = xC0;
-  g[1] = xC1;
-  g[2] = xC2;
-#pragma unroll
-  for (int c = 3; c < 6; c++) g[c] = __fadd_rn(__fadd_rn(__fmul_rn(x0, CJ[0][c]), __fmul_rn(x1, CJ[1][c])), __fmul_rn(x2, CJ[2][c]));
-#pragma unroll
-  for (int c = 0; c < 6; c++) acc[1 + c] += static_cast<double>(__fmul_rn(e, g[c]));
-
-  if (HESS) {
-    // x_trans4_x_c_inv4 * point_hessian_ blocks (i,j), i,j in 3..5: a b c / b d e / c e f  (NDT:429-437)
-    const float xa = __fadd_rn(__fmul_rn(xC1, tab[11][pl]), __fmul_rn(xC2, tab[12][pl]));
-    const float xb = __fadd_rn(__fmul_rn(xC1, tab[13][pl]), __fmul_rn(xC2, tab[14][pl]));
-    const float xc = __fadd_rn(__fmul_rn(xC1, tab[15][pl]), __fmul_rn(xC2, tab[16][pl]));
-    const float xd = __fadd_rn(__fadd_rn(__fmul_rn(xC0, tab[17][pl]), __fmul_rn(xC1, tab[18][pl])), __fmul_rn(xC2, tab[19][pl]));
-    const float xe = __fadd_rn(__fadd_rn(__fmul_rn(xC0, tab[20][pl]), __fmul_rn(xC1, tab[21][pl])), __fmul_rn(xC2, tab[22][pl]));
-    const float xf = __fadd_rn(__fadd_rn(__fmul_rn(xC0, tab[23][pl]), __fmul_rn(xC1, tab[24][pl])), __fmul_rn(xC2, tab[25][pl]));
-    const float xCH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
-    const float nd2 = -P.gauss_d2f;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const float ngi = __fmul_rn(nd2, g[i]);
-#pragma unroll
-      for (int j = i; j < 6; j++) {
-        // JCJ(j,i) = point_gradient4.col(j) . CJ.col(i)
-        float jcj;
-        if (j < 3) {
-          jcj = CJ[j][i];
-        } else if (j == 3) {
-          jcj = __fadd_rn(__fmul_rn(J13, CJ[1][i]), __fmul_rn(J23, CJ[2][i]));
-        } else if (j == 4) {
-          jcj = __fadd_rn(__fadd_rn(__fmul_rn(J04, CJ[0][i]), __fmul_rn(J14, CJ[1][i])), __fmul_rn(J24, CJ[2][i]));
-        } else {
-          jcj = __fadd_rn(__fadd_rn(__fmul_rn(J05, CJ[0][i]), __fmul_rn(J15, CJ[1][i])), __fmul_rn(J25, CJ[2][i]));
-        }
-        float inner = __fmul_rn(ngi, g[j]);
-        if (i >= 3) inner = __fadd_rn(inner, xCH[i - 3][j - 3]);
-        inner = __fadd_rn(inner, jcj);
-        acc[7 + tri(i, j)] += static_cast<double>(__fmul_rn(e, inner));
-      }
-    }
-  }
-}
-
-// CTA reduction of K per-thread doubles -> partials[cta][k] (row stride kRow); the last CTA to arrive sums the rows
-// in CTA order (4 warps take interleaved row subsets with coalesced 256-byte row loads, then a fixed 4-way combine).
-template <int K, int NT>
-__device__ __forceinline__ void cta_reduce_and_finish(double (&acc)[K], double* __restrict__ partials, double* __restrict__ result,
-                                                     unsigned* __restrict__ counter) {
-  static_assert(K <= kRow, "row too long");
-  constexpr int NW = NT / 32;
-  __shared__ double sm[NW][kRow];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    double v = acc[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) sm[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kRow) {
-    double v = 0;
-    if (threadIdx.x < K) {
-#pragma unroll
-      for (int w = 0; w < NW; w++) v += sm[w][threadIdx.x];
-    }
-    partials[static_cast<size_t>(blockIdx.x) * kRow + threadIdx.x] = v;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    if (warp < 4) {
-      double v = 0;
-      for (unsigned b = warp; b < gridDim.x; b += 4) v += __ldcg(partials + static_cast<size_t>(b) * kRow + lane);
-      sm[warp][lane] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) result[threadIdx.x] = ((sm[0][threadIdx.x] + sm[1][threadIdx.x]) + sm[2][threadIdx.x]) + sm[3][threadIdx.x];
-    if (threadIdx.x == 0) *counter = 0;  // re-arm for the next launch on this stream
-  }
-}
-
-template <bool HESS>
-__global__ void __launch_bounds__(kDerivThreads, 1) ndt_derivatives_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
-                                                                         const VoxelRec* __restrict__ recs, double* __restrict__ partials,
-                                                                         double* __restrict__ result, unsigned* __restrict__ counter) {
-  constexpr int K = HESS ? 29 : 8;
-  extern __shared__ __align__(16) unsigned char deriv_smem[];
-  DerivScratch& S = *reinterpret_cast<DerivScratch*>(deriv_smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float(*tab)[32] = S.tab[warp];
-  int* pair_slot = S.pair_slot[warp];
-  unsigned char* pair_lane = S.pair_lane[warp];
-
-  double acc[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = 0.0;
-
-  // contiguous, balanced range of this warp
-  const long long total_warps = static_cast<long long>(gridDim.x) * kDerivWarps;
-  const long long gw = static_cast<long long>(blockIdx.x) * kDerivWarps + warp;
-  const int begin = static_cast<int>((static_cast<long long>(n) * gw) / total_warps);
-  const int end = static_cast<int>((static_cast<long long>(n) * (gw + 1)) / total_warps);
-
-  for (int base = begin; base < end; base += 32) {
-    const int i = base + lane;
-    const bool live = i < end;
-    int ix = 0, iy = 0, iz = 0;
-    if (live) {
-      const float4 p = src[i];
-      const float3 xt = transform_pcl(P.T, p.x, p.y, p.z);
-      // getNeighborhoodAtPoint (VGC:379-381): ijk = floor(x / leaf) with an IEEE f32 division
-      ix = static_cast<int>(floorf(__fdiv_rn(xt.x, ct.leaf[0])));
-      iy = static_cast<int>(floorf(__fdiv_rn(xt.y, ct.leaf[1])));
-      iz = static_cast<int>(floorf(__fdiv_rn(xt.z, ct.leaf[2])));
-      tab[0][lane] = xt.x;
-      tab[1][lane] = xt.y;
-      tab[2][lane] = xt.z;
-      // rows of (j_ang * x4) and (h_ang * x4) with x4 = (x,y,z,0): ((r0*x + r1*y) + r2*z) + 0   (NDT:404,417)
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        tab[3 + r][lane] = __fadd_rn(__fadd_rn(__fmul_rn(P.j_ang[r][0], p.x), __fmul_rn(P.j_ang[r][1], p.y)), __fmul_rn(P.j_ang[r][2], p.z));
-      if (HESS) {
-        // a = (0, h0, h1), b = (0, h2, h3), c = (0, h4, h5), d = (h6..8), e = (h9..11), f = (h12..14)
-#pragma unroll
-        for (int r = 0; r < 15; r++)
-          tab[11 + r][lane] = __fadd_rn(__fadd_rn(__fmul_rn(P.h_ang[r][0], p.x), __fmul_rn(P.h_ang[r][1], p.y)), __fmul_rn(P.h_ang[r][2], p.z));
-      }
-    }
-    for (int ob = 0; ob < P.n_offsets; ob += kBatch) {
-      // probes of this batch: issue all table loads before looking at any result
-      int slots[kBatch];
-#pragma unroll
-      for (int o = 0; o < kBatch; o++) {
-        slots[o] = -1;
-        if (live && ob + o < P.n_offsets) {
-          const int cx = ix + P.off[ob + o][0], cy = iy + P.off[ob + o][1], cz = iz + P.off[ob + o][2];
-          if (cx >= ct.min_b[0] && cx <= ct.max_b[0] && cy >= ct.min_b[1] && cy <= ct.max_b[1] && cz >= ct.min_b[2] && cz <= ct.max_b[2]) {
-            const int lin = (cx - ct.min_b[0]) * ct.mul[0] + (cy - ct.min_b[1]) * ct.mul[1] + (cz - ct.min_b[2]) * ct.mul[2];
-            slots[o] = cell_lookup(ct, lin);
-          }
-        }
-      }
-      int cnt = 0;
-#pragma unroll
-      for (int o = 0; o < kBatch; o++) cnt += slots[o] >= 0 ? 1 : 0;
-      // exclusive warp prefix sum of cnt -> position of this lane's pairs in the list (lane order, then probe order)
-      int pos = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, pos, d);
-        if (lane >= d) pos += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, pos, 31);
-      pos -= cnt;
-#pragma unroll
-      for (int o = 0; o < kBatch; o++) {
-        if (slots[o] >= 0) {
-          pair_slot[pos] = slots[o];
-          pair_lane[pos] = static_cast<unsigned char>(lane);
-          pos++;
-        }
-      }
-      __syncwarp();
-      for (int t = lane; t < total; t += 32) {
-        const int slot = pair_slot[t];
-        const int pl = pair_lane[t];
-        VoxelRec r;
-        const uint4* rp = reinterpret_cast<const uint4*>(recs + slot);
-        uint4* rw = reinterpret_cast<uint4*>(&r);
-        rw[0] = __ldg(rp + 0);
-        rw[1] = __ldg(rp + 1);
-        rw[2] = __ldg(rp + 2);
-        rw[3] = __ldg(rp + 3);
-        accumulate_term<HESS>(P, tab, pl, r, acc);
-      }
-      __syncwarp();
-    }
-  }
-  cta_reduce_and_finish<K, kDerivThreads>(acc, partials, result, counter);
-}
+namespace lgs {
 
 // computeHessian / updateHessian (NDT:539-644) with the f64 point derivatives (NDT:443-480)
 __global__ void __launch_bounds__(kEvalBlock) ndt_hessian_f64_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
                                                                    const double* __restrict__ vmean, const double* __restrict__ vicov,
                                                                    double* __restrict__ partials, double* __restrict__ result,
-                                                                   unsigned* __restrict__ counter) {
+                                                                   unsigned* __restrict__ counter, const Mailbox mb) {
   double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; k++) acc[k] = 0.0;
@@ -554,13 +312,13 @@ __global__ void __launch_bounds__(kEvalBlock) ndt_hessian_f64_kernel(const float
       }
     }
   }
-  block_reduce_and_finish<36>(acc, partials, result, counter);
+  block_reduce_and_finish<36>(acc, partials, result, counter, mb);
 }
 
 // calculateScore (NDT:934-982)
 __global__ void __launch_bounds__(kEvalBlock) ndt_score_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
                                                              const double* __restrict__ vmean, const double* __restrict__ vicov, double gauss_d3,
-                                                             double* __restrict__ partials, double* __restrict__ result, unsigned* __restrict__ counter) {
+                                                             double* __restrict__ partials, double* __restrict__ result, unsigned* __restrict__ counter, const Mailbox mb) {
   double acc[1] = {0.0};
   auto s3 = [](double a, double b, double c) { return a + (b + c); };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -589,7 +347,7 @@ __global__ void __launch_bounds__(kEvalBlock) ndt_score_kernel(const float4* __r
       acc[0] += score_inc / cnt;
     }
   }
-  block_reduce_and_finish<1>(acc, partials, result, counter);
+  block_reduce_and_finish<1>(acc, partials, result, counter, mb);
 }
 
 __global__ void __launch_bounds__(256) transform_cloud_kernel(const float4* __restrict__ src, int64_t n, EvalParams P, float4* __restrict__ out) {
@@ -909,6 +667,8 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   CellTable ct = make_cell_table(n);
   const float4* src = n->source.as<float4>();
   const int ns = static_cast<int>(n->n_source);
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (n->profiling) {
     LGS_CUDA(cudaEventCreate(&ev0));
@@ -917,27 +677,41 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   }
   static bool smem_opt_in = false;  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per process)
   if (!smem_opt_in) {
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(DerivScratch))));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(DerivScratch))));
+    const int smem = static_cast<int>(sizeof(DerivSmem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_opt_in = true;
   }
-  if (mode == 0)
-    ndt_derivatives_kernel<true><<<kNumSMs, kDerivThreads, sizeof(DerivScratch), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->partials.as<double>(), result, counter);
-  else if (mode == 1)
-    ndt_derivatives_kernel<false><<<kNumSMs, kDerivThreads, sizeof(DerivScratch), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->partials.as<double>(), result, counter);
-  else
+  if (mode != 2) {
+    // one CTA per SM (fewer when the cloud has fewer rounds of 32 points than SMs)
+    const int dgrid = std::max(1, std::min(kNumSMs, (ns + 31) / 32));
+    const u64 one2 = 0x3f8000003f800000ull;  // (1.0f, 1.0f): see ndt_deriv.cuh
+    const bool d7 = n->search == LGS_NDT_DIRECT7;
+    VoxelRec* rc = n->recs.as<VoxelRec>();
+    double* pt = n->partials.as<double>();
+    if (mode == 0 && d7)
+      ndt_derivatives_kernel<true, true><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
+    else if (mode == 0)
+      ndt_derivatives_kernel<true, false><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
+    else if (d7)
+      ndt_derivatives_kernel<false, true><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
+    else
+      ndt_derivatives_kernel<false, false><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
+  } else {
     ndt_hessian_f64_kernel<<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->partials.as<double>(),
-                                                       result, counter);
+                                                       result, counter, mb);
+  }
   if (n->profiling) {
     LGS_CUDA(cudaEventRecord(ev1, st));
     n->prof_events[mode].emplace_back(ev0, ev1);
   }
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
-  LGS_TRY(ctx->pin.reserve(kNumAcc * sizeof(double)));
-  double* h = ctx->pin.as<double>();
-  LGS_CUDA(cudaMemcpyAsync(h, result, K * sizeof(double), cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
+  // the last CTA publishes the K sums to the host mailbox; no D2H copy, no stream synchronisation
+  LGS_TRY(mailbox_wait(ctx, mb));
+  const double* h = ctx->mbox->v;
   if (mode == 2) {
     memcpy(H, h, 36 * sizeof(double));
   } else {
@@ -1257,13 +1031,14 @@ int lgs_ndt_calculate_score(lgs_ndt* n, const float* T16, double* score) {
     }
     double* result = n->result.as<double>();
     unsigned* counter = reinterpret_cast<unsigned*>(result + kNumAcc);
+    Mailbox mb;
+    LGS_TRY(mailbox_next(ctx, &mb));
     ndt_score_kernel<<<grid, kEvalBlock, 0, st>>>(n->source.as<float4>(), static_cast<int>(n->n_source), P, make_cell_table(n),
-                                                 n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->gauss_d3, n->partials.as<double>(), result, counter);
+                                                 n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->gauss_d3, n->partials.as<double>(), result, counter, mb);
     ctx->launches++;
-    LGS_TRY(ctx->pin.reserve(64));
-    LGS_CUDA(cudaMemcpyAsync(ctx->pin.p, result, sizeof(double), cudaMemcpyDeviceToHost, st));
-    LGS_CUDA(cudaStreamSynchronize(st));
-    *score = ctx->pin.as<double>()[0];
+    LGS_CUDA(cudaGetLastError());
+    LGS_TRY(mailbox_wait(ctx, mb));
+    *score = ctx->mbox->v[0];
   }
   *score /= static_cast<double>(n->n_source);
   return LGS_OK;
@@ -1332,6 +1107,15 @@ int lgs_ndt_profile(lgs_ndt* n, int32_t enable, double* out8) {
   n->profiling = enable != 0;
   return LGS_OK;
 }
+
+#ifdef LGS_DERIV_TRACE
+// development aid: per-CTA phase stamps of the last derivative launch (see ndt_deriv.cuh), 8 doubles per CTA
+int lgs_ndt_debug_trace(lgs_ndt* n, double* out, int32_t n_cta) {
+  LGS_TRY(use_device(n->ctx));
+  LGS_CUDA(cudaMemcpy(out, n->partials.as<double>() + static_cast<size_t>(n_cta) * kRow, sizeof(double) * 8 * n_cta, cudaMemcpyDeviceToHost));
+  return LGS_OK;
+}
+#endif
 
 int lgs_ndt_derivatives(lgs_ndt* n, const float* T16, const double* p6, int32_t mode, double* score, double* g6, double* H36) {
   LGS_REQUIRE(n && T16 && p6 && H36, "null argument");
