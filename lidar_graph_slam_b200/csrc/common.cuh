@@ -101,17 +101,21 @@ struct PinnedBuf {
 };
 
 // Result mailbox: a small block of host memory (pinned, mapped into the device address space) that the last CTA of
-// a reduction kernel writes its result into, followed by a sequence token.  The host polls the token instead of
-// issuing a D2H copy and a stream synchronisation: one PCIe write (~1-2 us) replaces ~15-25 us of copy + sync
-// latency per Gauss-Newton / line-search evaluation.
-constexpr int kMailboxDoubles = 48;
+// a reduction kernel writes its result into.  Every value travels as one 16-byte record {value, token} written with
+// a single 128-bit store, so each record validates itself (a 16-byte aligned record lies in one cache line and one
+// PCIe write; the host reads the token first and the value after it): no fence, no flag, no D2H copy and no stream
+// synchronisation - one posted PCIe write replaces ~15-25 us of copy + sync latency per Gauss-Newton / line-search
+// evaluation.
+constexpr int kMailboxRecords = 48;
+struct MailboxRecord {
+  double v;
+  unsigned long long token;
+};
 struct MailboxHost {
-  double v[kMailboxDoubles];
-  unsigned long long seq;
+  MailboxRecord r[kMailboxRecords];
 };
 struct Mailbox {  // kernel argument
-  double* v;
-  unsigned long long* seq;
+  MailboxRecord* r;
   unsigned long long token;
 };
 
@@ -144,10 +148,10 @@ int upload_cloud(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes,
 // Copy an already packed device cloud into dst (device to device).
 int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst);
 
-// Next mailbox token + kernel argument; mailbox_wait spins until the kernel publishes that token (checking the
-// stream for errors now and then) and leaves the result in ctx->mbox->v.
+// Next mailbox token + kernel argument; mailbox_wait spins until the kernel has published k records with that token
+// (checking the stream for errors now and then) and copies the values to out.
 int mailbox_next(lgs_ctx* ctx, Mailbox* mb);
-int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb);
+int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb, int k, double* out);
 
 inline int grid_for(int64_t n, int block) { return static_cast<int>((n + block - 1) / block); }
 
@@ -166,15 +170,14 @@ __host__ __device__ __forceinline__ float dec_f_host(unsigned u) {
 
 // pcl::transformPointCloud order (PCL >= 1.10): c0*x + (c1*y + (c2*z + c3)), explicit rn ops so the
 // compiler can neither contract nor reassociate.  T column-major.
-// publish K doubles (threads 0..K-1 hold them) to the mailbox; must be called by every thread of the CTA
+// publish K doubles (threads 0..K-1 hold them) to the mailbox: one 128-bit store per value
 template <int K>
 __device__ __forceinline__ void mailbox_publish(const Mailbox& mb, double v) {
+  static_assert(K <= kMailboxRecords, "mailbox too small");
   if (threadIdx.x < K) {
-    mb.v[threadIdx.x] = v;
-    __threadfence_system();
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mb.r + threadIdx.x), "l"(bits), "l"(mb.token) : "memory");
   }
-  __syncthreads();
-  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(mb.seq) = mb.token;
 }
 
 __device__ __forceinline__ float3 transform_pcl(const float* __restrict__ T, float x, float y, float z) {

@@ -66,35 +66,36 @@ int mailbox_next(lgs_ctx* ctx, Mailbox* mb) {
   }
   void* dv = nullptr;
   LGS_CUDA(cudaHostGetDevicePointer(&dv, ctx->mbox, 0));
-  MailboxHost* d = static_cast<MailboxHost*>(dv);
-  mb->v = d->v;
-  mb->seq = &d->seq;
+  mb->r = static_cast<MailboxHost*>(dv)->r;
   mb->token = ++ctx->mbox_token;
   return LGS_OK;
 }
 
-int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb) {
-  volatile unsigned long long* seq = &ctx->mbox->seq;
+int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb, int k, double* out) {
+  const volatile MailboxRecord* r = ctx->mbox->r;
   unsigned spins = 0;
-  while (*seq != mb.token) {
+  for (int i = 0; i < k; i++) {
+    while (r[i].token != mb.token) {
 #if defined(__x86_64__) || defined(__i386__)
-    __builtin_ia32_pause();
+      __builtin_ia32_pause();
 #endif
-    if ((++spins & 0x3fffu) == 0) {
-      // a failed or finished-without-publishing launch must not hang the caller
-      cudaError_t e = cudaStreamQuery(ctx->stream);
-      if (e == cudaErrorNotReady) continue;
-      if (e != cudaSuccess) {
-        set_error("kernel failed while waiting for its result: %s", cudaGetErrorString(e));
-        return LGS_ERR_CUDA;
-      }
-      if (*seq != mb.token) {
-        set_error("stream drained but the result mailbox was not written (token %llu)", mb.token);
-        return LGS_ERR_CUDA;
+      if ((++spins & 0x3fffu) == 0) {
+        // a failed or finished-without-publishing launch must not hang the caller
+        cudaError_t e = cudaStreamQuery(ctx->stream);
+        if (e == cudaErrorNotReady) continue;
+        if (e != cudaSuccess) {
+          set_error("kernel failed while waiting for its result: %s", cudaGetErrorString(e));
+          return LGS_ERR_CUDA;
+        }
+        if (r[i].token != mb.token) {
+          set_error("stream drained but the result mailbox was not written (token %llu, record %d)", mb.token, i);
+          return LGS_ERR_CUDA;
+        }
       }
     }
+    std::atomic_thread_fence(std::memory_order_acquire);  // token before value
+    out[i] = r[i].v;
   }
-  std::atomic_thread_fence(std::memory_order_acquire);
   return LGS_OK;
 }
 

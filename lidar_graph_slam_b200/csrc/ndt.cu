@@ -39,6 +39,8 @@ struct CellTable {
   const int* hkeys;     // hash keys (-1 = empty)
   unsigned hmask;
   float leaf[3];
+  float inv_leaf[3];    // exact reciprocals when every leaf is a power of two (leaf_pow2): x / leaf == x * inv_leaf bit for bit
+  int leaf_pow2;
   int min_b[3], max_b[3], mul[3];
 };
 
@@ -567,7 +569,10 @@ CellTable make_cell_table(const lgs_ndt* n) {
   ct.table = n->table.as<int>();
   ct.hkeys = n->hkeys.as<int>();
   ct.hmask = n->hmask;
+  int mant_exp = 0;
+  ct.leaf_pow2 = std::frexp(n->resolution, &mant_exp) == 0.5f && mant_exp > -100 && mant_exp < 100 ? 1 : 0;
   for (int a = 0; a < 3; a++) {
+    ct.inv_leaf[a] = 1.0f / n->resolution;
     ct.leaf[a] = n->resolution;
     ct.min_b[a] = n->min_b[a];
     ct.max_b[a] = n->max_b[a];
@@ -710,8 +715,8 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   // the last CTA publishes the K sums to the host mailbox; no D2H copy, no stream synchronisation
-  LGS_TRY(mailbox_wait(ctx, mb));
-  const double* h = ctx->mbox->v;
+  double h[kMailboxRecords];
+  LGS_TRY(mailbox_wait(ctx, mb, K, h));
   if (mode == 2) {
     memcpy(H, h, 36 * sizeof(double));
   } else {
@@ -1037,8 +1042,7 @@ int lgs_ndt_calculate_score(lgs_ndt* n, const float* T16, double* score) {
                                                  n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->gauss_d3, n->partials.as<double>(), result, counter, mb);
     ctx->launches++;
     LGS_CUDA(cudaGetLastError());
-    LGS_TRY(mailbox_wait(ctx, mb));
-    *score = ctx->mbox->v[0];
+    LGS_TRY(mailbox_wait(ctx, mb, 1, score));
   }
   *score /= static_cast<double>(n->n_source);
   return LGS_OK;
