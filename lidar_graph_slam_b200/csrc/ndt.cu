@@ -233,90 +233,6 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double
 
 namespace lgs {
 
-// computeHessian / updateHessian (NDT:539-644) with the f64 point derivatives (NDT:443-480)
-__global__ void __launch_bounds__(kEvalBlock) ndt_hessian_f64_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
-                                                                   const double* __restrict__ vmean, const double* __restrict__ vicov,
-                                                                   double* __restrict__ partials, double* __restrict__ result,
-                                                                   unsigned* __restrict__ counter, const Mailbox mb) {
-  double acc[36];
-#pragma unroll
-  for (int k = 0; k < 36; k++) acc[k] = 0.0;
-  auto s3 = [](double a, double b, double c) { return a + (b + c); };  // Eigen's unrolled 3-element reduction order
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = src[i];
-    const float3 xt = transform_pcl(P.T, p.x, p.y, p.z);
-    const int ix = static_cast<int>(floorf(__fdiv_rn(xt.x, ct.leaf[0])));
-    const int iy = static_cast<int>(floorf(__fdiv_rn(xt.y, ct.leaf[1])));
-    const int iz = static_cast<int>(floorf(__fdiv_rn(xt.z, ct.leaf[2])));
-    const double x[3] = {p.x, p.y, p.z};
-    double J[3][6];
-    double vec[6][3];
-    bool have = false;
-    for (int o = 0; o < P.n_offsets; o++) {
-      const int cx = ix + P.off[o][0], cy = iy + P.off[o][1], cz = iz + P.off[o][2];
-      if (cx < ct.min_b[0] || cx > ct.max_b[0] || cy < ct.min_b[1] || cy > ct.max_b[1] || cz < ct.min_b[2] || cz > ct.max_b[2]) continue;
-      const int lin = (cx - ct.min_b[0]) * ct.mul[0] + (cy - ct.min_b[1]) * ct.mul[1] + (cz - ct.min_b[2]) * ct.mul[2];
-      const int slot = cell_lookup(ct, lin);
-      if (slot < 0) continue;
-      if (!have) {
-        have = true;
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int c = 0; c < 6; c++) J[a][c] = (a == c) ? 1.0 : 0.0;
-#define LGS_DJ(r) s3(x[0] * P.j_ang_d[r][0], x[1] * P.j_ang_d[r][1], x[2] * P.j_ang_d[r][2])
-#define LGS_DH(r) s3(x[0] * P.h_ang_d[r][0], x[1] * P.h_ang_d[r][1], x[2] * P.h_ang_d[r][2])
-        J[1][3] = LGS_DJ(0); J[2][3] = LGS_DJ(1);
-        J[0][4] = LGS_DJ(2); J[1][4] = LGS_DJ(3); J[2][4] = LGS_DJ(4);
-        J[0][5] = LGS_DJ(5); J[1][5] = LGS_DJ(6); J[2][5] = LGS_DJ(7);
-        vec[0][0] = 0; vec[0][1] = LGS_DH(0); vec[0][2] = LGS_DH(1);
-        vec[1][0] = 0; vec[1][1] = LGS_DH(2); vec[1][2] = LGS_DH(3);
-        vec[2][0] = 0; vec[2][1] = LGS_DH(4); vec[2][2] = LGS_DH(5);
-        vec[3][0] = LGS_DH(6); vec[3][1] = LGS_DH(7); vec[3][2] = LGS_DH(8);
-        vec[4][0] = LGS_DH(9); vec[4][1] = LGS_DH(10); vec[4][2] = LGS_DH(11);
-        vec[5][0] = LGS_DH(12); vec[5][1] = LGS_DH(13); vec[5][2] = LGS_DH(14);
-#undef LGS_DJ
-#undef LGS_DH
-      }
-      const double* mean = vmean + static_cast<size_t>(slot) * 3;
-      const double* C = vicov + static_cast<size_t>(slot) * 9;
-      const double xx[3] = {static_cast<double>(xt.x) - mean[0], static_cast<double>(xt.y) - mean[1], static_cast<double>(xt.z) - mean[2]};
-      double Cx[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) Cx[r] = s3(C[r * 3] * xx[0], C[r * 3 + 1] * xx[1], C[r * 3 + 2] * xx[2]);
-      double e = P.gauss_d2 * exp(-P.gauss_d2 * s3(xx[0] * Cx[0], xx[1] * Cx[1], xx[2] * Cx[2]) / 2);
-      if (e > 1 || e < 0 || e != e) continue;
-      e *= P.gauss_d1;
-      double CJ[6][3], xCJ[6];
-#pragma unroll
-      for (int c = 0; c < 6; c++) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) CJ[c][r] = s3(C[r * 3] * J[0][c], C[r * 3 + 1] * J[1][c], C[r * 3 + 2] * J[2][c]);
-        xCJ[c] = s3(xx[0] * CJ[c][0], xx[1] * CJ[c][1], xx[2] * CJ[c][2]);
-      }
-      const int blk[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-#pragma unroll
-      for (int ii = 0; ii < 6; ii++) {
-#pragma unroll
-        for (int jj = 0; jj < 6; jj++) {
-          double hv[3] = {0, 0, 0};
-          if (ii >= 3 && jj >= 3) {
-            const double* vv = vec[blk[ii - 3][jj - 3]];
-            hv[0] = vv[0]; hv[1] = vv[1]; hv[2] = vv[2];
-          }
-          double Ch[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++) Ch[r] = s3(C[r * 3] * hv[0], C[r * 3 + 1] * hv[1], C[r * 3 + 2] * hv[2]);
-          const double xCH = s3(xx[0] * Ch[0], xx[1] * Ch[1], xx[2] * Ch[2]);
-          const double jcj = s3(J[0][jj] * CJ[ii][0], J[1][jj] * CJ[ii][1], J[2][jj] * CJ[ii][2]);
-          acc[ii * 6 + jj] += e * (-P.gauss_d2 * xCJ[ii] * xCJ[jj] + xCH + jcj);
-        }
-      }
-    }
-  }
-  block_reduce_and_finish<36>(acc, partials, result, counter, mb);
-}
-
 // calculateScore (NDT:934-982)
 __global__ void __launch_bounds__(kEvalBlock) ndt_score_kernel(const float4* __restrict__ src, int n, EvalParams P, CellTable ct,
                                                              const double* __restrict__ vmean, const double* __restrict__ vicov, double gauss_d3,
@@ -655,7 +571,7 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   P.gauss_d2 = n->gauss_d2;
   P.gauss_d2f = static_cast<float>(n->gauss_d2);
   fill_offsets(n->search, &P);
-  const int K = mode == 0 ? 29 : (mode == 1 ? 8 : 36);
+  const int K = mode == 0 ? 29 : (mode == 1 ? 8 : 22);
   if (score) *score = 0;
   if (g) std::fill(g, g + 6, 0.0);
   if (H) std::fill(H, H + 36, 0.0);
@@ -683,30 +599,30 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   static bool smem_opt_in = false;  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per process)
   if (!smem_opt_in) {
     const int smem = static_cast<int>(sizeof(DerivSmem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_opt_in = true;
   }
-  if (mode != 2) {
+  {
     // one CTA per SM (fewer when the cloud has fewer rounds of 32 points than SMs)
     const int dgrid = std::max(1, std::min(kNumSMs, (ns + 31) / 32));
     const u64 one2 = 0x3f8000003f800000ull;  // (1.0f, 1.0f): see ndt_deriv.cuh
     const bool d7 = n->search == LGS_NDT_DIRECT7;
     VoxelRec* rc = n->recs.as<VoxelRec>();
+    const double *vm = n->ex_mean.as<double>(), *vc = n->ex_icov.as<double>();
     double* pt = n->partials.as<double>();
-    if (mode == 0 && d7)
-      ndt_derivatives_kernel<true, true><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
-    else if (mode == 0)
-      ndt_derivatives_kernel<true, false><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
-    else if (d7)
-      ndt_derivatives_kernel<false, true><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
-    else
-      ndt_derivatives_kernel<false, false><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, pt, result, counter, one2, mb);
-  } else {
-    ndt_hessian_f64_kernel<<<grid, kEvalBlock, 0, st>>>(src, ns, P, ct, n->ex_mean.as<double>(), n->ex_icov.as<double>(), n->partials.as<double>(),
-                                                       result, counter, mb);
+#define LGS_LAUNCH(M, D) ndt_derivatives_kernel<M, D><<<dgrid, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, rc, vm, vc, pt, result, counter, one2, mb)
+    if (mode == 0 && d7) LGS_LAUNCH(0, true);
+    else if (mode == 0) LGS_LAUNCH(0, false);
+    else if (mode == 1 && d7) LGS_LAUNCH(1, true);
+    else if (mode == 1) LGS_LAUNCH(1, false);
+    else if (d7) LGS_LAUNCH(2, true);
+    else LGS_LAUNCH(2, false);
+#undef LGS_LAUNCH
   }
   if (n->profiling) {
     LGS_CUDA(cudaEventRecord(ev1, st));
@@ -718,7 +634,8 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   double h[kMailboxRecords];
   LGS_TRY(mailbox_wait(ctx, mb, K, h));
   if (mode == 2) {
-    memcpy(H, h, 36 * sizeof(double));
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[tri(i, j)];
   } else {
     *score = h[0];
     memcpy(g, h + 1, 6 * sizeof(double));

@@ -152,7 +152,11 @@ def test_ndt_velodyne_voxels_and_derivatives(api, oracle, velodyne_pair):
                     assert sg == pytest.approx(so, rel=1e-12)
                     np.testing.assert_allclose(gg, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
                 if mode == 2:
+                    # computeHessian in f64: upper triangle formed like the reference and mirrored (its own (j,i)
+                    # entry differs from (i,j) by f64 rounding of the terms only)
+                    np.testing.assert_allclose(np.triu(Hg), np.triu(Ho), rtol=1e-9, atol=1e-11 * scale)
                     np.testing.assert_allclose(Hg, Ho, rtol=1e-9, atol=1e-11 * scale)
+                    assert np.array_equal(Hg, Hg.T)
                 if mode == 0:
                     # the kernel forms the upper triangle exactly as the reference does and mirrors it; the reference's
                     # own (j,i) entry differs from its (i,j) entry by f32 rounding of the terms only

@@ -76,7 +76,7 @@ def main():
     import ctypes as C
     L = g._L
     if hasattr(L, "lgs_ndt_debug_trace"):
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             g.derivatives(T, p, mode)
             tr = np.zeros((148, 8))
             L.lgs_ndt_debug_trace(g._h, tr.ctypes.data_as(C.c_void_p), 148)
