@@ -195,12 +195,13 @@ def loop_closure_bench(rank, world, device, pairs_per_rank):
     sizes = [len(a) + len(b) for a, b in zip(scans, submaps)]
     mine = partition_pairs(sizes, rank, world)
     my_scans, my_subs = [scans[i] for i in mine], [submaps[i] for i in mine]
-    api.batch_align(my_scans[:1], my_subs[:1], n_workers=1, device=device)  # warm-up (allocations, module load)
+    n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", 2)
+    api.batch_align(my_scans[:2 * n_workers], my_subs[:2 * n_workers], n_workers=n_workers, device=device)  # warm-up: every worker allocates its device state once
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    recs = api.batch_align(my_scans, my_subs, method=api.METHOD_GICP, device=device, n_workers=4, pair_id0=0)
+    recs = api.batch_align(my_scans, my_subs, method=api.METHOD_GICP, device=device, n_workers=n_workers, pair_id0=0)
     local = torch.from_numpy(records_to_array(recs)).cuda(device)
     gathered = gather_records(local, n_total, torch.tensor(mine, dtype=torch.int64), rank, world)
     torch.cuda.synchronize()
@@ -220,7 +221,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 8), help="loop-closure pairs per rank (0 disables)")
+    ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 32), help="loop-closure pairs per rank (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)

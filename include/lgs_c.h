@@ -224,6 +224,11 @@ int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* param
                     const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
                     const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev);
 
+/* The per-worker device state of lgs_batch_align (stream, registration objects, staging buffers) is kept in a
+ * process-wide pool between calls, the way the reference keeps one registration_ object per node for its lifetime
+ * (graph_based_slam.hpp:108).  This frees it (call with no batch in flight, e.g. at node shutdown). */
+void lgs_batch_release(void);
+
 #ifdef __cplusplus
 }
 #endif

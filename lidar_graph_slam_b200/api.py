@@ -361,3 +361,8 @@ def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stre
                             g.ctypes.data_as(C.c_void_p) if g is not None else None, int(pair_id0), recs,
                             C.c_void_p(records_dev) if records_dev else None))
     return [recs[i] for i in range(n)]
+
+
+def batch_release():
+    """Frees the worker state batch_align keeps between calls (streams, registration objects, device buffers)."""
+    _lib.load().lgs_batch_release()

@@ -5,6 +5,9 @@
 // stream with deterministic reductions, so a pair's record does not depend on W, on the pair order, or on which
 // GPU of the box it was dealt to.
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <mutex>
 #include <thread>
@@ -35,12 +38,33 @@ struct BatchShared {
   std::string err;
 };
 
+// development aid: LGS_BATCH_TRACE=1 prints the host wall time of every stage of every pair (with a stream
+// synchronisation after each stage, so the numbers are not the production timeline)
+struct StageClock {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  explicit StageClock(cudaStream_t s) : on(getenv("LGS_BATCH_TRACE") != nullptr), st(s) {
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void lap(int k) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    ms[k] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
 int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, DevBuf* sub_raw, DevBuf* sub_ds, BatchShared* S, int64_t i) {
   const lgs_batch_params& bp = *S->bp;
   lgs_align_result& rec = S->records[i];
   memset(&rec, 0, sizeof(rec));
+  StageClock clk(ctx->stream);
   // submap -> (optional) VoxelGrid -> device-resident target
   LGS_TRY(upload_cloud(ctx, S->submaps[i], S->n_submap[i], S->stride, sub_raw));
+  clk.lap(0);
   const float* tgt_dev = sub_raw->as<float>();
   int64_t n_tgt = S->n_submap[i];
   if (bp.submap_leaf > 0 && n_tgt > 0) {
@@ -51,67 +75,127 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, DevBuf* sub_raw, DevBuf
     tgt_dev = sub_ds->as<float>();
     n_tgt = info.n_out;
   }
+  clk.lap(1);
   const float* guess = S->guesses ? S->guesses + 16 * i : nullptr;
   const double max_range = bp.fitness_max_range > 0 ? bp.fitness_max_range : std::numeric_limits<double>::max();
   if (bp.method == LGS_METHOD_GICP) {
     LGS_TRY(lgs_gicp_set_target_dev(gicp, tgt_dev, n_tgt));
+    clk.lap(2);
     LGS_TRY(lgs_gicp_set_source(gicp, S->scans[i], S->n_scan[i], S->stride));
+    clk.lap(3);
     LGS_TRY(lgs_gicp_align(gicp, guess, &rec, nullptr));
+    clk.lap(4);
     LGS_TRY(lgs_gicp_fitness(gicp, max_range, &rec.fitness));
+    clk.lap(5);
   } else {
     LGS_TRY(lgs_ndt_set_target_dev(ndt, tgt_dev, n_tgt));
+    clk.lap(2);
     LGS_TRY(lgs_ndt_set_source(ndt, S->scans[i], S->n_scan[i], S->stride));
+    clk.lap(3);
     LGS_TRY(lgs_ndt_align(ndt, guess, &rec, nullptr));
+    clk.lap(4);
     LGS_TRY(lgs_ndt_fitness(ndt, max_range, &rec.fitness));
+    clk.lap(5);
   }
+  if (clk.on)
+    fprintf(stderr, "[lgs batch] pair %lld: upload %.2f  voxelgrid %.2f  set_target %.2f  set_source %.2f  align %.2f  fitness %.2f ms (target %lld pts)\n",
+            static_cast<long long>(i), clk.ms[0], clk.ms[1], clk.ms[2], clk.ms[3], clk.ms[4], clk.ms[5], static_cast<long long>(n_tgt));
   rec.pair_id = S->pair_id0 + static_cast<int32_t>(i);
   return LGS_OK;
 }
 
-void worker(BatchShared* S) {
+// A worker's device state (stream, registration objects, staging buffers) outlives the call: creating a stream, the
+// pinned result mailbox and ~20 device buffers costs tens of milliseconds, more than verifying a pair.  Slots live in
+// a per-process pool keyed by device; lgs_batch_align borrows W of them and returns them; lgs_batch_release frees them.
+struct WorkerSlot {
+  int device = -1;
   lgs_ctx* ctx = nullptr;
   lgs_gicp* gicp = nullptr;
   lgs_ndt* ndt = nullptr;
   DevBuf sub_raw, sub_ds;
-  int rc = lgs_ctx_create(S->device, nullptr, &ctx);
+  void destroy() {
+    if (ctx) {
+      cudaSetDevice(device);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    sub_raw.release();
+    sub_ds.release();
+    if (gicp) lgs_gicp_destroy(gicp);
+    if (ndt) lgs_ndt_destroy(ndt);
+    if (ctx) lgs_ctx_destroy(ctx);
+    ctx = nullptr;
+    gicp = nullptr;
+    ndt = nullptr;
+  }
+};
+
+std::mutex g_pool_mu;
+std::vector<WorkerSlot*> g_pool;  // idle slots
+
+WorkerSlot* borrow_slot(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (size_t i = 0; i < g_pool.size(); i++)
+    if (g_pool[i]->device == device) {
+      WorkerSlot* w = g_pool[i];
+      g_pool.erase(g_pool.begin() + i);
+      return w;
+    }
+  WorkerSlot* w = new WorkerSlot;
+  w->device = device;
+  return w;
+}
+
+void return_slot(WorkerSlot* w) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool.push_back(w);
+}
+
+void worker(BatchShared* S) {
+  WorkerSlot* w = borrow_slot(S->device);
+  int rc = LGS_OK;
   const lgs_batch_params& bp = *S->bp;
+  if (!w->ctx) rc = lgs_ctx_create(S->device, nullptr, &w->ctx);
+  if (rc == LGS_OK) rc = use_device(w->ctx);
   if (rc == LGS_OK) {
     if (bp.method == LGS_METHOD_GICP) {
-      rc = lgs_gicp_create(ctx, &gicp);
+      if (!w->gicp) rc = lgs_gicp_create(w->ctx, &w->gicp);
       if (rc == LGS_OK) {
-        if (bp.k_correspondences > 0) lgs_gicp_set_correspondence_randomness(gicp, bp.k_correspondences);
-        if (bp.max_iterations > 0) lgs_gicp_set_maximum_iterations(gicp, bp.max_iterations);
-        if (bp.transformation_epsilon > 0) lgs_gicp_set_transformation_epsilon(gicp, bp.transformation_epsilon);
-        if (bp.max_correspondence_distance > 0) lgs_gicp_set_max_correspondence_distance(gicp, bp.max_correspondence_distance);
+        // every call starts from the library defaults (fast_gicp.hpp / gicp_settings.hpp), then the batch's settings
+        lgs_gicp_set_correspondence_randomness(w->gicp, bp.k_correspondences > 0 ? bp.k_correspondences : 20);
+        lgs_gicp_set_maximum_iterations(w->gicp, bp.max_iterations > 0 ? bp.max_iterations : 64);
+        lgs_gicp_set_transformation_epsilon(w->gicp, bp.transformation_epsilon > 0 ? bp.transformation_epsilon : 5e-4);
+        lgs_gicp_set_max_correspondence_distance(w->gicp, bp.max_correspondence_distance > 0 ? bp.max_correspondence_distance
+                                                                                              : static_cast<double>(std::numeric_limits<float>::max()));
       }
     } else {
-      rc = lgs_ndt_create(ctx, &ndt);
+      if (!w->ndt) rc = lgs_ndt_create(w->ctx, &w->ndt);
       if (rc == LGS_OK) {
-        if (bp.ndt_resolution > 0) lgs_ndt_set_resolution(ndt, bp.ndt_resolution);
-        if (bp.ndt_step_size > 0) lgs_ndt_set_step_size(ndt, bp.ndt_step_size);
-        if (bp.max_iterations > 0) lgs_ndt_set_maximum_iterations(ndt, bp.max_iterations);
-        if (bp.transformation_epsilon > 0) lgs_ndt_set_transformation_epsilon(ndt, bp.transformation_epsilon);
+        lgs_ndt_set_resolution(w->ndt, bp.ndt_resolution > 0 ? bp.ndt_resolution : 1.0f);
+        lgs_ndt_set_step_size(w->ndt, bp.ndt_step_size > 0 ? bp.ndt_step_size : 0.1);
+        lgs_ndt_set_maximum_iterations(w->ndt, bp.max_iterations > 0 ? bp.max_iterations : 35);
+        lgs_ndt_set_transformation_epsilon(w->ndt, bp.transformation_epsilon > 0 ? bp.transformation_epsilon : 0.1);
       }
     }
   }
   while (rc == LGS_OK && !S->failed.load()) {
     const int64_t i = S->next.fetch_add(1);
     if (i >= S->n_pairs) break;
-    rc = run_pair(ctx, gicp, ndt, &sub_raw, &sub_ds, S, i);
+    rc = run_pair(w->ctx, w->gicp, w->ndt, &w->sub_raw, &w->sub_ds, S, i);
   }
   if (rc != LGS_OK) {
     std::lock_guard<std::mutex> lk(S->err_mu);
     if (!S->failed.exchange(rc)) S->err = lgs_last_error();
   }
-  if (ctx) {
+  if (w->ctx) {
     cudaSetDevice(S->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(w->ctx->stream);
   }
-  sub_raw.release();
-  sub_ds.release();
-  if (gicp) lgs_gicp_destroy(gicp);
-  if (ndt) lgs_ndt_destroy(ndt);
-  if (ctx) lgs_ctx_destroy(ctx);
+  if (rc != LGS_OK) {  // a failed slot is not reused
+    w->destroy();
+    delete w;
+  } else {
+    return_slot(w);
+  }
 }
 
 }  // namespace
@@ -157,4 +241,16 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
     LGS_CUDA(cudaStreamSynchronize(st));
   }
   return LGS_OK;
+}
+
+extern "C" void lgs_batch_release(void) {
+  std::vector<WorkerSlot*> all;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    all.swap(g_pool);
+  }
+  for (WorkerSlot* w : all) {
+    w->destroy();
+    delete w;
+  }
 }

@@ -188,9 +188,29 @@ __device__ __forceinline__ void gicp_point_terms(const LinParams& P, const float
   }
 }
 
-__global__ void __launch_bounds__(kLinBlock) gicp_linearize_kernel(NNView tv, const float4* __restrict__ src, const float4* __restrict__ tgt, int n,
+// update_correspondences, search half (FG:115-137): one warp per source point; pt = trans_f * input, exact 1-NN in
+// the target, kept when its squared distance is below the threshold.  The Mahalanobis half (FG:139-150) is fused
+// into gicp_linearize_kernel.
+constexpr int kCorrBlock = 256;
+__global__ void __launch_bounds__(kCorrBlock) gicp_correspondence_kernel(NNView tv, const float4* __restrict__ src, int n, LinParams P,
+                                                                        int* __restrict__ corr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = blockIdx.x * (kCorrBlock / 32) + warp; i < n; i += gridDim.x * (kCorrBlock / 32)) {
+    const float4 a = __ldg(src + i);
+    // pt = trans_f * input (Isometry3f * Vector4f, column-by-column GEMV)
+    const float qx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[0], a.x), __fmul_rn(P.Tf[1], a.y)), __fmul_rn(P.Tf[2], a.z)), P.Tf[3]);
+    const float qy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[4], a.x), __fmul_rn(P.Tf[5], a.y)), __fmul_rn(P.Tf[6], a.z)), P.Tf[7]);
+    const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[8], a.x), __fmul_rn(P.Tf[9], a.y)), __fmul_rn(P.Tf[10], a.z)), P.Tf[11]);
+    float d2;
+    int id;
+    nn_search1_warp(tv, qx, qy, qz, lane, d2, id);
+    if (lane == 0) corr[i] = (static_cast<double>(d2) < P.corr_thr2) ? id : -1;  // FG:136
+  }
+}
+
+__global__ void __launch_bounds__(kLinBlock) gicp_linearize_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, int n,
                                                                   LinParams P, const double* __restrict__ cov_src,
-                                                                  const double* __restrict__ cov_tgt, int* __restrict__ corr,
+                                                                  const double* __restrict__ cov_tgt, const int* __restrict__ corr,
                                                                   double* __restrict__ mahal, int want_hb, double* __restrict__ partials,
                                                                   double* __restrict__ result, unsigned* __restrict__ counter) {
   double acc[43];
@@ -198,15 +218,7 @@ __global__ void __launch_bounds__(kLinBlock) gicp_linearize_kernel(NNView tv, co
   for (int k = 0; k < 43; k++) acc[k] = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 a = src[i];
-    // pt = trans_f * input (Isometry3f * Vector4f, column-by-column GEMV)
-    const float qx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[0], a.x), __fmul_rn(P.Tf[1], a.y)), __fmul_rn(P.Tf[2], a.z)), P.Tf[3]);
-    const float qy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[4], a.x), __fmul_rn(P.Tf[5], a.y)), __fmul_rn(P.Tf[6], a.z)), P.Tf[7]);
-    const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[8], a.x), __fmul_rn(P.Tf[9], a.y)), __fmul_rn(P.Tf[10], a.z)), P.Tf[11]);
-    float d2;
-    int id;
-    nn_search1(tv, qx, qy, qz, d2, id);
-    const int c = (static_cast<double>(d2) < P.corr_thr2) ? id : -1;  // FG:136
-    corr[i] = c;
+    const int c = corr[i];
     if (c < 0) continue;
     // RCR = cov_B + T cov_A T^T (3x3 block), mahalanobis = RCR^-1  (FG:146-150)
     const double* CA = cov_src + static_cast<size_t>(i) * 9;
@@ -353,10 +365,12 @@ int linearize(lgs_gicp* g, const double* T, double* cost, double* H, double* b) 
   fill_lin_params(g, T, &P);
   double* result = g->result.as<double>();
   unsigned* counter = reinterpret_cast<unsigned*>(result + 44);
-  gicp_linearize_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P,
+  const int cgrid = std::max(1, std::min(grid_for(n, kCorrBlock / 32), kNumSMs * 8));
+  gicp_correspondence_kernel<<<cgrid, kCorrBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), n, P, g->corr.as<int>());
+  gicp_linearize_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P,
                                                           g->source->covs.as<double>(), g->target->covs.as<double>(), g->corr.as<int>(),
                                                           g->mahal.as<double>(), (H && b) ? 1 : 0, g->partials.as<double>(), result, counter);
-  ctx->launches++;
+  ctx->launches += 2;
   LGS_CUDA(cudaGetLastError());
   LGS_TRY(ctx->pin.reserve(44 * 8));
   double* h = ctx->pin.as<double>();
@@ -450,7 +464,16 @@ int step_lm(lgs_gicp* g, double* x0, double* delta, bool* ok) {
 
 int set_cloud(lgs_gicp* g, std::shared_ptr<GicpCloud>* slot, const void* pts, const float* pts_dev, int64_t n, int32_t stride) {
   LGS_TRY(use_device(g->ctx));
-  auto c = std::make_shared<GicpCloud>();
+  // a bundle nobody else holds (no swap partner, no exported alias) is recycled with its device buffers: steady-state
+  // calls never reach cudaMalloc / cudaFree, which would serialise every stream of the device
+  std::shared_ptr<GicpCloud> c;
+  if (*slot && slot->use_count() == 1 && (g->source != g->target)) {
+    c = *slot;
+    c->nn_ready = false;
+    c->covs_ready = false;
+  } else {
+    c = std::make_shared<GicpCloud>();
+  }
   if (pts_dev)
     LGS_TRY(adopt_cloud_dev(g->ctx, pts_dev, n, &c->pts));
   else

@@ -79,49 +79,67 @@ __global__ void __launch_bounds__(256) nn_gather_kernel(const float4* __restrict
   spts[i] = p;
 }
 
-__global__ void __launch_bounds__(256) nn_leaf_box_kernel(const float4* __restrict__ spts, int n, int n_leaves_p2, float4* __restrict__ bmin,
+// level 0: one warp per leaf of 32 consecutive sorted points (coalesced 512-byte load, butterfly min / max)
+__global__ void __launch_bounds__(256) nn_leaf_box_kernel(const float4* __restrict__ spts, int n, int n_leaves, float4* __restrict__ bmin,
                                                          float4* __restrict__ bmax) {
-  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-  if (leaf >= n_leaves_p2) return;
+  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (leaf >= n_leaves) return;
   const float inf = __int_as_float(0x7f800000);
   float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
-  int b = leaf * kLeafSize, e = min(b + kLeafSize, n);
-  for (int j = b; j < e; j++) {
-    float4 p = spts[j];
-    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  const int j = leaf * kLeaf + lane;
+  if (j < n) {
+    const float4 p = spts[j];
+    mn[0] = mx[0] = p.x;
+    mn[1] = mx[1] = p.y;
+    mn[2] = mx[2] = p.z;
   }
-  int node = n_leaves_p2 - 1 + leaf;
-  bmin[node] = make_float4(mn[0], mn[1], mn[2], 0.f);
-  bmax[node] = make_float4(mx[0], mx[1], mx[2], 0.f);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(kFullMask, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(kFullMask, mx[a], off));
+    }
+  if (lane == 0) {
+    bmin[leaf] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    bmax[leaf] = make_float4(mx[0], mx[1], mx[2], 0.f);
+  }
 }
 
-// one level of the bottom-up merge: nodes [first, first + count)
-__global__ void __launch_bounds__(256) nn_merge_level_kernel(int first, int count, float4* __restrict__ bmin, float4* __restrict__ bmax) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
-  int node = first + k;
-  int l = 2 * node + 1, r = l + 1;
-  float4 a = bmin[l], b = bmin[r];
-  bmin[node] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.f);
-  a = bmax[l];
-  b = bmax[r];
-  bmax[node] = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), 0.f);
+// level l + 1 from level l: one thread per node, union of its (up to) 32 child boxes
+__global__ void __launch_bounds__(128) nn_node_box_kernel(int child_off, int child_cnt, int node_off, int node_cnt, float4* __restrict__ bmin,
+                                                         float4* __restrict__ bmax) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= node_cnt) return;
+  const int b = node * kLeaf, e = min(b + kLeaf, child_cnt);
+  float4 lo = bmin[child_off + b], hi = bmax[child_off + b];
+  for (int c = b + 1; c < e; c++) {
+    const float4 a = bmin[child_off + c], z = bmax[child_off + c];
+    lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+    hi.x = fmaxf(hi.x, z.x); hi.y = fmaxf(hi.y, z.y); hi.z = fmaxf(hi.z, z.z);
+  }
+  bmin[node_off + node] = lo;
+  bmax[node_off + node] = hi;
 }
 
 int NNIndex::build(lgs_ctx* ctx, const float4* pts, int64_t n_in) {
   LGS_REQUIRE(n_in >= 0 && n_in < (int64_t(1) << 31), "point count out of range");
   n = n_in;
-  n_leaves_p2 = 1;
+  n_levels = 0;
   if (n == 0) return LGS_OK;
   cudaStream_t st = ctx->stream;
-  const int n_leaves = static_cast<int>((n + kLeafSize - 1) / kLeafSize);
-  while (n_leaves_p2 < n_leaves) n_leaves_p2 <<= 1;
-  const size_t n_nodes = 2 * static_cast<size_t>(n_leaves_p2) - 1;
+  // level sizes: cnt[0] leaves, then ceil(/32) per level; padded to 3 or 6 levels (see nn.cuh)
+  int64_t c = (n + kLeaf - 1) / kLeaf, total = 0;
+  for (int l = 0; l < kMaxLevels; l++) {
+    cnt[l] = static_cast<int>(c);
+    off[l] = static_cast<int>(total);
+    total += c;
+    c = (c + kLeaf - 1) / kLeaf;
+  }
+  n_levels = cnt[2] <= kLeaf ? 3 : 6;
   LGS_TRY(spts.reserve(static_cast<size_t>(n) * 16));
-  LGS_TRY(bmin.reserve(n_nodes * 16));
-  LGS_TRY(bmax.reserve(n_nodes * 16));
+  LGS_TRY(bmin.reserve(static_cast<size_t>(total) * 16));
+  LGS_TRY(bmax.reserve(static_cast<size_t>(total) * 16));
   LGS_TRY(codes.reserve(static_cast<size_t>(n) * 4));
   LGS_TRY(codes_alt.reserve(static_cast<size_t>(n) * 4));
   LGS_TRY(perm.reserve(static_cast<size_t>(n) * 4));
@@ -138,11 +156,11 @@ int NNIndex::build(lgs_ctx* ctx, const float4* pts, int64_t n_in) {
   LGS_TRY(ctx->cub_tmp.reserve(tb));
   cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, dk, dv, static_cast<int>(n), 0, 30, st);
   nn_gather_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, dv.Current(), n, spts.as<float4>());
-  nn_leaf_box_kernel<<<grid_for(n_leaves_p2, 256), 256, 0, st>>>(spts.as<float4>(), static_cast<int>(n), n_leaves_p2, bmin.as<float4>(),
-                                                                bmax.as<float4>());
+  nn_leaf_box_kernel<<<grid_for(static_cast<int64_t>(cnt[0]) * 32, 256), 256, 0, st>>>(spts.as<float4>(), static_cast<int>(n), cnt[0],
+                                                                                     bmin.as<float4>(), bmax.as<float4>());
   ctx->launches += 5 + 6;
-  for (int count = n_leaves_p2 / 2; count >= 1; count >>= 1) {
-    nn_merge_level_kernel<<<grid_for(count, 256), 256, 0, st>>>(count - 1, count, bmin.as<float4>(), bmax.as<float4>());
+  for (int l = 1; l < n_levels; l++) {
+    nn_node_box_kernel<<<grid_for(cnt[l], 128), 128, 0, st>>>(off[l - 1], cnt[l - 1], off[l], cnt[l], bmin.as<float4>(), bmax.as<float4>());
     ctx->launches++;
   }
   LGS_CUDA(cudaGetLastError());
@@ -152,40 +170,40 @@ int NNIndex::build(lgs_ctx* ctx, const float4* pts, int64_t n_in) {
 // ---------------------------------------------------------------------------------------------
 // fitness: pcl::Registration::getFitnessScore
 
-constexpr int kFitBlock = 128;
+constexpr int kFitBlock = 256;
+constexpr int kFitWarps = kFitBlock / 32;
 
+// one warp per source point; lane 0 of every warp accumulates its points in index order, warps and blocks are
+// combined in a fixed order: reproducible sums
 __global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const float4* __restrict__ src, int n, const float* __restrict__ Tdev,
                                                               double max_range, double* __restrict__ partials, double* __restrict__ result,
                                                               unsigned* __restrict__ counter) {
   __shared__ float T[16];
   if (threadIdx.x < 16) T[threadIdx.x] = Tdev[threadIdx.x];
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sum = 0.0, cnt = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = src[i];
+  for (int i = blockIdx.x * kFitWarps + warp; i < n; i += gridDim.x * kFitWarps) {
+    const float4 p = __ldg(src + i);
     const float3 q = transform_pcl(T, p.x, p.y, p.z);
     float d;
     int id;
-    nn_search1(v, q.x, q.y, q.z, d, id);
+    nn_search1_warp(v, q.x, q.y, q.z, lane, d, id);
     if (static_cast<double>(d) <= max_range) {
       sum += static_cast<double>(d);
       cnt += 1.0;
     }
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-  }
-  __shared__ double ssum[kFitBlock / 32], scnt[kFitBlock / 32];
+  __shared__ double ssum[kFitWarps], scnt[kFitWarps];
   __shared__ bool is_last;
-  if ((threadIdx.x & 31) == 0) {
-    ssum[threadIdx.x >> 5] = sum;
-    scnt[threadIdx.x >> 5] = cnt;
+  if (lane == 0) {
+    ssum[warp] = sum;
+    scnt[warp] = cnt;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0, c = 0;
-    for (int w = 0; w < kFitBlock / 32; w++) {
+    for (int w = 0; w < kFitWarps; w++) {
       s += ssum[w];
       c += scnt[w];
     }
@@ -195,16 +213,23 @@ __global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const f
     is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last && threadIdx.x < 32) {
     __threadfence();
     double s = 0, c = 0;
-    for (unsigned b = 0; b < gridDim.x; b++) {
-      s += partials[2 * b];
-      c += partials[2 * b + 1];
+    for (unsigned b = lane; b < gridDim.x; b += 32) {
+      s += __ldcg(partials + 2 * b);
+      c += __ldcg(partials + 2 * b + 1);
     }
-    result[0] = s;
-    result[1] = c;
-    *counter = 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(kFullMask, s, off);
+      c += __shfl_xor_sync(kFullMask, c, off);
+    }
+    if (lane == 0) {
+      result[0] = s;
+      result[1] = c;
+      *counter = 0;
+    }
   }
 }
 
@@ -212,7 +237,7 @@ int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_
   *fitness = std::numeric_limits<double>::max();
   if (n_src == 0 || index.n == 0) return LGS_OK;
   cudaStream_t st = ctx->stream;
-  const int grid = std::max(1, std::min(grid_for(n_src, kFitBlock), kNumSMs * 16));
+  const int grid = std::max(1, std::min(grid_for(n_src, kFitWarps), kNumSMs * 8));
   LGS_TRY(ctx->tmp[0].reserve(static_cast<size_t>(grid) * 16 + 256));
   double* partials = ctx->tmp[0].as<double>();
   double* result = partials + 2 * grid;
@@ -236,76 +261,34 @@ int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_
 // ---------------------------------------------------------------------------------------------
 // k-NN
 
+constexpr int kKnnBlock = 256;
+constexpr int kKnnWarps = kKnnBlock / 32;
+
+// one warp per query.  SELF: query t is sorted point t (consecutive warps search neighbouring regions, so the boxes
+// and leaves they touch are shared through L1) and the row written is the point's original index.
 template <bool SELF>
-__global__ void __launch_bounds__(128) nn_knn_kernel(NNView v, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
-                                                    float* __restrict__ out_d2) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  float4 qp = SELF ? __ldg(v.spts + t) : queries[t];
-  const int row = SELF ? __float_as_int(qp.w) : t;
-  const float qx = qp.x, qy = qp.y, qz = qp.z;
-  float bd[kMaxK];
-  int bi[kMaxK];
-  int found = 0;
-  const float inf = __int_as_float(0x7f800000);
-  float worst = inf;
-  int worst_i = 0x7fffffff;
-  const int first_leaf = v.n_leaves_p2 - 1;
-  int stack[48];
-  float sdist[48];
-  int sp = 1;
-  stack[0] = 0;
-  sdist[0] = nn_box_dist2(qx, qy, qz, __ldg(v.bmin), __ldg(v.bmax));
-  while (sp > 0) {
-    --sp;
-    const int node = stack[sp];
-    if (sdist[sp] > worst) continue;
-    if (node >= first_leaf) {
-      const int b = (node - first_leaf) * kLeafSize;
-      const int e = min(b + kLeafSize, v.n);
-      for (int j = b; j < e; j++) {
-        const float4 p = __ldg(v.spts + j);
-        const float d = nn_dist2(qx, qy, qz, p);
-        const int oi = __float_as_int(p.w);
-        if (found < k || d < worst || (d == worst && oi < worst_i)) {
-          int pos = found < k ? found : k - 1;
-          if (found < k) found++;
-          while (pos > 0 && (d < bd[pos - 1] || (d == bd[pos - 1] && oi < bi[pos - 1]))) {
-            bd[pos] = bd[pos - 1];
-            bi[pos] = bi[pos - 1];
-            --pos;
-          }
-          bd[pos] = d;
-          bi[pos] = oi;
-          if (found == k) {
-            worst = bd[k - 1];
-            worst_i = bi[k - 1];
-          }
-        }
-      }
-    } else {
-      const int l = 2 * node + 1, r = l + 1;
-      const float dl = nn_box_dist2(qx, qy, qz, __ldg(v.bmin + l), __ldg(v.bmax + l));
-      const float dr = nn_box_dist2(qx, qy, qz, __ldg(v.bmin + r), __ldg(v.bmax + r));
-      if (dl <= dr) {
-        if (dr <= worst) { stack[sp] = r; sdist[sp++] = dr; }
-        if (dl <= worst) { stack[sp] = l; sdist[sp++] = dl; }
-      } else {
-        if (dl <= worst) { stack[sp] = l; sdist[sp++] = dl; }
-        if (dr <= worst) { stack[sp] = r; sdist[sp++] = dr; }
-      }
+__global__ void __launch_bounds__(kKnnBlock) nn_knn_kernel(NNView v, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
+                                                          float* __restrict__ out_d2) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x * kKnnWarps + warp; t < m; t += gridDim.x * kKnnWarps) {
+    const float4 qp = SELF ? __ldg(v.spts + t) : __ldg(queries + t);
+    const int row = SELF ? __float_as_int(qp.w) : t;
+    NNKBest B;
+    nn_searchk_warp(v, qp.x, qp.y, qp.z, lane, k, B);
+    if (lane < k) {
+      const bool have = B.bi != 0x7fffffff;
+      out_idx[static_cast<size_t>(row) * k + lane] = have ? B.bi : -1;
+      if (out_d2) out_d2[static_cast<size_t>(row) * k + lane] = have ? B.bd : 0.f;
     }
   }
-  for (int j = 0; j < k; j++) {
-    out_idx[static_cast<size_t>(row) * k + j] = j < found ? bi[j] : -1;
-    if (out_d2) out_d2[static_cast<size_t>(row) * k + j] = j < found ? bd[j] : 0.f;
-  }
 }
+
+static int knn_grid(int64_t m) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((m + kKnnWarps - 1) / kKnnWarps, kNumSMs * 64))); }
 
 int nn_self_knn(lgs_ctx* ctx, const NNIndex& index, int k, int* out_idx_dev, float* out_d2_dev) {
   LGS_REQUIRE(k >= 1 && k <= kMaxK, "k must be in [1, 32]");
   if (index.n == 0) return LGS_OK;
-  nn_knn_kernel<true><<<grid_for(index.n, 128), 128, 0, ctx->stream>>>(index.view(), nullptr, static_cast<int>(index.n), k, out_idx_dev, out_d2_dev);
+  nn_knn_kernel<true><<<knn_grid(index.n), kKnnBlock, 0, ctx->stream>>>(index.view(), nullptr, static_cast<int>(index.n), k, out_idx_dev, out_d2_dev);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   return LGS_OK;
@@ -319,7 +302,7 @@ int nn_knn(lgs_ctx* ctx, const NNIndex& index, const float4* queries, int64_t m,
     if (out_d2_dev) LGS_CUDA(cudaMemsetAsync(out_d2_dev, 0, static_cast<size_t>(m) * k * 4, ctx->stream));
     return LGS_OK;
   }
-  nn_knn_kernel<false><<<grid_for(m, 128), 128, 0, ctx->stream>>>(index.view(), queries, static_cast<int>(m), k, out_idx_dev, out_d2_dev);
+  nn_knn_kernel<false><<<knn_grid(m), kKnnBlock, 0, ctx->stream>>>(index.view(), queries, static_cast<int>(m), k, out_idx_dev, out_d2_dev);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   return LGS_OK;

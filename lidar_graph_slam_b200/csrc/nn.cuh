@@ -1,35 +1,67 @@
-// Exact nearest-neighbour search on the GPU: an implicit, complete binary BVH over the Morton-sorted
-// target cloud.  Stands in for pcl::search::KdTree / FLANN KDTreeSingleIndex (exact, L2_Simple<float>)
-// at FG:133 (1-NN per LM iteration), FG:254 (k-NN covariances) and in pcl::Registration::getFitnessScore
-// (GBS:321).  Exactness: the f32 box distance uses the same subtraction / multiply / add sequence as the
-// f32 point distance, and IEEE rounding is monotone, so box_dist2(q, B) <= dist2(q, p) for every p in B;
-// pruning only on box_dist2 > current worst therefore never discards a candidate.  Ties are resolved
-// towards the smaller original point index, which makes results independent of traversal order.
+// Exact nearest-neighbour search on the GPU: an implicit 32-ary bounding-volume hierarchy over the Morton-sorted
+// target cloud, searched by one WARP per query.  Stands in for pcl::search::KdTree / FLANN KDTreeSingleIndex (exact,
+// L2_Simple<float>) at FG:133 (1-NN per LM iteration), FG:254 (k-NN covariances) and in
+// pcl::Registration::getFitnessScore (GBS:321).
+//
+// Layout.  Level 0 = leaves of 32 consecutive sorted points; a node of level l + 1 owns 32 consecutive boxes of level
+// l.  Boxes of all levels sit in two float4 arrays (min / max), level l at off[l], cnt[l] of them.  No pointers, no
+// per-node child counts: the children of node j are boxes 32 j .. min(32 j + 32, cnt) - 1 of the level below.  The
+// hierarchy is padded to 3 (clouds up to 2^20 points) or 6 levels (up to 2^31) so that only two traversal depths are
+// instantiated; padding levels hold a single box.
+//
+// Search.  The 32 lanes of a warp test the 32 children of a node (or the 32 points of a leaf) at once: one coalesced
+// 512-byte load, one distance each, and warp votes / redux to pick the nearest child still worth visiting.  Control
+// flow is warp-uniform and the traversal state lives in registers (recursion is unrolled by templates over the
+// level), so there is no per-thread stack in local memory.  The k best candidates are a sorted list held one entry
+// per lane (k <= 32); a candidate is inserted with one vote, one shuffle-up and one select.
+//
+// Exactness.  The f32 box distance uses the same subtraction / multiply / add sequence as the f32 point distance, and
+// IEEE rounding is monotone, so box_dist2(q, B) <= dist2(q, p) for every p in B; pruning only on box_dist2 > current
+// worst therefore never discards a candidate.  Ties are resolved towards the smaller original point index, which
+// makes results independent of the traversal order: any exact method returns the same rows.
 #pragma once
 #include "common.cuh"
 
 namespace lgs {
 
-constexpr int kLeafSize = 8;
+constexpr int kLeaf = 32;       // points per leaf = children per node = lanes per warp
 constexpr int kMaxK = 32;
+constexpr int kMaxLevels = 6;
 
 struct NNView {
   const float4* spts;  // Morton-sorted points; .w carries the original index (int bits)
-  const float4* bmin;  // per node (heap order): xyz = box min
+  const float4* bmin;  // boxes, all levels concatenated: xyz = box min
   const float4* bmax;
   int n;               // points
-  int n_leaves_p2;     // padded leaf count (power of two)
+  int n_levels;        // 3 or 6 (0 for an empty index)
+  int off[kMaxLevels];
+  int cnt[kMaxLevels];
 };
 
 struct NNIndex {
   DevBuf spts, bmin, bmax, codes, codes_alt, perm, perm_alt, small;
   int64_t n = 0;
-  int n_leaves_p2 = 0;
+  int n_levels = 0;
+  int off[kMaxLevels] = {0, 0, 0, 0, 0, 0};
+  int cnt[kMaxLevels] = {0, 0, 0, 0, 0, 0};
   int build(lgs_ctx* ctx, const float4* pts, int64_t n);
-  NNView view() const { return NNView{spts.as<float4>(), bmin.as<float4>(), bmax.as<float4>(), static_cast<int>(n), n_leaves_p2}; }
+  NNView view() const {
+    NNView v;
+    v.spts = spts.as<float4>();
+    v.bmin = bmin.as<float4>();
+    v.bmax = bmax.as<float4>();
+    v.n = static_cast<int>(n);
+    v.n_levels = n_levels;
+    for (int l = 0; l < kMaxLevels; l++) {
+      v.off[l] = off[l];
+      v.cnt[l] = cnt[l];
+    }
+    return v;
+  }
   void release() {
     for (DevBuf* b : {&spts, &bmin, &bmax, &codes, &codes_alt, &perm, &perm_alt, &small}) b->release();
     n = 0;
+    n_levels = 0;
   }
 };
 
@@ -44,6 +76,9 @@ int nn_self_knn(lgs_ctx* ctx, const NNIndex& index, int k, int* out_idx_dev, flo
 int nn_knn(lgs_ctx* ctx, const NNIndex& index, const float4* queries, int64_t m, int k, int* out_idx_dev, float* out_d2_dev);
 
 #ifdef __CUDACC__
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr unsigned kNoBox = 0xffffffffu;  // above the bit pattern of +inf: "no child here / already visited"
+
 __device__ __forceinline__ float nn_dist2(float qx, float qy, float qz, const float4& p) {
   const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -58,48 +93,162 @@ __device__ __forceinline__ float nn_box_dist2(float qx, float qy, float qz, cons
   return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
 }
 
-// 1-NN traversal.  Returns the squared distance and the original index of the nearest indexed point.
-__device__ __forceinline__ void nn_search1(const NNView& v, float qx, float qy, float qz, float& best_d, int& best_i) {
-  best_d = __int_as_float(0x7f800000);
-  best_i = 0x7fffffff;
-  if (v.n == 0) return;
-  const int first_leaf = v.n_leaves_p2 - 1;
-  int stack[48];
-  float sdist[48];
-  int sp = 0;
-  stack[0] = 0;
-  sdist[0] = nn_box_dist2(qx, qy, qz, __ldg(v.bmin), __ldg(v.bmax));
-  sp = 1;
-  while (sp > 0) {
-    --sp;
-    const int node = stack[sp];
-    const float bd = sdist[sp];
-    if (bd > best_d) continue;
-    if (node >= first_leaf) {
-      const int b = (node - first_leaf) * kLeafSize;
-      const int e = min(b + kLeafSize, v.n);
-      for (int j = b; j < e; j++) {
-        const float4 p = __ldg(v.spts + j);
-        const float d = nn_dist2(qx, qy, qz, p);
-        const int oi = __float_as_int(p.w);
-        if (d < best_d || (d == best_d && oi < best_i)) {
-          best_d = d;
-          best_i = oi;
-        }
-      }
+// Squared distances are non-negative, so their bit patterns order like unsigned integers: redux.sync.min.u32 gives
+// the warp minimum in one instruction.
+__device__ __forceinline__ unsigned nn_child_dists(const NNView& v, int level, int first, int count, float qx, float qy, float qz, int lane) {
+  unsigned cd = kNoBox;
+  if (lane < count) {
+    const float4 lo = __ldg(v.bmin + v.off[level] + first + lane);
+    const float4 hi = __ldg(v.bmax + v.off[level] + first + lane);
+    cd = __float_as_uint(nn_box_dist2(qx, qy, qz, lo, hi));
+  }
+  return cd;
+}
+
+// ---- 1-NN -------------------------------------------------------------------------------------------------------
+// best_d / best_i are warp-uniform.
+__device__ __forceinline__ void nn1_leaf(const NNView& v, int leaf, float qx, float qy, float qz, int lane, float& best_d, int& best_i) {
+  const int j = leaf * kLeaf + lane;
+  unsigned db = kNoBox;
+  int oi = 0x7fffffff;
+  if (j < v.n) {
+    const float4 p = __ldg(v.spts + j);
+    db = __float_as_uint(nn_dist2(qx, qy, qz, p));
+    oi = __float_as_int(p.w);
+  }
+  const unsigned m = __reduce_min_sync(kFullMask, db);
+  const float md = __uint_as_float(m);
+  if (m == kNoBox || md > best_d) return;
+  const int mi = __reduce_min_sync(kFullMask, db == m ? oi : 0x7fffffff);
+  if (md < best_d || mi < best_i) {
+    best_d = md;
+    best_i = mi;
+  }
+}
+
+template <int LC>  // LC = level of the children
+__device__ __forceinline__ void nn1_descend(const NNView& v, int first, int count, float qx, float qy, float qz, int lane, float& best_d, int& best_i) {
+  unsigned cd = nn_child_dists(v, LC, first, count, qx, qy, qz, lane);
+  while (true) {
+    const unsigned m = __reduce_min_sync(kFullMask, cd);
+    if (m == kNoBox || __uint_as_float(m) > best_d) break;
+    const int pick = __ffs(__ballot_sync(kFullMask, cd == m)) - 1;
+    if (lane == pick) cd = kNoBox;
+    const int c = first + pick;
+    if constexpr (LC == 0) {
+      nn1_leaf(v, c, qx, qy, qz, lane, best_d, best_i);
     } else {
-      const int l = 2 * node + 1, r = l + 1;
-      const float dl = nn_box_dist2(qx, qy, qz, __ldg(v.bmin + l), __ldg(v.bmax + l));
-      const float dr = nn_box_dist2(qx, qy, qz, __ldg(v.bmin + r), __ldg(v.bmax + r));
-      if (dl <= dr) {
-        if (dr <= best_d) { stack[sp] = r; sdist[sp++] = dr; }
-        if (dl <= best_d) { stack[sp] = l; sdist[sp++] = dl; }
-      } else {
-        if (dl <= best_d) { stack[sp] = l; sdist[sp++] = dl; }
-        if (dr <= best_d) { stack[sp] = r; sdist[sp++] = dr; }
-      }
+      nn1_descend<LC - 1>(v, c * kLeaf, min(kLeaf, v.cnt[LC - 1] - c * kLeaf), qx, qy, qz, lane, best_d, best_i);
     }
   }
+}
+
+// squared distance and original index of the nearest indexed point (inf / INT_MAX for an empty index); all 32
+// lanes of the warp must call with the same query
+__device__ __forceinline__ void nn_search1_warp(const NNView& v, float qx, float qy, float qz, int lane, float& best_d, int& best_i) {
+  best_d = __int_as_float(0x7f800000);
+  best_i = 0x7fffffff;
+  if (v.n_levels == 3)
+    nn1_descend<2>(v, 0, v.cnt[2], qx, qy, qz, lane, best_d, best_i);
+  else if (v.n_levels == 6)
+    nn1_descend<5>(v, 0, v.cnt[5], qx, qy, qz, lane, best_d, best_i);
+}
+
+// ---- k-NN -------------------------------------------------------------------------------------------------------
+// The warp holds a list of 32 candidates sorted ascending by (d2, idx), entry j in lane j; worst / worst_i
+// (warp-uniform) mirror entry k - 1.  Empty entries are (+inf, INT_MAX).
+struct NNKBest {
+  float bd;
+  int bi;
+  float worst;
+  int worst_i;
+  bool fresh;  // nothing inserted yet (warp-uniform)
+};
+
+__device__ __forceinline__ bool nn_key_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+__device__ __forceinline__ void nnk_leaf(const NNView& v, int leaf, float qx, float qy, float qz, int lane, int k, NNKBest& B) {
+  const int j = leaf * kLeaf + lane;
+  float d = __int_as_float(0x7f800000);
+  int oi = 0x7fffffff;
+  if (j < v.n) {
+    const float4 p = __ldg(v.spts + j);
+    d = nn_dist2(qx, qy, qz, p);
+    oi = __float_as_int(p.w);
+  }
+  if (B.fresh) {
+    // first leaf: the list is empty, so the 32 candidates sorted are the list (bitonic network over the lanes)
+    B.fresh = false;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int s = size >> 1; s > 0; s >>= 1) {
+        const float od = __shfl_xor_sync(kFullMask, d, s);
+        const int oo = __shfl_xor_sync(kFullMask, oi, s);
+        const bool want_min = ((lane & size) == 0) == ((lane & s) == 0);
+        const bool other_less = nn_key_less(od, oo, d, oi);
+        if (want_min == other_less) {  // min keeper takes a smaller partner, max keeper takes a partner that is not smaller
+          d = od;
+          oi = oo;
+        }
+      }
+    }
+    B.bd = d;
+    B.bi = oi;
+  } else {
+    unsigned q = __ballot_sync(kFullMask, nn_key_less(d, oi, B.worst, B.worst_i));
+    while (q) {
+      const int src = __ffs(q) - 1;
+      q &= q - 1;
+      const float cd = __shfl_sync(kFullMask, d, src);
+      const int ci = __shfl_sync(kFullMask, oi, src);
+      if (!nn_key_less(cd, ci, B.worst, B.worst_i)) continue;  // the list tightened since the vote
+      const int pos = __popc(__ballot_sync(kFullMask, nn_key_less(B.bd, B.bi, cd, ci)));  // entries ahead of the candidate: a prefix
+      const float ud = __shfl_up_sync(kFullMask, B.bd, 1);
+      const int ui = __shfl_up_sync(kFullMask, B.bi, 1);
+      if (lane > pos) {
+        B.bd = ud;
+        B.bi = ui;
+      } else if (lane == pos) {
+        B.bd = cd;
+        B.bi = ci;
+      }
+      B.worst = __shfl_sync(kFullMask, B.bd, k - 1);
+      B.worst_i = __shfl_sync(kFullMask, B.bi, k - 1);
+    }
+    return;
+  }
+  B.worst = __shfl_sync(kFullMask, B.bd, k - 1);
+  B.worst_i = __shfl_sync(kFullMask, B.bi, k - 1);
+}
+
+template <int LC>
+__device__ __forceinline__ void nnk_descend(const NNView& v, int first, int count, float qx, float qy, float qz, int lane, int k, NNKBest& B) {
+  unsigned cd = nn_child_dists(v, LC, first, count, qx, qy, qz, lane);
+  while (true) {
+    const unsigned m = __reduce_min_sync(kFullMask, cd);
+    if (m == kNoBox || __uint_as_float(m) > B.worst) break;
+    const int pick = __ffs(__ballot_sync(kFullMask, cd == m)) - 1;
+    if (lane == pick) cd = kNoBox;
+    const int c = first + pick;
+    if constexpr (LC == 0) {
+      nnk_leaf(v, c, qx, qy, qz, lane, k, B);
+    } else {
+      nnk_descend<LC - 1>(v, c * kLeaf, min(kLeaf, v.cnt[LC - 1] - c * kLeaf), qx, qy, qz, lane, k, B);
+    }
+  }
+}
+
+// after the call lane j < k holds the j-th nearest indexed point in (B.bd, B.bi); bi == INT_MAX where the index has
+// fewer than k points
+__device__ __forceinline__ void nn_searchk_warp(const NNView& v, float qx, float qy, float qz, int lane, int k, NNKBest& B) {
+  B.bd = B.worst = __int_as_float(0x7f800000);
+  B.bi = B.worst_i = 0x7fffffff;
+  B.fresh = true;
+  if (v.n_levels == 3)
+    nnk_descend<2>(v, 0, v.cnt[2], qx, qy, qz, lane, k, B);
+  else if (v.n_levels == 6)
+    nnk_descend<5>(v, 0, v.cnt[5], qx, qy, qz, lane, k, B);
 }
 #endif
 

@@ -27,6 +27,7 @@ def main():
     method = api.METHOD_GICP if args.method == "gicp" else api.METHOD_NDT
     api.batch_align(scans[:1], submaps[:1], method=method, n_workers=1)
     for w in [int(x) for x in args.workers.split(",")]:
+        api.batch_align(scans[:2 * w], submaps[:2 * w], method=method, n_workers=w)  # new workers allocate their device state once
         t0 = time.perf_counter()
         recs = api.batch_align(scans, submaps, method=method, n_workers=w)
         dt = time.perf_counter() - t0
