@@ -197,6 +197,11 @@ int lgs_gicp_linearize(lgs_gicp* g, const double* T16_rowmajor, double* cost, do
 int lgs_knn(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const void* queries, int64_t m, int32_t qstride_bytes,
             int32_t k, int32_t* idx, float* d2);
 
+/* parity hook for the device radix sort that orders points by voxel (the std::sort of pcl::VoxelGrid::applyFilter
+ * and the std::map iteration order of VGC:218-263): stable sort of n (key, value) pairs by the low `bits` key bits,
+ * in place in the caller's host arrays */
+int lgs_sort_pairs(lgs_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int32_t bits);
+
 /* ------------------------------------------------------------------------------------------- */
 /* batched loop-closure verification: GBS:297-322 for a list of (scan, submap) pairs              */
 #define LGS_METHOD_NDT 0

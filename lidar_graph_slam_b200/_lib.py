@@ -91,6 +91,7 @@ SYMBOLS = {
     "lgs_gicp_export_covariances": (_i32, [_vp, _i32, _vp]),
     "lgs_gicp_linearize": (_i32, [_vp, _vp, C.POINTER(_f64), _vp, _vp, _vp]),
     "lgs_knn": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "lgs_sort_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lgs_batch_release": (None, []),
 }

@@ -335,6 +335,17 @@ def knn(pts, queries, k, ctx=None):
     return idx[:m], d2[:m]
 
 
+def sort_pairs(keys, vals, bits=32, ctx=None):
+    """Stable device radix sort of (uint32 key, uint32 value) pairs by the low `bits` key bits (parity hook for the
+    sort that orders points by voxel).  Returns sorted copies."""
+    ctx = ctx or default_context()
+    k = np.array(keys, dtype=np.uint32, copy=True).ravel()
+    v = np.array(vals, dtype=np.uint32, copy=True).ravel()
+    assert k.shape == v.shape
+    check(ctx._L.lgs_sort_pairs(ctx._h, k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), k.shape[0], int(bits)))
+    return k, v
+
+
 def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stream=None, pair_id0=0, records_dev=None, max_iterations=100,
                 transformation_epsilon=0.01, max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0, ndt_step_size=0.1,
                 submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0):

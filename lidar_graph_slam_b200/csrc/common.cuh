@@ -128,7 +128,7 @@ struct lgs_ctx {
   int64_t launches = 0;
   lgs::DevBuf raw;       // AoS upload staging
   lgs::DevBuf tmp[8];    // general scratch arenas (per-call meaning)
-  lgs::DevBuf cub_tmp;   // CUB temp storage
+  lgs::DevBuf sort_tmp;  // look-back scratch of the sort / scan primitives (sort.cuh)
   lgs::PinnedBuf pin;    // small D2H results
   lgs::PinnedBuf pin_up; // small H2D parameter blocks
   lgs::DevBuf vg_in, vg_out, vg_vidx, vg_rank;  // host-facing voxel-grid call: staged cloud + device-side outputs

@@ -144,7 +144,7 @@ void lgs_ctx_destroy(lgs_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->raw.release();
   for (auto& b : c->tmp) b.release();
-  c->cub_tmp.release();
+  c->sort_tmp.release();
   c->pin.release();
   c->pin_up.release();
   c->vg_in.release();

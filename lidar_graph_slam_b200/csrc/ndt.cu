@@ -11,8 +11,6 @@
 //   hessian_f64  -> computeHessian / updateHessian (NDT:539-644) in f64.
 //   align        -> computeTransformation (NDT:80-171) + computeStepLengthMT (NDT:771-931) driven from the host;
 //                   each evaluation is one kernel launch + one 352-byte D2H.
-#include <cub/cub.cuh>
-
 #include <algorithm>
 #include <cmath>
 #include <limits>

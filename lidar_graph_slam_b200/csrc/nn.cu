@@ -1,9 +1,9 @@
 // Build and query kernels of the exact nearest-neighbour index (see nn.cuh).
-#include <cub/cub.cuh>
 
 #include <cfloat>
 
 #include "nn.cuh"
+#include "sort.cuh"
 
 namespace lgs {
 
@@ -148,17 +148,14 @@ int NNIndex::build(lgs_ctx* ctx, const float4* pts, int64_t n_in) {
   BoxAcc* acc = small.as<BoxAcc>();
   nn_box_init_kernel<<<1, 32, 0, st>>>(acc);
   nn_bbox_kernel<<<std::min(grid_for(n, 256), kNumSMs * 8), 256, 0, st>>>(pts, n, acc);
-  cub::DoubleBuffer<unsigned> dk(codes.as<unsigned>(), codes_alt.as<unsigned>());
-  cub::DoubleBuffer<unsigned> dv(perm.as<unsigned>(), perm_alt.as<unsigned>());
-  nn_morton_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, n, acc, dk.Current(), dv.Current());
-  size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, static_cast<int>(n), 0, 30, st);
-  LGS_TRY(ctx->cub_tmp.reserve(tb));
-  cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, dk, dv, static_cast<int>(n), 0, 30, st);
-  nn_gather_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, dv.Current(), n, spts.as<float4>());
+  nn_morton_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, n, acc, codes.as<unsigned>(), perm.as<unsigned>());
+  unsigned *sorted_codes, *sorted_perm;
+  LGS_TRY(radix_sort_pairs(ctx, codes.as<unsigned>(), perm.as<unsigned>(), codes_alt.as<unsigned>(), perm_alt.as<unsigned>(), n, 30, &sorted_codes,
+                           &sorted_perm));
+  nn_gather_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, sorted_perm, n, spts.as<float4>());
   nn_leaf_box_kernel<<<grid_for(static_cast<int64_t>(cnt[0]) * 32, 256), 256, 0, st>>>(spts.as<float4>(), static_cast<int>(n), cnt[0],
                                                                                      bmin.as<float4>(), bmax.as<float4>());
-  ctx->launches += 5 + 6;
+  ctx->launches += 5;
   for (int l = 1; l < n_levels; l++) {
     nn_node_box_kernel<<<grid_for(cnt[l], 128), 128, 0, st>>>(off[l - 1], cnt[l - 1], off[l], cnt[l], bmin.as<float4>(), bmax.as<float4>());
     ctx->launches++;

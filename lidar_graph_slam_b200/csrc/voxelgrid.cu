@@ -7,18 +7,18 @@
 //   K1 crop_bbox      16 B/pt read : crop predicate, bbox of the kept points (block reduce + 6 atomics)
 //   -- 32-byte D2H of the bbox; the host derives min_b/div_b/divb_mul with the reference's f32 arithmetic
 //   K2 voxel_key      16 B/pt read, 12 B/pt write: key = ijk . divb_mul (explicit IEEE f32 ops), value = point index
-//   K3 radix sort     (key,value) pairs, only the bits the grid needs (stable => members stay in index order)
-//   K4 segment heads  + select => start offset of every occupied voxel
+//   K3 radix sort     (key,value) pairs, only the bits the grid needs (stable => members stay in index order);
+//                     own onesweep kernels, sort.cuh
+//   K4 segment heads  single-pass look-back scan (sort.cuh) => start offset of every occupied voxel
 //   K5 centroid       one thread per voxel: sequential f32 sums in ascending point index (the oracle's order),
 //                     scatter of the per-point membership rank
 // Integer outputs (voxel idx, occupancy, membership, order) are bit-exact by construction: no FMA
 // contraction or reassociation can reach the key arithmetic because it is written with __f*_rn intrinsics.
-#include <cub/cub.cuh>
-
 #include <cfloat>
 #include <cmath>
 #include <limits>
 
+#include "sort.cuh"
 #include "voxel_common.cuh"
 
 namespace lgs {
@@ -131,20 +131,41 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict
   if (member_rank) member_rank[i] = -1;
 }
 
-__global__ void __launch_bounds__(256) head_flag_kernel(const unsigned* __restrict__ keys, int64_t n_kept, unsigned char* __restrict__ flags) {
-  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= n_kept) return;
-  flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-}
-
-// qualifies[v] = 1 if the voxel holds >= min_pts points
-__global__ void __launch_bounds__(256) qualify_kernel(const int* __restrict__ seg_start, int n_seg, int64_t n_kept, int min_pts, int* __restrict__ qual) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n_seg) return;
-  int b = seg_start[v];
-  int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_kept);
-  qual[v] = (e - b >= min_pts) ? 1 : 0;
-}
+// scan_select functors (sort.cuh)
+struct SegmentHeads {  // start offset of every run of equal keys
+  const unsigned* keys;
+  int* seg_start;
+  __device__ bool flag(int64_t i) const { return i == 0 || keys[i] != keys[i - 1]; }
+  __device__ void emit(int64_t i, int64_t pos, bool f) const {
+    if (f) seg_start[pos] = static_cast<int>(i);
+  }
+};
+struct QualifiedVoxels {  // qual[v] = voxel holds >= min_pts points; out_rank[v] = its position among the qualified ones
+  const int* seg_start;
+  int n_seg;
+  int n_kept;
+  int min_pts;
+  int* qual;
+  int* out_rank;
+  __device__ bool flag(int64_t v) const {
+    const int b = seg_start[v];
+    const int e = (v + 1 < n_seg) ? seg_start[v + 1] : n_kept;
+    return e - b >= min_pts;
+  }
+  __device__ void emit(int64_t v, int64_t pos, bool f) const {
+    qual[v] = f ? 1 : 0;
+    out_rank[v] = static_cast<int>(pos);
+  }
+};
+struct KeptPoints {  // compaction of the points that survive the crop, original order
+  const float4* pts;
+  const unsigned char* keep;
+  float4* out;
+  __device__ bool flag(int64_t i) const { return keep[i] != 0; }
+  __device__ void emit(int64_t i, int64_t pos, bool f) const {
+    if (f) out[pos] = pts[i];
+  }
+};
 
 // One thread per occupied voxel.  CentroidPoint<PointXYZI> (PCL): f32 accumulators for xyz and
 // intensity, divided by the point count; members are visited in ascending point index.
@@ -250,34 +271,19 @@ int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float 
   LGS_TRY(ctx->tmp[2].reserve(n * 4));
   LGS_TRY(ctx->tmp[3].reserve(n * 4));
   LGS_TRY(ctx->tmp[4].reserve(n * 4));
-  cub::DoubleBuffer<unsigned> dkeys(ctx->tmp[1].as<unsigned>(), ctx->tmp[3].as<unsigned>());
-  cub::DoubleBuffer<unsigned> dvals(ctx->tmp[2].as<unsigned>(), ctx->tmp[4].as<unsigned>());
-  voxel_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, keep, n, g, dkeys.Current(), dvals.Current(), voxel_idx_dev, member_rank_dev);
+  unsigned *keys0 = ctx->tmp[1].as<unsigned>(), *vals0 = ctx->tmp[2].as<unsigned>();
+  voxel_key_kernel<<<grid_for(n, 256), 256, 0, st>>>(pts, keep, n, g, keys0, vals0, voxel_idx_dev, member_rank_dev);
   ctx->launches++;
-  {
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, dkeys, dvals, static_cast<int>(n), 0, end_bit, st);
-    LGS_TRY(ctx->cub_tmp.reserve(tb));
-    cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, dkeys, dvals, static_cast<int>(n), 0, end_bit, st);
-    ctx->launches += (end_bit + 7) / 8 + 2;
-  }
-  out->keys = dkeys.Current();
-  out->vals = dvals.Current();
+  unsigned *skeys, *svals;
+  LGS_TRY(radix_sort_pairs(ctx, keys0, vals0, ctx->tmp[3].as<unsigned>(), ctx->tmp[4].as<unsigned>(), n, end_bit, &skeys, &svals));
+  out->keys = skeys;
+  out->vals = svals;
 
   // segment heads -> start offsets
-  LGS_TRY(ctx->tmp[5].reserve(static_cast<size_t>(n_kept) * (1 + 4) + 64));
-  unsigned char* flags = ctx->tmp[5].as<unsigned char>();
-  int* seg_start = reinterpret_cast<int*>(flags + ((n_kept + 15) / 16) * 16);
+  LGS_TRY(ctx->tmp[5].reserve(static_cast<size_t>(n_kept) * 4 + 64));
+  int* seg_start = ctx->tmp[5].as<int>();
   int* d_nseg = reinterpret_cast<int*>(reinterpret_cast<char*>(acc) + 48);
-  head_flag_kernel<<<grid_for(n_kept, 256), 256, 0, st>>>(out->keys, n_kept, flags);
-  {
-    size_t tb = 0;
-    cub::CountingInputIterator<int> it(0);
-    cub::DeviceSelect::Flagged(nullptr, tb, it, flags, seg_start, d_nseg, static_cast<int>(n_kept), st);
-    LGS_TRY(ctx->cub_tmp.reserve(tb));
-    cub::DeviceSelect::Flagged(ctx->cub_tmp.p, tb, it, flags, seg_start, d_nseg, static_cast<int>(n_kept), st);
-    ctx->launches += 3;
-  }
+  LGS_TRY(scan_select(ctx, SegmentHeads{out->keys, seg_start}, n_kept, d_nseg));
   int* h_small = ctx->pin.as<int>() + 32;
   LGS_CUDA(cudaMemcpyAsync(h_small, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
   LGS_CUDA(cudaStreamSynchronize(st));
@@ -307,12 +313,8 @@ int voxelgrid_device(lgs_ctx* ctx, const float4* pts, int64_t n, const float lea
       if (!sv.keep) {
         LGS_CUDA(cudaMemcpyAsync(out_pts_dev, pts, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToDevice, st));
       } else {
-        size_t tb = 0;
-        LGS_TRY(ctx->tmp[5].reserve(sizeof(int)));
-        cub::DeviceSelect::Flagged(nullptr, tb, pts, sv.keep, out_pts_dev, ctx->tmp[5].as<int>(), static_cast<int>(n), st);
-        LGS_TRY(ctx->cub_tmp.reserve(tb));
-        cub::DeviceSelect::Flagged(ctx->cub_tmp.p, tb, pts, sv.keep, out_pts_dev, ctx->tmp[5].as<int>(), static_cast<int>(n), st);
-        ctx->launches += 2;
+        LGS_TRY(ctx->tmp[5].reserve(64));
+        LGS_TRY(scan_select(ctx, KeptPoints{pts, sv.keep, out_pts_dev}, n, ctx->tmp[5].as<int>()));
       }
       LGS_CUDA(cudaGetLastError());
     }
@@ -328,12 +330,7 @@ int voxelgrid_device(lgs_ctx* ctx, const float4* pts, int64_t n, const float lea
     LGS_TRY(ctx->tmp[7].reserve(static_cast<size_t>(n_seg) * 8 + 64));
     qual = ctx->tmp[7].as<int>();
     out_rank = qual + n_seg;
-    qualify_kernel<<<grid_for(n_seg, 256), 256, 0, st>>>(sv.seg_start, n_seg, n_kept, min_pts, qual);
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, qual, out_rank, n_seg, st);
-    LGS_TRY(ctx->cub_tmp.reserve(tb));
-    cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tb, qual, out_rank, n_seg, st);
-    ctx->launches += 3;
+    LGS_TRY(scan_select(ctx, QualifiedVoxels{sv.seg_start, n_seg, static_cast<int>(n_kept), min_pts, qual, out_rank}, n_seg, nullptr));
     LGS_CUDA(cudaMemcpyAsync(h_small, qual + n_seg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     LGS_CUDA(cudaMemcpyAsync(h_small + 1, out_rank + n_seg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     LGS_CUDA(cudaStreamSynchronize(st));

@@ -317,3 +317,23 @@ def loop_pairs(n_pairs=8, n_keyframes=41, n_beams=64, n_azimuth=1875, scan_leaf=
         submaps.append(d["submap%d" % u])
         corrections.append(np.linalg.inv(off))
     return scans, submaps, corrections
+
+
+def rolling_map(n_points=20_000_000, seed=SEED):
+    """cfg 3: a large rolling map of exactly `n_points` points: the cfg 0 local map (20 keyframes of the synthetic
+    world) laid out again and again along the drive (60 m apart, alternate rows 35 m to the side, each copy with its own
+    sub-voxel shift so that no two copies voxelise alike), plus the cfg 0 sweep and guess, which register against the
+    first copy.  Returns dict(source, target, T_true, guess)."""
+    d = ndt_scan_to_map(seed=seed)
+    base = d["target"]
+    n_copies = (n_points + len(base) - 1) // len(base)
+    rs = np.random.RandomState((seed ^ 0x5EED) & 0x7FFFFFFF)
+    out = np.empty((n_copies * len(base), 4), np.float32)
+    for j in range(n_copies):
+        shift = np.array([60.0 * (j // 2), 35.0 * (j % 2), 0.0], np.float32)
+        if j:
+            shift += rs.uniform(-0.5, 0.5, 3).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
+        blk = out[j * len(base):(j + 1) * len(base)]
+        blk[:, :3] = base[:, :3] + shift
+        blk[:, 3] = base[:, 3]
+    return dict(source=d["source"], target=out[:n_points], T_true=d["T_true"], guess=d["guess"])

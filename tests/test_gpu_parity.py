@@ -199,6 +199,20 @@ def test_ndt_cfg0_synthetic_scan_to_map(api, oracle):
     assert g.calculateScore(g.getFinalTransformation()) == pytest.approx(o.calculateScore(o.final_transformation), rel=1e-9)
 
 
+@pytest.mark.parametrize("res", [1.0, 0.5])
+def test_ndt_cfg3_rolling_map_20m(api, oracle, res):
+    """cfg 3 at full size: 120 000-pt sweep against the 20 M-point rolling map at 1.0 m and 0.5 m.  The voxel table of
+    all 20 M points equals the oracle's (occupancy, counts and validity bit-exact; means / covariances 1e-9), the
+    align takes the same iterations to the same pose."""
+    from lidar_graph_slam_b200 import synth
+    d = synth.rolling_map()
+    assert d["target"].shape == (20_000_000, 4)
+    g, o = _ndt_pair(api, oracle, d["target"], d["source"], res=res)
+    vo, valid = _compare_voxels(g, o)
+    assert valid.sum() > 100_000
+    _compare_align(g, o, d["guess"])
+
+
 def test_ndt_hash_table_path_and_refusal(api, oracle):
     """A sparse, very wide target forces the hashed cell table; results must equal the dense-table oracle semantics.
     A grid above INT32_MAX cells is refused like VGC:79-84 (every lookup misses, align returns the guess)."""
@@ -232,6 +246,24 @@ def test_ndt_set_target_always_rebuilds(api, oracle, velodyne_pair):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,bits", [(1, 8), (2, 1), (31, 5), (1024, 8), (1025, 9), (4097, 13), (262144, 21), (1048576 + 77, 30), (3000001, 32)])
+def test_radix_sort_pairs_stable_and_exact(api, n, bits):
+    """The device sort that orders points by voxel: same permutation as numpy's stable sort (bit-exact, ties in input
+    order), for both tile sizes, partial last tiles, clustered keys (long runs of one voxel, as in a sweep) and 1..4
+    digit passes."""
+    rs = np.random.RandomState(n % 9973)
+    mask = np.uint64((1 << bits) - 1)
+    keys = (rs.randint(0, 1 << 32, n, dtype=np.uint64) & mask).astype(np.uint32)
+    if n > 1000:  # runs of equal keys and a heavily skewed digit
+        keys[: n // 3] = np.repeat(keys[: n // 3: 37], 37)[: n // 3]
+        keys[n // 2: n // 2 + n // 8] = keys[0]
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    ks, vs = api.sort_pairs(keys, vals, bits)
+    assert np.array_equal(ks, keys[order])
+    assert np.array_equal(vs, vals[order])
+
+
 def test_knn_exact(api, oracle, velodyne_pair):
     pts = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
     q = oracle.voxel_grid(velodyne_pair["source"], 0.4)["points"]
