@@ -48,18 +48,11 @@ def _env_int(name, default):
 def make_workload(rank):
     """Target map + a pool of source sweeps with perturbed guesses, distinct per rank (multi-sequence)."""
     from lidar_graph_slam_b200 import synth
-    d = synth.ndt_scan_to_map(perturb_seed=1 + rank, seed=synth.SEED + 7919 * rank)
-    sweeps, guesses = [d["source"]], [d["guess"]]
-    rs = np.random.RandomState(100 + rank)
-    # further "scans" of the sequence: the same sweep geometry re-observed with fresh noise is not available without
-    # re-casting, so the pool perturbs the initial guess (what changes from scan to scan for the optimiser) and
-    # rotates through physically re-cast sweeps when present
-    for k in range(1, N_SWEEP_POOL):
-        dd = np.array([0.3, 0.3, 0.05, np.radians(0.5), np.radians(0.5), np.radians(2.0)]) * rs.uniform(-1, 1, 6)
-        P = synth.pose_matrix(dd[0], dd[1], dd[5], z=dd[2], roll=dd[3], pitch=dd[4])
-        sweeps.append(d["source"])
-        guesses.append((d["T_true"] @ P).astype(np.float32))
-    return d["target"], sweeps, guesses, d["T_true"]
+    seed = synth.SEED + 7919 * rank
+    d = synth.ndt_scan_to_map(perturb_seed=1 + rank, seed=seed)
+    # further scans of the sequence: sweeps physically re-cast 0.5 m apart with fresh noise and their own guesses
+    sweeps, guesses, poses = synth.ndt_sweep_pool(d, N_SWEEP_POOL, seed=seed, perturb_seed=1 + rank)
+    return d["target"], sweeps, guesses, poses
 
 
 class ClockSampler:
@@ -109,6 +102,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            j = json.load(f)
+        return float(j["dram_bytes_per_launch"]), j.get("source")
+    except Exception:
+        return None, None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -121,7 +132,7 @@ def measured_peak_hbm():
 def cpu_baseline(target, sweeps, guesses, budget_s=20.0, threads=0):
     """The oracle (kind 'port': CPU restatement of the reference's ndt_omp path) on the host cores, bounded sample."""
     from oracle import pyoracle as O
-    nthreads = threads or O.max_threads()
+    nthreads = threads or host_threads()
     n = O.NDT()
     n.setNumThreads(nthreads)
     n.setResolution(NDT_PARAMS["resolution"])
@@ -149,7 +160,7 @@ def run_reference(args, rank, world):
         return
     from oracle import pyoracle as O
     target, sweeps, guesses, _ = make_workload(0)
-    nthreads = O.max_threads()
+    nthreads = host_threads()
     n = O.NDT()
     n.setNumThreads(nthreads)
     n.setResolution(NDT_PARAMS["resolution"])
@@ -175,8 +186,8 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = steps / dt
     line = {"impl": "reference", "metric": "ndt_scan_to_map_aligns_per_sec", "value": val, "unit": "aligns/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 terms / f64 accumulation",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "impl_note": "oracle port of pclomp::NDT (reference needs PCL/Eigen, unbuildable here)"},
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "arithmetic": "f32 terms, f64 accumulation and optimiser state", "impl_note": "oracle port of pclomp::NDT (reference needs PCL/Eigen, unbuildable here)"},
             "cpu_baseline": {"value": val, "unit": "aligns/s", "cores": nthreads, "kind": "port",
                              "sample": "%d aligns of the cfg0 workload, %d OpenMP threads" % (steps, nthreads)},
             "e2e": {"value": val, "unit": "aligns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -243,7 +254,7 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
-    target, sweeps, guesses, T_true = make_workload(rank)
+    target, sweeps, guesses, poses = make_workload(rank)
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     ctx = api.Context(local_rank, stream.cuda_stream)
@@ -309,7 +320,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # accuracy sanity of the timed workload (not a parity test: those live in tests/)
-    E = np.linalg.inv(T_true) @ ndt.getFinalTransformation().astype(np.float64)
+    step_dev(0)
+    E = np.linalg.inv(poses[0]) @ ndt.getFinalTransformation().astype(np.float64)
     t_err = float(np.linalg.norm(E[:3, 3]))
 
     # per-kernel timing pass for the roofline (CUDA events around every evaluation launch, same stream)
@@ -324,6 +336,7 @@ def main():
     kern_ms = prof["hess_ms"] / max(prof["hess_launches"], 1)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     peak, peak_src = measured_peak_hbm()
+    traffic, traffic_src = ncu_traffic()
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device="cuda:%d" % local_rank)
@@ -340,15 +353,16 @@ def main():
             loop = {"error": repr(e)}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(target, sweeps, guesses)
 
     if rank == 0:
         line = {
             "metric": "ndt_scan_to_map_aligns_per_sec", "value": total_steps / (ms_dev_max * 1e-3), "unit": "aligns/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 terms / f64 accumulation", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "ndt": NDT_PARAMS, "n_source": int(n_src), "n_target": int(target.shape[0]),
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arithmetic": "f32 terms, f64 accumulation and optimiser state", "ndt": NDT_PARAMS,
+                       "sweep_pool": "%d distinct re-cast sweeps, each with its own perturbed guess" % len(sweeps), "n_source": int(n_src), "n_target": int(target.shape[0]),
                        "voxels": int(gi.n_voxels), "valid_voxels": int(gi.n_valid), "cell_table": "dense" if gi.dense else "hash",
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pairs); within an align the 1.9 MB sweep and the voxel table are re-read from L2 by design",
                        "parallelism": "1 sequence per GPU (replicas, no collective)" if world > 1 else "single GPU",
@@ -356,7 +370,7 @@ def main():
             "e2e": {"value": total_steps / (ms_host_max * 1e-3), "unit": "aligns/s", "h2d_bytes_per_step": int(n_src) * 16 + 64,
                     "d2h_bytes_per_step": int(round(evals_host / K * 44 * 8))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "ndt_derivatives_kernel<true>", "kernel_ms": kern_ms, "launches_timed": prof["hess_launches"],
                          "algorithmic_bytes": alg_bytes, "h_bar": hbar, "peak_source": peak_src,
                          "other_kernels_ms": {"ndt_derivatives_kernel<false>": prof["grad_ms"] / max(prof["grad_launches"], 1),

@@ -247,9 +247,28 @@ def ndt_scan_to_map(n_map=1_000_000, n_keyframes=20, n_beams=64, n_azimuth=1875,
         d = np.array([0.3, 0.3, 0.05, np.radians(0.5), np.radians(0.5), np.radians(2.0)]) * rs.uniform(-1, 1, 6)
         P = pose_matrix(d[0], d[1], d[5], z=d[2], roll=d[3], pitch=d[4])
         guess = pose_s @ P
-        return dict(source=source, target=np.ascontiguousarray(target, np.float32), T_true=pose_s, guess=guess.astype(np.float32))
+        return dict(source=source, target=np.ascontiguousarray(target, np.float32), T_true=pose_s, guess=guess.astype(np.float32),
+                    n_keyframes_used=np.int64(k))
 
-    return _cached("ndt_scan_to_map", (n_map, n_keyframes, n_beams, n_azimuth, map_leaf, seed, perturb_seed, 3), make)
+    return _cached("ndt_scan_to_map", (n_map, n_keyframes, n_beams, n_azimuth, map_leaf, seed, perturb_seed, 4), make)
+
+
+def ndt_sweep_pool(d, n_sweeps, n_beams=64, n_azimuth=1875, seed=SEED, perturb_seed=1):
+    """Further scans of the cfg 0 sequence against the same local map `d` (an ndt_scan_to_map result): sweeps re-cast
+    from poses 0.5 m apart behind the first one, each with its own range noise and its own perturbed guess.
+    Returns (sweeps, guesses, true_poses) including d's own sweep first."""
+    w = World(seed)
+    k = int(d["n_keyframes_used"])
+    sweeps, guesses, poses = [d["source"]], [d["guess"]], [d["T_true"]]
+    rs = np.random.RandomState(1000 + perturb_seed)
+    for j in range(1, n_sweeps):
+        pose = trajectory_pose(k - 1 + 0.5 - 0.5 * j)
+        sweeps.append(cast_sweep(w, pose, frame=10_000 + j, n_beams=n_beams, n_azimuth=n_azimuth))
+        dd = np.array([0.3, 0.3, 0.05, np.radians(0.5), np.radians(0.5), np.radians(2.0)]) * rs.uniform(-1, 1, 6)
+        P = pose_matrix(dd[0], dd[1], dd[5], z=dd[2], roll=dd[3], pitch=dd[4])
+        guesses.append((pose @ P).astype(np.float32))
+        poses.append(pose)
+    return sweeps, guesses, poses
 
 
 def prefilter_sweeps(n_sweeps=4, n_beams=128, n_azimuth=2048, seed=SEED):
