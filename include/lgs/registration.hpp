@@ -92,6 +92,44 @@ class VoxelGrid {
   lgs_voxelgrid_info info_{};
 };
 
+// pcl::StatisticalOutlierRemoval<PointXYZI> as the prefilter node drives it (PPF:132-140)
+class StatisticalOutlierRemoval {
+ public:
+  explicit StatisticalOutlierRemoval(std::shared_ptr<Context> ctx = defaultContext()) : ctx_(std::move(ctx)) {
+    ok_ = lgs_sor_create(ctx_->get(), &h_) == LGS_OK;
+  }
+  ~StatisticalOutlierRemoval() { lgs_sor_destroy(h_); }
+  StatisticalOutlierRemoval(const StatisticalOutlierRemoval&) = delete;
+  StatisticalOutlierRemoval& operator=(const StatisticalOutlierRemoval&) = delete;
+  void setMeanK(int k) { ok_ = lgs_sor_set_mean_k(h_, k) == LGS_OK && ok_; }
+  void setStddevMulThresh(double m) { ok_ = lgs_sor_set_stddev_mul_thresh(h_, m) == LGS_OK && ok_; }
+  void setNegative(bool negative) { ok_ = lgs_sor_set_negative(h_, negative ? 1 : 0) == LGS_OK && ok_; }
+  void setInputCloud(const std::shared_ptr<const PointCloud>& cloud) { input_ = cloud; }
+  void filter(PointCloud& output) {
+    output.clear();
+    if (!input_ || !h_) return;
+    const int64_t n = static_cast<int64_t>(input_->size());
+    std::vector<float> packed(static_cast<size_t>(n > 0 ? n : 1) * 4);
+    keep_.assign(static_cast<size_t>(n), 0);
+    ok_ = lgs_sor_filter(h_, input_->data(), n, sizeof(PointXYZI), packed.data(), keep_.data(), nullptr, &info_) == LGS_OK;
+    if (!ok_) return;
+    output.resize(static_cast<size_t>(info_.n_out));
+    for (int64_t i = 0; i < info_.n_out; i++)
+      output[i] = PointXYZI{packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], 1.0f, packed[4 * i + 3], 0, 0, 0};
+  }
+  const std::vector<uint8_t>& keptMask() const { return keep_; }
+  const lgs_sor_info& info() const { return info_; }
+  bool ok() const { return ok_; }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  lgs_sor* h_ = nullptr;
+  bool ok_ = true;
+  std::shared_ptr<const PointCloud> input_;
+  std::vector<uint8_t> keep_;
+  lgs_sor_info info_{};
+};
+
 // pcl::Registration<PointXYZI, PointXYZI> surface shared by both methods
 class Registration {
  public:

@@ -85,6 +85,32 @@ int lgs_voxelgrid_filter_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, cons
                              int32_t* out_voxel_idx_dev, int32_t* out_member_rank_dev, lgs_voxelgrid_info* info);
 
 /* ------------------------------------------------------------------------------------------- */
+/* prefilter, second stage: pcl::StatisticalOutlierRemoval<PointXYZI>                            */
+/*   replaces PPF:132-140 (outlier_filter: setInputCloud / setMeanK / setStddevMulThresh /        */
+/*   filter), called on the voxel grid's output at PPF:79-80                                      */
+typedef struct lgs_sor lgs_sor;
+
+typedef struct lgs_sor_info {
+  int64_t n_out;     /* points kept */
+  double mean;       /* mean of the per-point mean neighbour distances */
+  double stddev;     /* their sample standard deviation */
+  double threshold;  /* mean + stddev_mul * stddev */
+} lgs_sor_info;
+
+int lgs_sor_create(lgs_ctx* ctx, lgs_sor** out);
+void lgs_sor_destroy(lgs_sor* sor);
+int lgs_sor_set_mean_k(lgs_sor* sor, int32_t mean_k);              /* setMeanK, PPF:137; 1..31 */
+int lgs_sor_set_stddev_mul_thresh(lgs_sor* sor, double mul);       /* setStddevMulThresh, PPF:138 */
+int lgs_sor_set_negative(lgs_sor* sor, int32_t negative);          /* pcl::FilterIndices::setNegative */
+/* filter (PPF:139): out_pts (capacity n packed xyzi) receives the kept points in input order; out_keep[n] the per-point
+ * decision; out_distances[n] the per-point mean distance to its mean_k nearest neighbours.  Any output may be NULL.
+ * The cloud must be finite (the voxel grid's output always is). */
+int lgs_sor_filter(lgs_sor* sor, const void* pts, int64_t n, int32_t stride_bytes, float* out_pts, uint8_t* out_keep,
+                   float* out_distances, lgs_sor_info* info);
+int lgs_sor_filter_dev(lgs_sor* sor, const float* pts_dev, int64_t n, float* out_pts_dev, uint8_t* out_keep_dev,
+                       float* out_distances_dev, lgs_sor_info* info);
+
+/* ------------------------------------------------------------------------------------------- */
 /* shared result of one registration (both methods)                                              */
 typedef struct lgs_align_result {
   float T[16];               /* getFinalTransformation(), column-major */

@@ -21,6 +21,10 @@ class VoxelGridInfo(C.Structure):
                 ("min_b", C.c_int32 * 3), ("max_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3)]
 
 
+class SorInfo(C.Structure):
+    _fields_ = [("n_out", C.c_int64), ("mean", C.c_double), ("stddev", C.c_double), ("threshold", C.c_double)]
+
+
 class AlignResult(C.Structure):
     _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("trans_probability", C.c_double), ("iterations", C.c_int32),
                 ("converged", C.c_int32), ("evaluations", C.c_int32), ("line_search_trials", C.c_int32),
@@ -50,6 +54,13 @@ SYMBOLS = {
     "lgs_ctx_launch_count": (_i64, [_vp]),
     "lgs_voxelgrid_filter": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
     "lgs_voxelgrid_filter_dev": (_i32, [_vp, _vp, _i64, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
+    "lgs_sor_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_sor_destroy": (None, [_vp]),
+    "lgs_sor_set_mean_k": (_i32, [_vp, _i32]),
+    "lgs_sor_set_stddev_mul_thresh": (_i32, [_vp, _f64]),
+    "lgs_sor_set_negative": (_i32, [_vp, _i32]),
+    "lgs_sor_filter": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, C.POINTER(SorInfo)]),
+    "lgs_sor_filter_dev": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(SorInfo)]),
     "lgs_ndt_create": (_i32, [_vp, C.POINTER(_vp)]),
     "lgs_ndt_destroy": (None, [_vp]),
     "lgs_ndt_set_resolution": (_i32, [_vp, _f32]),

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AlignResult, BatchParams, NdtGridInfo, VoxelGridInfo, check
+from ._lib import AlignResult, BatchParams, NdtGridInfo, SorInfo, VoxelGridInfo, check
 
 NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = 0, 1, 2, 3, 4
@@ -152,6 +152,59 @@ class VoxelGrid:
         self.voxel_idx = vidx[:n] if want_membership else None
         self.member_rank = rank[:n] if want_membership else None
         return out[: info.n_out].copy()
+
+
+class StatisticalOutlierRemoval:
+    """pcl::StatisticalOutlierRemoval<PointXYZI> as the prefilter node drives it right after the voxel grid
+    (PPF:79-80,132-140)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_sor_create(self.ctx._h, C.byref(h)))
+        self._h = h
+        self._cloud = None
+        self.info = None
+        self.keep = None
+        self.distances = None
+
+    def setMeanK(self, k): check(self._L.lgs_sor_set_mean_k(self._h, int(k)))
+    def setStddevMulThresh(self, m): check(self._L.lgs_sor_set_stddev_mul_thresh(self._h, float(m)))
+    def setNegative(self, negative): check(self._L.lgs_sor_set_negative(self._h, 1 if negative else 0))
+    def setInputCloud(self, cloud): self._cloud = cloud
+
+    def filter(self):
+        """Returns the kept points (M, 4) in input order; the per-point decision and mean neighbour distance land in
+        the attributes `keep` and `distances`."""
+        info = SorInfo()
+        if _is_torch(self._cloud):
+            import torch
+            p, n = _dev_cloud(self._cloud)
+            dev = self._cloud.device
+            out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+            keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            dist = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+            check(self._L.lgs_sor_filter_dev(self._h, p, n, C.c_void_p(out.data_ptr()), C.c_void_p(keep.data_ptr()), C.c_void_p(dist.data_ptr()),
+                                             C.byref(info)))
+            self.info, self.keep, self.distances = info, keep[:n].bool(), dist[:n]
+            return out[: info.n_out]
+        a, p, n, stride = _host_cloud(self._cloud)
+        out = np.empty((max(n, 1), 4), np.float32)
+        keep = np.empty(max(n, 1), np.uint8)
+        dist = np.empty(max(n, 1), np.float32)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        check(self._L.lgs_sor_filter(self._h, p, n, stride, vp(out), vp(keep), vp(dist), C.byref(info)))
+        self.info, self.keep, self.distances = info, keep[:n].astype(bool), dist[:n]
+        return out[: info.n_out].copy()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.lgs_sor_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class _Registration:

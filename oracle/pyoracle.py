@@ -75,6 +75,12 @@ def lib():
         L.orc_knn.argtypes = [vp, C.c_long, vp, C.c_long, C.c_int, vp, vp, C.c_int]
         L.orc_fitness.restype = C.c_double
         L.orc_fitness.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_double, C.c_int]
+        L.orc_sor_run.restype = vp
+        L.orc_sor_run.argtypes = [vp, C.c_long, C.c_int, C.c_double, C.c_int]
+        L.orc_sor_out_n.restype = C.c_long
+        L.orc_sor_out_n.argtypes = [vp]
+        L.orc_sor_get.argtypes = [vp] * 5
+        L.orc_sor_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -116,6 +122,24 @@ def voxel_grid(pts, leaf, min_points_per_voxel=0, range_min=-1.0, box=None):
                     min_b=grid[0:3].copy(), max_b=grid[3:6].copy(), div_b=grid[6:9].copy(), n_kept=L.orc_vg_n_kept(h))
     finally:
         L.orc_vg_free(h)
+
+
+def statistical_outlier_removal(pts, mean_k=30, stddev_mul=1.2, negative=False):
+    """Oracle of pcl::StatisticalOutlierRemoval as the prefilter node uses it (PPF:132-140).  Returns a dict."""
+    L = lib()
+    pts = _pts(pts)
+    n = pts.shape[0]
+    h = L.orc_sor_run(_p(pts), n, int(mean_k), float(stddev_mul), 1 if negative else 0)
+    try:
+        m = L.orc_sor_out_n(h)
+        out = np.empty((m, 4), np.float32)
+        dist = np.empty(n, np.float32)
+        keep = np.empty(n, np.uint8)
+        stats = np.zeros(3)
+        L.orc_sor_get(h, _p(out), _p(dist), _p(keep), _p(stats))
+    finally:
+        L.orc_sor_free(h)
+    return dict(points=out, distances=dist, keep=keep.astype(bool), mean=stats[0], stddev=stats[1], threshold=stats[2])
 
 
 class NDT:

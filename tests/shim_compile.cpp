@@ -1,5 +1,5 @@
 // Compile-and-link check of the header-only C++ shim (include/lgs/registration.hpp) against liblgs_b200.so.
-// Mirrors the reference's call sequence (LSM:149,162-172; PPF:118-120).  Runs the calls only when a GPU exists.
+// Mirrors the reference's call sequence (LSM:149,162-172; PPF:118-120,136-139).  Runs the calls only when a GPU exists.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -22,6 +22,13 @@ int main(int argc, char** argv) {
   vg.setInputCloud(cloud);
   lgs::PointCloud filtered;
   vg.filter(filtered);
+  lgs::StatisticalOutlierRemoval sor;  // PPF:132-140, on the voxel grid's output
+  sor.setMeanK(30);
+  sor.setStddevMulThresh(1.2);
+  sor.setInputCloud(std::make_shared<lgs::PointCloud>(filtered));
+  lgs::PointCloud inliers;
+  sor.filter(inliers);
+  if (!sor.ok() || inliers.empty() || inliers.size() > filtered.size()) return 2;
   std::shared_ptr<lgs::Registration> registration = std::make_shared<lgs::NormalDistributionsTransform>();
   auto ndt = std::static_pointer_cast<lgs::NormalDistributionsTransform>(registration);
   ndt->setTransformationEpsilon(0.01);

@@ -246,6 +246,45 @@ def test_ndt_set_target_always_rebuilds(api, oracle, velodyne_pair):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def test_statistical_outlier_removal_parity(api, oracle, velodyne_pair):
+    """Second prefilter stage (PPF:132-140): per-point mean neighbour distances bit-identical to the oracle's, the same
+    threshold (1e-12), the same kept set in the same order; mean_k / multiplier / negative variants; chained after the
+    voxel grid on a 128-beam sweep like the node does; device-resident input."""
+    import torch
+    from lidar_graph_slam_b200 import synth
+    clouds = [oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"],
+              oracle.voxel_grid(synth.prefilter_sweeps(n_sweeps=1)[0], 0.2, range_min=1.0)["points"]]
+    for pts in clouds:
+        for mean_k, mul, neg in ((30, 1.2, False), (8, 0.5, False), (30, 1.2, True), (31, 2.0, False)):
+            s = api.StatisticalOutlierRemoval()
+            s.setMeanK(mean_k)
+            s.setStddevMulThresh(mul)
+            s.setNegative(neg)
+            s.setInputCloud(pts)
+            out = s.filter()
+            ref = oracle.statistical_outlier_removal(pts, mean_k, mul, neg)
+            assert np.array_equal(s.distances, ref["distances"])
+            assert s.info.threshold == pytest.approx(ref["threshold"], rel=1e-12)
+            assert s.info.mean == pytest.approx(ref["mean"], rel=1e-12) and s.info.stddev == pytest.approx(ref["stddev"], rel=1e-10)
+            assert np.array_equal(s.keep, ref["keep"])
+            assert np.array_equal(out, ref["points"])
+            assert 0 < len(out) < len(pts)
+    # device-resident input, outputs stay on the device
+    s.setInputCloud(torch.from_numpy(pts).cuda())
+    out_d = s.filter()
+    assert np.array_equal(out_d.cpu().numpy(), out) and np.array_equal(s.keep.cpu().numpy(), ref["keep"])
+    # tiny clouds: fewer points than mean_k + 1, and the empty cloud
+    s = api.StatisticalOutlierRemoval()
+    s.setMeanK(30)
+    s.setStddevMulThresh(1.0)
+    s.setInputCloud(pts[:7])
+    out = s.filter()
+    ref = oracle.statistical_outlier_removal(pts[:7], 30, 1.0)
+    assert np.array_equal(s.distances, ref["distances"]) and np.array_equal(out, ref["points"])
+    s.setInputCloud(np.zeros((0, 4), np.float32))
+    assert len(s.filter()) == 0
+
+
 @pytest.mark.parametrize("n,bits", [(1, 8), (2, 1), (31, 5), (1024, 8), (1025, 9), (4097, 13), (262144, 21), (1048576 + 77, 30), (3000001, 32)])
 def test_radix_sort_pairs_stable_and_exact(api, n, bits):
     """The device sort that orders points by voxel: same permutation as numpy's stable sort (bit-exact, ties in input

@@ -222,6 +222,24 @@ def test_gicp_covariances_plane_structure(oracle, velodyne_pair):
     np.testing.assert_allclose(w, np.tile([1e-3, 1.0, 1.0], (len(pts), 1)), rtol=1e-9)
 
 
+def test_statistical_outlier_removal_against_scipy(oracle, velodyne_pair):
+    """The SOR oracle (restated PCL algorithm, parity unpinned) against an independent scipy/numpy evaluation."""
+    from scipy.spatial import cKDTree
+    pts = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    r = oracle.statistical_outlier_removal(pts, 30, 1.2)
+    xyz = pts[:, :3].astype(np.float64)
+    d, _ = cKDTree(xyz).query(xyz, k=31)
+    md = d[:, 1:].mean(1)
+    np.testing.assert_allclose(r["distances"], md, rtol=2e-6)
+    thr = md.mean() + 1.2 * md.std(ddof=1)
+    assert r["threshold"] == pytest.approx(thr, rel=1e-6)
+    keep = md <= thr
+    assert (keep != r["keep"]).sum() <= 2  # only points within float rounding of the threshold may differ
+    assert np.array_equal(r["points"], pts[r["keep"]])
+    neg = oracle.statistical_outlier_removal(pts, 30, 1.2, negative=True)
+    assert np.array_equal(neg["keep"], ~r["keep"])
+
+
 def test_fitness_definition(oracle, velodyne_pair):
     from scipy.spatial import cKDTree
     tgt = oracle.voxel_grid(velodyne_pair["target"], 0.3)["points"]

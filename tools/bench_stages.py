@@ -55,8 +55,8 @@ def main():
         print(json.dumps(dict(stage=stage, ms_median=ms_med, ms_min=ms_min, algorithmic_bytes=alg_bytes, gbs=gbs, frac_of_hbm_peak=gbs / peak, **kw)), flush=True)
 
     # ---- cfg 1: prefilter
-    sweeps = synth.prefilter_sweeps()
-    sw = torch.from_numpy(sweeps["sweep0"]).cuda()
+    sweeps = synth.prefilter_sweeps(n_sweeps=1)
+    sw = torch.from_numpy(sweeps[0]).cuda()
     for leaf in (0.2, 0.1):
         vg = api.VoxelGrid(ctx)
         vg.setLeafSize(leaf)
@@ -68,7 +68,7 @@ def main():
         med, mn = timed(lambda: vg.filter())
         emit("cfg1 prefilter leaf %.1f (device-resident sweep)" % leaf, med, mn, 16 * n + 4 * n + 4 * n + 16 * v, n=n, voxels=v,
              sweeps_per_s=1e3 / med, launches_per_call=(ctx.launch_count - l0) / (args.reps + 3))
-        host = torch.from_numpy(sweeps["sweep0"]).pin_memory().numpy()
+        host = torch.from_numpy(sweeps[0]).pin_memory().numpy()
         vg.setInputCloud(host)
         med, mn = timed(lambda: vg.filter())
         emit("cfg1 prefilter leaf %.1f (host sweep in, host outputs back)" % leaf, med, mn, 16 * n + 4 * n + 4 * n + 16 * v, n=n, voxels=v, sweeps_per_s=1e3 / med)
