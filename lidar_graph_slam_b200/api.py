@@ -33,9 +33,14 @@ def _host_cloud(pts):
     return a, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1] * 4
 
 
-def _dev_cloud(t):
+def _dev_cloud(t, ctx=None):
+    """Device-resident cloud.  The library works on the context's stream: when that is not torch's current stream
+    (the default context owns a non-blocking stream), torch's pending work on the tensor is waited for first."""
     if not (t.is_cuda and t.dim() == 2 and t.shape[1] == 4 and t.is_contiguous() and str(t.dtype) == "torch.float32"):
         raise ValueError("device cloud must be a contiguous CUDA float32 tensor of shape (N, 4)")
+    if ctx is not None and not ctx.shares_torch_stream(t.device):
+        import torch
+        torch.cuda.current_stream(t.device).synchronize()
     return C.c_void_p(t.data_ptr()), t.shape[0]
 
 
@@ -59,6 +64,14 @@ class Context:
         check(self._L.lgs_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = device
+        self.stream = int(stream) if stream else None
+
+    def shares_torch_stream(self, device=None):
+        """True when the context runs on torch's current stream (stream-ordered with torch work, no sync needed)."""
+        if self.stream is None:
+            return False
+        import torch
+        return torch.cuda.current_stream(device).cuda_stream == self.stream
 
     def synchronize(self):
         check(self._L.lgs_ctx_synchronize(self._h))
@@ -130,13 +143,15 @@ class VoxelGrid:
         info = VoxelGridInfo()
         if _is_torch(self._cloud):
             import torch
-            p, n = _dev_cloud(self._cloud)
+            p, n = _dev_cloud(self._cloud, self.ctx)
             out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=self._cloud.device)
             vidx = torch.empty(max(n, 1), dtype=torch.int32, device=self._cloud.device) if want_membership else None
             rank = torch.empty(max(n, 1), dtype=torch.int32, device=self._cloud.device) if want_membership else None
             check(self._L.lgs_voxelgrid_filter_dev(self.ctx._h, p, n, leaf_p, self._min_pts, self._range_min, box_p, C.c_void_p(out.data_ptr()),
                                                    C.c_void_p(vidx.data_ptr()) if want_membership else None,
                                                    C.c_void_p(rank.data_ptr()) if want_membership else None, C.byref(info)))
+            if not self.ctx.shares_torch_stream(self._cloud.device):
+                self.ctx.synchronize()  # outputs are written on the context's stream; torch reads them on its own
             self.info = info
             self.voxel_idx = vidx[:n] if want_membership else None
             self.member_rank = rank[:n] if want_membership else None
@@ -180,13 +195,15 @@ class StatisticalOutlierRemoval:
         info = SorInfo()
         if _is_torch(self._cloud):
             import torch
-            p, n = _dev_cloud(self._cloud)
+            p, n = _dev_cloud(self._cloud, self.ctx)
             dev = self._cloud.device
             out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
             keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
             dist = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
             check(self._L.lgs_sor_filter_dev(self._h, p, n, C.c_void_p(out.data_ptr()), C.c_void_p(keep.data_ptr()), C.c_void_p(dist.data_ptr()),
                                              C.byref(info)))
+            if not self.ctx.shares_torch_stream(dev):
+                self.ctx.synchronize()
             self.info, self.keep, self.distances = info, keep[:n].bool(), dist[:n]
             return out[: info.n_out]
         a, p, n, stride = _host_cloud(self._cloud)
@@ -217,7 +234,7 @@ class _Registration:
 
     def _set_cloud(self, which, cloud):
         if _is_torch(cloud):
-            p, n = _dev_cloud(cloud)
+            p, n = _dev_cloud(cloud, self.ctx)
             check(self._fn("set_%s_dev" % which)(self._h, p, n))
         else:
             _, p, n, stride = _host_cloud(cloud)
