@@ -5,6 +5,7 @@
 //   lgs::VoxelGrid                      <- pcl::VoxelGrid<pcl::PointXYZI>            (PPF:118-120, GBS:61,311-313,490-493)
 //   lgs::NormalDistributionsTransform   <- pclomp::NormalDistributionsTransform      (LSM:56-72, GBS:101-119)
 //   lgs::FastGICP                       <- fast_gicp::FastGICP                       (LSM:38-54, GBS:82-100)
+//   lgs::GeneralizedIterativeClosestPoint <- pclomp::GeneralizedIterativeClosestPoint (LSM:73-96, GBS:120-141)
 //
 // Clouds are std::vector<lgs::PointXYZI> with pcl::PointXYZI's 32-byte layout; transforms are float[16]
 // column-major (Eigen::Matrix4f memory order), so `Eigen::Map<Eigen::Matrix4f>(m.data())` is a view, not a copy.
@@ -265,6 +266,53 @@ class FastGICP : public Registration {
   std::shared_ptr<Context> ctx_;
   lgs_gicp* h_ = nullptr;
   size_t n_target_ = 0;
+};
+
+// pclomp::GeneralizedIterativeClosestPoint (gicp_omp.h:116-270), the "GICP" registration_method of LSM:73-96 / GBS:120-141
+class GeneralizedIterativeClosestPoint : public Registration {
+ public:
+  explicit GeneralizedIterativeClosestPoint(std::shared_ptr<Context> ctx = defaultContext()) : ctx_(std::move(ctx)) {
+    if (lgs_gicp_omp_create(ctx_->get(), &h_) != LGS_OK) throw std::runtime_error(lgs_last_error());
+  }
+  ~GeneralizedIterativeClosestPoint() override { lgs_gicp_omp_destroy(h_); }
+  void setCorrespondenceRandomness(int k) { k_ = k; check(lgs_gicp_omp_set_correspondence_randomness(h_, k)); }
+  int getCorrespondenceRandomness() const { return k_; }
+  void setMaxCorrespondenceDistance(double d) { check(lgs_gicp_omp_set_max_correspondence_distance(h_, d)); }
+  void setTransformationEpsilon(double e) { check(lgs_gicp_omp_set_transformation_epsilon(h_, e)); }
+  void setRotationEpsilon(double e) { rot_eps_ = e; check(lgs_gicp_omp_set_rotation_epsilon(h_, e)); }
+  double getRotationEpsilon() const { return rot_eps_; }
+  void setMaximumIterations(int n) { check(lgs_gicp_omp_set_maximum_iterations(h_, n)); }
+  void setMaximumOptimizerIterations(int n) { max_inner_ = n; check(lgs_gicp_omp_set_maximum_optimizer_iterations(h_, n)); }
+  int getMaximumOptimizerIterations() const { return max_inner_; }
+  // set by the nodes (LSM:90,93, GBS:138-139) and never read by the reference's computeTransformation (GO:370-516)
+  void setUseReciprocalCorrespondences(bool) {}
+  void setEuclideanFitnessEpsilon(double) {}
+  void setRANSACIterations(int) {}
+  void setInputTarget(const std::shared_ptr<const PointCloud>& c) override {
+    check(lgs_gicp_omp_set_target(h_, c->data(), static_cast<int64_t>(c->size()), sizeof(PointXYZI)));
+  }
+  void setInputSource(const std::shared_ptr<const PointCloud>& c) override {
+    n_source_ = c->size();
+    check(lgs_gicp_omp_set_source(h_, c->data(), static_cast<int64_t>(c->size()), sizeof(PointXYZI)));
+  }
+  void align(PointCloud& output, const Matrix4f& guess = Identity4f()) override {
+    ok_ = true;
+    std::vector<float> packed((n_source_ ? n_source_ : 1) * 4);
+    check(lgs_gicp_omp_align(h_, guess.data(), &result_, packed.data()));
+    if (ok_) fill_output(output, packed, n_source_);
+  }
+  double getFitnessScore(double max_range = DBL_MAX) override {
+    double f = DBL_MAX;
+    check(lgs_gicp_omp_fitness(h_, max_range, &f));
+    return f;
+  }
+  lgs_gicp_omp* handle() const { return h_; }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  lgs_gicp_omp* h_ = nullptr;
+  int k_ = 20, max_inner_ = 20;
+  double rot_eps_ = 2e-3;
 };
 
 }  // namespace lgs

@@ -219,6 +219,37 @@ int lgs_gicp_export_covariances(lgs_gicp* g, int32_t which, double* covs);
  * optionally the per-source-point correspondence index (-1 = none) */
 int lgs_gicp_linearize(lgs_gicp* g, const double* T16_rowmajor, double* cost, double* H36, double* b6, int32_t* correspondences);
 
+/* ------------------------------------------------------------------------------------------- */
+/* PCL-style GICP: pclomp::GeneralizedIterativeClosestPoint (BFGS) behind pcl::Registration       */
+/*   GO = thirdparty/ndt_omp/include/pclomp/gicp_omp_impl.hpp, GO.h = .../gicp_omp.h;             */
+/*   constructed at LSM:73-96 and GBS:120-141 (registration_method "GICP")                        */
+typedef struct lgs_gicp_omp lgs_gicp_omp;
+
+int lgs_gicp_omp_create(lgs_ctx* ctx, lgs_gicp_omp** out);               /* defaults GO.h:116-126 */
+void lgs_gicp_omp_destroy(lgs_gicp_omp* g);
+int lgs_gicp_omp_set_correspondence_randomness(lgs_gicp_omp* g, int32_t k);      /* GO.h:248, LSM:94 */
+int lgs_gicp_omp_set_max_correspondence_distance(lgs_gicp_omp* g, double d);     /* LSM:88 */
+int lgs_gicp_omp_set_transformation_epsilon(lgs_gicp_omp* g, double eps);        /* LSM:92 */
+int lgs_gicp_omp_set_rotation_epsilon(lgs_gicp_omp* g, double eps);              /* GO.h:234 */
+int lgs_gicp_omp_set_maximum_iterations(lgs_gicp_omp* g, int32_t n);             /* LSM:89 */
+int lgs_gicp_omp_set_maximum_optimizer_iterations(lgs_gicp_omp* g, int32_t n);   /* GO.h:262, LSM:91 */
+/* setInputSource / setInputTarget (GO.h:139-169): upload, drop the cloud's covariances */
+int lgs_gicp_omp_set_source(lgs_gicp_omp* g, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_gicp_omp_set_target(lgs_gicp_omp* g, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_gicp_omp_set_source_dev(lgs_gicp_omp* g, const float* pts_dev, int64_t n);
+int lgs_gicp_omp_set_target_dev(lgs_gicp_omp* g, const float* pts_dev, int64_t n);
+/* align (pcl::Registration::align + GO:370-516).  result: iterations = nr_iterations_ (outer iterations),
+ * evaluations = df + fdf functor calls, line_search_trials = operator() calls, hessian_recomputes = BFGS
+ * inner iterations summed over the outer iterations. */
+int lgs_gicp_omp_align(lgs_gicp_omp* g, const float* guess16, lgs_align_result* result, float* out_cloud);
+int lgs_gicp_omp_fitness(lgs_gicp_omp* g, double max_range, double* fitness);
+/* parity hooks: covariances as lgs_gicp_export_covariances (GO:48-122); one outer-iteration set-up at
+ * (transformation_, guess) followed by f(x), df(x), fdf(x) (GO:245-367): out15 = f, df[6], fdf f, fdf g[6],
+ * number of correspondences; corr (n_source, -1 = none) and mahal (n_source x 9 f32) may be NULL */
+int lgs_gicp_omp_export_covariances(lgs_gicp_omp* g, int32_t which, double* covs);
+int lgs_gicp_omp_functor(lgs_gicp_omp* g, const float* guess16, const float* transformation16, const double* x6, double* out15,
+                         int32_t* corr, float* mahal);
+
 /* exact k-NN of `queries` in `pts` (the search behind FG:133 and FG:254); idx/d2 are m x k, ascending */
 int lgs_knn(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const void* queries, int64_t m, int32_t qstride_bytes,
             int32_t k, int32_t* idx, float* d2);

@@ -101,6 +101,22 @@ SYMBOLS = {
     "lgs_gicp_final_hessian": (_i32, [_vp, _vp]),
     "lgs_gicp_export_covariances": (_i32, [_vp, _i32, _vp]),
     "lgs_gicp_linearize": (_i32, [_vp, _vp, C.POINTER(_f64), _vp, _vp, _vp]),
+    "lgs_gicp_omp_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_gicp_omp_destroy": (None, [_vp]),
+    "lgs_gicp_omp_set_correspondence_randomness": (_i32, [_vp, _i32]),
+    "lgs_gicp_omp_set_max_correspondence_distance": (_i32, [_vp, _f64]),
+    "lgs_gicp_omp_set_transformation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_gicp_omp_set_rotation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_gicp_omp_set_maximum_iterations": (_i32, [_vp, _i32]),
+    "lgs_gicp_omp_set_maximum_optimizer_iterations": (_i32, [_vp, _i32]),
+    "lgs_gicp_omp_set_source": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_gicp_omp_set_target": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_gicp_omp_set_source_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_gicp_omp_set_target_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_gicp_omp_align": (_i32, [_vp, _vp, C.POINTER(AlignResult), _vp]),
+    "lgs_gicp_omp_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
+    "lgs_gicp_omp_export_covariances": (_i32, [_vp, _i32, _vp]),
+    "lgs_gicp_omp_functor": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgs_knn": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "lgs_sort_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),

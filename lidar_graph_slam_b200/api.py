@@ -394,6 +394,50 @@ class FastGICP(_Registration):
         return cost.value, H.reshape(6, 6), b, corr[: self._ns]
 
 
+class GeneralizedIterativeClosestPoint(_Registration):
+    """pclomp::GeneralizedIterativeClosestPoint (gicp_omp.h:116-270; BFGS), the "GICP" method of LSM:73-96 / GBS:120-141."""
+
+    _prefix = "gicp_omp"
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_gicp_omp_create(self.ctx._h, C.byref(h)))
+        self._h = h
+        self._ns = self._nt = 0
+
+    def setCorrespondenceRandomness(self, k): check(self._L.lgs_gicp_omp_set_correspondence_randomness(self._h, int(k)))
+    def setMaxCorrespondenceDistance(self, d): check(self._L.lgs_gicp_omp_set_max_correspondence_distance(self._h, float(d)))
+    def setTransformationEpsilon(self, e): check(self._L.lgs_gicp_omp_set_transformation_epsilon(self._h, float(e)))
+    def setRotationEpsilon(self, e): check(self._L.lgs_gicp_omp_set_rotation_epsilon(self._h, float(e)))
+    def setMaximumIterations(self, n): check(self._L.lgs_gicp_omp_set_maximum_iterations(self._h, int(n)))
+    def setMaximumOptimizerIterations(self, n): check(self._L.lgs_gicp_omp_set_maximum_optimizer_iterations(self._h, int(n)))
+    # accepted and ignored, as by the reference's computeTransformation (GO:370-516 never reads them)
+    def setUseReciprocalCorrespondences(self, flag): pass
+    def setEuclideanFitnessEpsilon(self, e): pass
+    def setRANSACIterations(self, n): pass
+    def setNumThreads(self, n): pass
+
+    def covariances(self, which):
+        n = self._ns if which == 0 else self._nt
+        c = np.empty((n, 9))
+        check(self._L.lgs_gicp_omp_export_covariances(self._h, int(which), c.ctypes.data_as(C.c_void_p)))
+        return c.reshape(n, 3, 3)
+
+    def functor(self, guess, transformation, x):
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        gc = np.asarray(guess, np.float32).reshape(4, 4).ravel(order="F").copy()
+        tc = np.asarray(transformation, np.float32).reshape(4, 4).ravel(order="F").copy()
+        x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros(15)
+        corr = np.empty(max(self._ns, 1), np.int32)
+        mahal = np.empty((max(self._ns, 1), 9), np.float32)
+        check(self._L.lgs_gicp_omp_functor(self._h, vp(gc), vp(tc), vp(x), vp(out), vp(corr), vp(mahal)))
+        return dict(f=out[0], df=out[1:7].copy(), fdf_f=out[7], fdf_g=out[8:14].copy(), n_corr=int(out[14]), corr=corr[: self._ns],
+                    mahal=mahal[: self._ns])
+
+
 def knn(pts, queries, k, ctx=None):
     """Exact k-NN of `queries` in `pts` (the search behind FG:133 / FG:254).  Returns (idx (m,k) int32, d2 (m,k) f32)."""
     ctx = ctx or default_context()

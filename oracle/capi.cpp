@@ -172,6 +172,74 @@ double orc_gicp_linearize(void* h, const double* T16_rowmajor, double* H36, doub
   return c;
 }
 
+// ---- pclomp::GeneralizedIterativeClosestPoint (BFGS) ---------------------------------------------
+void* orc_pgicp_create() { return new PclGICP; }
+void orc_pgicp_destroy(void* h) { delete static_cast<PclGICP*>(h); }
+void orc_pgicp_set_params(void* h, int k, double max_corr_dist, double trans_eps, double rot_eps, int max_iter, int max_inner, double gicp_eps,
+                          int num_threads) {
+  PclGICP* g = static_cast<PclGICP*>(h);
+  g->k_correspondences = k;
+  g->corr_dist_threshold = max_corr_dist;
+  g->transformation_epsilon = trans_eps;
+  g->rotation_epsilon = rot_eps;
+  g->max_iterations = max_iter;
+  g->max_inner_iterations = max_inner;
+  g->gicp_epsilon = gicp_eps;
+  if (num_threads > 0) g->num_threads = num_threads;
+}
+void orc_pgicp_set_source(void* h, const float* pts, long n) { static_cast<PclGICP*>(h)->setInputSource(reinterpret_cast<const P4*>(pts), n); }
+void orc_pgicp_set_target(void* h, const float* pts, long n) { static_cast<PclGICP*>(h)->setInputTarget(reinterpret_cast<const P4*>(pts), n); }
+// stats5: f, df, fdf calls, total BFGS inner iterations, correspondences of the last outer iteration
+void orc_pgicp_align(void* h, const float* guess16, float* T16, int* iters, int* converged, float* out_cloud, int* stats5) {
+  PclGICP* g = static_cast<PclGICP*>(h);
+  std::vector<P4> out;
+  g->align(guess16, out_cloud ? &out : nullptr);
+  std::memcpy(T16, g->final_transformation, 16 * sizeof(float));
+  *iters = g->nr_iterations;
+  *converged = g->converged ? 1 : 0;
+  if (out_cloud) std::memcpy(out_cloud, out.data(), out.size() * sizeof(P4));
+  if (stats5) {
+    stats5[0] = g->f_calls;
+    stats5[1] = g->df_calls;
+    stats5[2] = g->fdf_calls;
+    stats5[3] = g->inner_iterations_total;
+    stats5[4] = static_cast<int>(g->corr_src.size());
+  }
+}
+double orc_pgicp_fitness(void* h, double max_range) { return static_cast<PclGICP*>(h)->getFitnessScore(max_range); }
+// which: 0 source, 1 target.  Computes them if missing.  9 doubles per point, row-major.
+void orc_pgicp_covariances(void* h, int which, double* covs) {
+  PclGICP* g = static_cast<PclGICP*>(h);
+  if (which == 0) {
+    if (g->source_covs.size() != g->source.size() * 9) g->computeCovariances(g->source, g->source_tree, g->source_covs);
+    std::memcpy(covs, g->source_covs.data(), g->source_covs.size() * sizeof(double));
+  } else {
+    if (g->target_covs.size() != g->target.size() * 9) g->computeCovariances(g->target, g->target_tree, g->target_covs);
+    std::memcpy(covs, g->target_covs.data(), g->target_covs.size() * sizeof(double));
+  }
+}
+// One outer-iteration set-up at (transformation, guess) followed by the three functor evaluations at x:
+// out15 = f(x), df(x)[6], fdf(x) -> f, g[6], number of correspondences.  corr (n_source ints, -1 = none) and
+// mahal (n_source x 9 floats) are optional.
+void orc_pgicp_functor(void* h, const float* guess16, const float* transformation16, const double* x6, double* out15, int* corr, float* mahal) {
+  PclGICP* g = static_cast<PclGICP*>(h);
+  if (g->target_covs.size() != g->target.size() * 9) g->computeCovariances(g->target, g->target_tree, g->target_covs);
+  if (g->source_covs.size() != g->source.size() * 9) g->computeCovariances(g->source, g->source_tree, g->source_covs);
+  g->output.resize(g->source.size());
+  for (size_t i = 0; i < g->source.size(); i++) g->output[i] = transform_point(guess16, g->source[i]);
+  std::memcpy(g->transformation, transformation16, 16 * sizeof(float));
+  g->update_correspondences(guess16);
+  out15[0] = g->functor_f(x6);
+  g->functor_df(x6, out15 + 1);
+  g->functor_fdf(x6, out15[7], out15 + 8);
+  out15[14] = static_cast<double>(g->corr_src.size());
+  if (corr) {
+    for (size_t i = 0; i < g->source.size(); i++) corr[i] = -1;
+    for (size_t i = 0; i < g->corr_src.size(); i++) corr[g->corr_src[i]] = g->corr_tgt[i];
+  }
+  if (mahal) std::memcpy(mahal, g->mahalanobis.data(), g->mahalanobis.size() * sizeof(float));
+}
+
 // ---- exact k-NN (tree built per call) -----------------------------------------------------------
 void orc_knn(const float* pts, long n, const float* queries, long m, int k, int* idx, float* d2, int num_threads) {
   KdTree t;

@@ -223,4 +223,57 @@ struct FastGICP {
   bool is_converged(const double delta[16]) const;                       // LSQ:82-91
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// pclomp::GeneralizedIterativeClosestPoint (GO = thirdparty/ndt_omp/include/pclomp/gicp_omp_impl.hpp,
+// GO.h = .../gicp_omp.h) over pcl::IterativeClosestPoint / pcl::Registration::align, optimised with PCL's BFGS
+// (pcl/registration/bfgs.h: un-vendored, a port of GSL's vector_bfgs2 restated from its published algorithm;
+// PARITY UNPINNED like the rest of the PCL internals).
+struct BfgsParameters {   // defaults of pcl BFGS::Parameters, then the overrides of GO:212-217
+  int max_iters = 400, bracket_iters = 100, section_iters = 100;
+  double rho = 0.01, sigma = 0.01, tau1 = 9, tau2 = 0.05, tau3 = 0.5, step_size = 1;
+  int order = 3;
+};
+enum { BFGS_NEGATIVE_GRADIENT_EPSILON = -3, BFGS_NOT_STARTED = -2, BFGS_RUNNING = -1, BFGS_SUCCESS = 0, BFGS_NO_PROGRESS = 1 };
+
+struct PclGICP {
+  // GO.h:116-126
+  int k_correspondences = 20;
+  double gicp_epsilon = 0.001;
+  double rotation_epsilon = 2e-3;
+  int max_inner_iterations = 20;
+  int max_iterations = 200;
+  double transformation_epsilon = 5e-4;
+  double corr_dist_threshold = 5.0;
+  int num_threads = 1;
+
+  std::vector<P4> source, target;
+  KdTree source_tree, target_tree;        // tree_reciprocal_ / tree_
+  std::vector<double> source_covs, target_covs;   // 9 doubles per point, row-major (GO:48-122)
+  std::vector<float> mahalanobis;          // 9 floats per source point: the 3x3 block of mahalanobis_[i] (GO:439-452)
+  std::vector<P4> output;                  // the source transformed by the guess (GO:398), w = 1
+  std::vector<int32_t> corr_src, corr_tgt; // the sorted correspondence list of the current outer iteration (GO:458-474)
+  float base_transformation[16];           // column-major; identity (GO:394)
+  float transformation[16], previous_transformation[16], final_transformation[16];
+  int nr_iterations = 0;
+  bool converged = false;
+  int f_calls = 0, df_calls = 0, fdf_calls = 0, inner_iterations_total = 0;
+
+  PclGICP();
+  void setInputSource(const P4* p, size_t n);   // GO.h:139-156
+  void setInputTarget(const P4* p, size_t n);   // GO.h:164-169
+  void align(const float* guess_colmajor, std::vector<P4>* out);   // pcl::Registration::align + GO:370-516
+  double getFitnessScore(double max_range);
+
+  void computeCovariances(const std::vector<P4>& cloud, const KdTree& tree, std::vector<double>& covs) const;  // GO:48-122
+  void update_correspondences(const float* guess_colmajor);     // GO:404-474
+  void applyState(float* t_colmajor, const double x[6]) const;  // GO:518-529
+  void computeRDerivative(const double x[6], const double R[9], double g[6]) const;  // GO:125-178
+  double functor_f(const double x[6]);                          // GO:245-275
+  void functor_df(const double x[6], double g[6]);              // GO:278-330
+  void functor_fdf(const double x[6], double& f, double g[6]);  // GO:333-367
+  // GO:180-242; returns false when the reference would throw (fewer than 4 correspondences / solver failure)
+  bool estimateRigidTransformationBFGS(float* transformation_colmajor);
+};
+
 }  // namespace lgs_oracle

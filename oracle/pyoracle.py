@@ -72,6 +72,16 @@ def lib():
         L.orc_gicp_covariances.argtypes = [vp, C.c_int, vp]
         L.orc_gicp_linearize.restype = C.c_double
         L.orc_gicp_linearize.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_pgicp_create.restype = vp
+        L.orc_pgicp_destroy.argtypes = [vp]
+        L.orc_pgicp_set_params.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.orc_pgicp_set_source.argtypes = [vp, vp, C.c_long]
+        L.orc_pgicp_set_target.argtypes = [vp, vp, C.c_long]
+        L.orc_pgicp_align.argtypes = [vp] * 7
+        L.orc_pgicp_fitness.restype = C.c_double
+        L.orc_pgicp_fitness.argtypes = [vp, C.c_double]
+        L.orc_pgicp_covariances.argtypes = [vp, C.c_int, vp]
+        L.orc_pgicp_functor.argtypes = [vp] * 7
         L.orc_knn.argtypes = [vp, C.c_long, vp, C.c_long, C.c_int, vp, vp, C.c_int]
         L.orc_fitness.restype = C.c_double
         L.orc_fitness.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_double, C.c_int]
@@ -304,6 +314,78 @@ class FastGICP:
         corr = np.empty(self._ns, np.int32)
         c = self._L.orc_gicp_linearize(self._h, _p(Tr), _p(H), _p(b), _p(corr))
         return c, H.reshape(6, 6), b, corr
+
+
+class GeneralizedIterativeClosestPoint:
+    """Oracle of pclomp::GeneralizedIterativeClosestPoint (BFGS; PCL method names, defaults of gicp_omp.h:116-126)."""
+
+    def __init__(self):
+        self._L = lib()
+        self._h = self._L.orc_pgicp_create()
+        self.params = dict(k=20, max_corr_dist=5.0, trans_eps=5e-4, rot_eps=2e-3, max_iter=200, max_inner=20, gicp_eps=1e-3, num_threads=0)
+        self._ns = self._nt = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_pgicp_destroy(self._h)
+            self._h = None
+
+    def _push(self):
+        p = self.params
+        self._L.orc_pgicp_set_params(self._h, p["k"], p["max_corr_dist"], p["trans_eps"], p["rot_eps"], p["max_iter"], p["max_inner"], p["gicp_eps"],
+                                     p["num_threads"])
+
+    def setCorrespondenceRandomness(self, k): self.params["k"] = int(k); self._push()
+    def setMaxCorrespondenceDistance(self, d): self.params["max_corr_dist"] = float(d); self._push()
+    def setTransformationEpsilon(self, e): self.params["trans_eps"] = float(e); self._push()
+    def setRotationEpsilon(self, e): self.params["rot_eps"] = float(e); self._push()
+    def setMaximumIterations(self, n): self.params["max_iter"] = int(n); self._push()
+    def setMaximumOptimizerIterations(self, n): self.params["max_inner"] = int(n); self._push()
+    def setNumThreads(self, n): self.params["num_threads"] = int(n); self._push()
+
+    def setInputSource(self, pts):
+        pts = _pts(pts)
+        self._ns = pts.shape[0]
+        self._L.orc_pgicp_set_source(self._h, _p(pts), pts.shape[0])
+
+    def setInputTarget(self, pts):
+        pts = _pts(pts)
+        self._nt = pts.shape[0]
+        self._L.orc_pgicp_set_target(self._h, _p(pts), pts.shape[0])
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, dtype=np.float32)
+        gc = g.ravel(order="F").copy()
+        T = np.empty(16, np.float32)
+        it, cv = C.c_int(), C.c_int()
+        out = np.empty((self._ns, 4), np.float32)
+        st = np.zeros(5, np.int32)
+        self._L.orc_pgicp_align(self._h, _p(gc), _p(T), C.addressof(it), C.addressof(cv), _p(out), _p(st))
+        self.final_transformation = T.reshape(4, 4, order="F").copy()
+        self.nr_iterations, self.converged = it.value, bool(cv.value)
+        self.stats = dict(f_calls=int(st[0]), df_calls=int(st[1]), fdf_calls=int(st[2]), inner_iterations=int(st[3]), correspondences=int(st[4]))
+        return out
+
+    def hasConverged(self): return self.converged
+    def getFinalTransformation(self): return self.final_transformation
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max): return self._L.orc_pgicp_fitness(self._h, float(max_range))
+
+    def covariances(self, which):
+        n = self._ns if which == 0 else self._nt
+        c = np.empty((n, 9))
+        self._L.orc_pgicp_covariances(self._h, int(which), _p(c))
+        return c.reshape(n, 3, 3)
+
+    def functor(self, guess, transformation, x):
+        """One outer-iteration set-up at (transformation_, guess), then f(x), df(x), fdf(x) (gicp_omp_impl.hpp:245-367)."""
+        gc = np.asarray(guess, np.float32).ravel(order="F").copy()
+        tc = np.asarray(transformation, np.float32).ravel(order="F").copy()
+        x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros(15)
+        corr = np.empty(self._ns, np.int32)
+        mahal = np.empty((self._ns, 9), np.float32)
+        self._L.orc_pgicp_functor(self._h, _p(gc), _p(tc), _p(x), _p(out), _p(corr), _p(mahal))
+        return dict(f=out[0], df=out[1:7].copy(), fdf_f=out[7], fdf_g=out[8:14].copy(), n_corr=int(out[14]), corr=corr, mahal=mahal)
 
 
 def knn(pts, queries, k, num_threads=0):

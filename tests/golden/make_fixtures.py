@@ -70,6 +70,14 @@ def main():
     te, re = pose_error(rel, gi.final_transformation)
     g["gicp_gtest_recipe"] = dict(iterations=gi.nr_iterations, converged=bool(gi.converged), stats=gi.stats, t_err=te, r_err_deg=re,
                                   fitness=gi.getFitnessScore(), T=[float(x) for x in gi.final_transformation.ravel()])
+    go = O.GeneralizedIterativeClosestPoint()
+    go.setNumThreads(1)
+    go.setInputTarget(t2)
+    go.setInputSource(s2)
+    go.align()
+    te, re = pose_error(rel, go.final_transformation)
+    g["gicp_omp_gtest_recipe"] = dict(iterations=go.nr_iterations, converged=bool(go.converged), stats=go.stats, t_err=te, r_err_deg=re,
+                                      fitness=go.getFitnessScore(), T=[float(x) for x in go.final_transformation.ravel()])
     with open(os.path.join(HERE, "oracle_golden.json"), "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(json.dumps(g, indent=1, sort_keys=True)[:1500])

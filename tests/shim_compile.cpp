@@ -42,5 +42,21 @@ int main(int argc, char** argv) {
   registration->align(aligned);
   std::printf("filtered %zu -> converged %d, iterations %d, fitness %.6f\n", filtered.size(), int(registration->hasConverged()),
               ndt->getFinalNumIteration(), registration->getFitnessScore());
-  return registration->hasConverged() ? 0 : 1;
+  if (!registration->hasConverged()) return 1;
+  // the "GICP" method of the nodes (LSM:73-96): pclomp::GeneralizedIterativeClosestPoint with the scan matcher's setters
+  auto gicp = std::make_shared<lgs::GeneralizedIterativeClosestPoint>();
+  gicp->setMaxCorrespondenceDistance(2.0);
+  gicp->setMaximumIterations(30);
+  gicp->setUseReciprocalCorrespondences(false);
+  gicp->setMaximumOptimizerIterations(20);
+  gicp->setTransformationEpsilon(0.01);
+  gicp->setEuclideanFitnessEpsilon(0.01);
+  gicp->setCorrespondenceRandomness(20);
+  registration = gicp;
+  registration->setInputTarget(cloud);
+  registration->setInputSource(std::make_shared<lgs::PointCloud>(filtered));
+  registration->align(aligned);
+  std::printf("GICP (BFGS): converged %d, outer iterations %d, fitness %.6f\n", int(registration->hasConverged()), registration->result().iterations,
+              registration->getFitnessScore());
+  return registration->hasConverged() ? 0 : 3;
 }

@@ -400,6 +400,91 @@ def test_gicp_velodyne_align_parity(api, oracle, velodyne_pair):
     _compare_gicp_align(g, o, guess)
 
 
+def _gicp_omp_pair(api, oracle, target, source, **kw):
+    g, o = api.GeneralizedIterativeClosestPoint(), oracle.GeneralizedIterativeClosestPoint()
+    for x in (g, o):
+        if "max_corr" in kw:
+            x.setMaxCorrespondenceDistance(kw["max_corr"])
+        if "eps" in kw:
+            x.setTransformationEpsilon(kw["eps"])
+        if "max_iter" in kw:
+            x.setMaximumIterations(kw["max_iter"])
+        if "max_inner" in kw:
+            x.setMaximumOptimizerIterations(kw["max_inner"])
+        if "k" in kw:
+            x.setCorrespondenceRandomness(kw["k"])
+        x.setInputTarget(target)
+        x.setInputSource(source)
+    return g, o
+
+
+def test_gicp_omp_covariances_and_functor(api, oracle, velodyne_pair):
+    """pclomp::GeneralizedIterativeClosestPoint pieces: computeCovariances (GO:48-122), the correspondence / Mahalanobis
+    set-up of one outer iteration (GO:404-474) and the three BFGS functor evaluations (GO:245-367)."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _gicp_omp_pair(api, oracle, t2, s2)
+    for which in (0, 1):
+        cg, co = g.covariances(which), o.covariances(which)
+        np.testing.assert_allclose(cg, co, rtol=1e-6, atol=1e-8)
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.2, -0.1, 0.05]
+    trans = np.eye(4, dtype=np.float32)
+    trans[:3, 3] = [0.05, 0.02, -0.01]
+    x = np.array([0.4, 0.1, -0.02, 0.003, -0.004, 0.01])
+    rg, ro = g.functor(guess, trans, x), o.functor(guess, trans, x)
+    assert np.array_equal(rg["corr"], ro["corr"])            # correspondence indices: bit-exact
+    assert rg["n_corr"] == ro["n_corr"] > 7000
+    valid = ro["corr"] >= 0
+    np.testing.assert_allclose(rg["mahal"][valid], ro["mahal"][valid], rtol=1e-6, atol=1e-6)
+    assert rg["f"] == pytest.approx(ro["f"], rel=1e-9)         # f32 terms are bit-identical; only the f64 sum order differs
+    assert rg["fdf_f"] == pytest.approx(ro["fdf_f"], rel=1e-10)
+    np.testing.assert_allclose(rg["df"], ro["df"], rtol=1e-9, atol=1e-10 * np.abs(ro["df"]).max())
+    np.testing.assert_allclose(rg["fdf_g"], ro["fdf_g"], rtol=1e-9, atol=1e-10 * np.abs(ro["fdf_g"]).max())
+    np.testing.assert_allclose(rg["fdf_g"], rg["df"], rtol=1e-12, atol=1e-14)
+
+
+def _compare_gicp_omp_align(g, o, guess=None):
+    og = o.align(guess)
+    gg = g.align(guess, want_output=True)
+    assert g.result.iterations == o.nr_iterations
+    assert bool(g.result.converged) == o.converged
+    # the BFGS trajectory: identical numbers of functor evaluations and inner iterations
+    assert g.result.line_search_trials == o.stats["f_calls"]
+    assert g.result.evaluations == o.stats["df_calls"] + o.stats["fdf_calls"]
+    assert g.result.hessian_recomputes == o.stats["inner_iterations"]
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD
+    assert g.getFitnessScore() == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+    np.testing.assert_allclose(gg, og, atol=2e-4)
+
+
+def test_gicp_omp_velodyne_align_parity(api, oracle, velodyne_pair):
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _gicp_omp_pair(api, oracle, t2, s2)
+    _compare_gicp_omp_align(g, o)
+    t_err, r_err = pose_error(velodyne_pair["relative"], g.getFinalTransformation())
+    assert t_err < 0.05 and np.degrees(r_err) < 1.0 and g.hasConverged()
+    # the same objects again (covariances are kept, GO:381-392), with a non-identity guess and the scan matcher's parameters
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.3, 0.0, 0.0]
+    _compare_gicp_omp_align(g, o, guess)
+    g, o = _gicp_omp_pair(api, oracle, t2, s2, max_corr=2.0, eps=0.01, max_iter=30, max_inner=10)
+    _compare_gicp_omp_align(g, o, guess)
+    # backward
+    g, o = _gicp_omp_pair(api, oracle, s2, t2)
+    _compare_gicp_omp_align(g, o)
+    t_err, r_err = pose_error(velodyne_pair["relative"], np.linalg.inv(g.getFinalTransformation().astype(np.float64)))
+    assert t_err < 0.05 and np.degrees(r_err) < 1.0
+    # fewer points than k: the reference logs an error and cannot proceed; here a state error, never a fallback
+    g = api.GeneralizedIterativeClosestPoint()
+    g.setInputTarget(t2)
+    g.setInputSource(s2[:10])
+    with pytest.raises(RuntimeError):
+        g.align()
+
+
 def test_gicp_cfg2_synthetic_odometry(api, oracle):
     """BASELINE configs[2] in miniature: scan-to-scan GICP over consecutive synthetic 64-beam sweeps, VoxelGrid 0.25 m
     (kitti.cpp:80-82), covariance reuse through swapSourceAndTarget (kitti.cpp:115-125)."""

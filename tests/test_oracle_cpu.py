@@ -202,6 +202,39 @@ def test_gicp_oracle_golden_and_gtest_band(oracle, velodyne_pair, golden):
     assert t_err < 0.05 and np.degrees(r_err) < 1.0 and s.converged
 
 
+def test_gicp_omp_oracle_gtest_band_and_gradient(oracle, velodyne_pair, golden):
+    """pclomp::GeneralizedIterativeClosestPoint restatement (gicp_omp_impl.hpp + PCL's BFGS): the bundled pair converges to
+    relative.txt inside the fast_gicp gtest band, the analytic gradient (df / fdf, GO:278-367) agrees with central differences
+    of the cost (operator(), GO:245-275), and the trajectory is frozen in the golden file."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g = oracle.GeneralizedIterativeClosestPoint()
+    g.setInputTarget(t2)
+    g.setInputSource(s2)
+    g.align()
+    t_err, r_err = pose_error(velodyne_pair["relative"], g.final_transformation)
+    assert g.converged and t_err < 0.05 and np.degrees(r_err) < 1.0
+    gold = golden["gicp_omp_gtest_recipe"]
+    assert g.nr_iterations == gold["iterations"]
+    assert g.stats == gold["stats"]
+    np.testing.assert_allclose(g.final_transformation.ravel(), gold["T"], atol=1e-6)
+    # covariances: eigenvalues (1, 1, gicp_epsilon) by construction (GO:107-120)
+    w = np.linalg.eigvalsh(g.covariances(0)[::97])
+    np.testing.assert_allclose(w, np.tile([1e-3, 1.0, 1.0], (w.shape[0], 1)), rtol=1e-9, atol=1e-12)
+    # gradient check at a non-trivial state
+    I = np.eye(4, dtype=np.float32)
+    x = np.array([0.3, -0.1, 0.05, 0.01, -0.02, 0.03])
+    r = g.functor(I, I, x)
+    np.testing.assert_allclose(r["df"], r["fdf_g"], rtol=1e-12)
+    assert r["f"] == pytest.approx(r["fdf_f"], rel=1e-5)  # operator() evaluates in f32, fdf in f64
+    for k in range(6):
+        h = 1e-3 if k < 3 else 1e-4
+        dx = np.zeros(6)
+        dx[k] = h
+        num = (g.functor(I, I, x + dx)["fdf_f"] - g.functor(I, I, x - dx)["fdf_f"]) / (2 * h)
+        assert num == pytest.approx(r["df"][k], rel=2e-2, abs=2e-3 * np.abs(r["df"]).max())
+
+
 def test_knn_against_scipy(oracle, velodyne_pair):
     from scipy.spatial import cKDTree
     pts = oracle.voxel_grid(velodyne_pair["target"], 0.3)["points"]
