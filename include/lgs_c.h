@@ -111,6 +111,35 @@ int lgs_sor_filter_dev(lgs_sor* sor, const float* pts_dev, int64_t n, float* out
                        float* out_distances_dev, lgs_sor_info* info);
 
 /* ------------------------------------------------------------------------------------------- */
+/* ingest: sensor_msgs/PointCloud2 payload -> packed xyzi device cloud                            */
+/*   replaces the host-side pcl::fromROSMsg of the nodes (PPF:65-70, LSM:122-130, GBS:287-295):   */
+/*   the message bytes are uploaded as they are and repacked on the GPU; the result feeds every   */
+/*   *_dev entry point (lgs_voxelgrid_filter_dev, lgs_*_set_source_dev / set_target_dev, ...)      */
+#define LGS_PC2_INT8 1 /* sensor_msgs/PointField datatype constants */
+#define LGS_PC2_UINT8 2
+#define LGS_PC2_INT16 3
+#define LGS_PC2_UINT16 4
+#define LGS_PC2_INT32 5
+#define LGS_PC2_UINT32 6
+#define LGS_PC2_FLOAT32 7
+#define LGS_PC2_FLOAT64 8
+
+typedef struct lgs_pc2_layout {
+  uint32_t width, height;      /* points = width * height */
+  uint32_t point_step;         /* bytes per record, 12..256, any alignment (Velodyne: 22) */
+  uint32_t row_step;           /* 0 or width * point_step */
+  int32_t offset_x, offset_y, offset_z;
+  int32_t datatype_xyz;        /* must be LGS_PC2_FLOAT32 */
+  int32_t offset_intensity;    /* -1: the message has no intensity field */
+  int32_t datatype_intensity;  /* anything but FLOAT32 is not mapped, like pcl::fromROSMsg: intensity = 0 */
+  int32_t is_bigendian;        /* must be 0 */
+  int32_t reserved;
+} lgs_pc2_layout;
+
+/* data: the message's `data` bytes (host).  out_dev: device buffer of width*height x 4 floats. */
+int lgs_cloud_from_pointcloud2(lgs_ctx* ctx, const void* data, const lgs_pc2_layout* layout, float* out_dev, int64_t* n_points);
+
+/* ------------------------------------------------------------------------------------------- */
 /* shared result of one registration (both methods)                                              */
 typedef struct lgs_align_result {
   float T[16];               /* getFinalTransformation(), column-major */

@@ -25,6 +25,12 @@ class SorInfo(C.Structure):
     _fields_ = [("n_out", C.c_int64), ("mean", C.c_double), ("stddev", C.c_double), ("threshold", C.c_double)]
 
 
+class Pc2Layout(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("point_step", C.c_uint32), ("row_step", C.c_uint32),
+                ("offset_x", C.c_int32), ("offset_y", C.c_int32), ("offset_z", C.c_int32), ("datatype_xyz", C.c_int32),
+                ("offset_intensity", C.c_int32), ("datatype_intensity", C.c_int32), ("is_bigendian", C.c_int32), ("reserved", C.c_int32)]
+
+
 class AlignResult(C.Structure):
     _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("trans_probability", C.c_double), ("iterations", C.c_int32),
                 ("converged", C.c_int32), ("evaluations", C.c_int32), ("line_search_trials", C.c_int32),
@@ -54,6 +60,7 @@ SYMBOLS = {
     "lgs_ctx_launch_count": (_i64, [_vp]),
     "lgs_voxelgrid_filter": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
     "lgs_voxelgrid_filter_dev": (_i32, [_vp, _vp, _i64, _vp, _i32, _f64, _vp, _vp, _vp, _vp, C.POINTER(VoxelGridInfo)]),
+    "lgs_cloud_from_pointcloud2": (_i32, [_vp, _vp, C.POINTER(Pc2Layout), _vp, C.POINTER(_i64)]),
     "lgs_sor_create": (_i32, [_vp, C.POINTER(_vp)]),
     "lgs_sor_destroy": (None, [_vp]),
     "lgs_sor_set_mean_k": (_i32, [_vp, _i32]),

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AlignResult, BatchParams, NdtGridInfo, SorInfo, VoxelGridInfo, check
+from ._lib import AlignResult, BatchParams, NdtGridInfo, Pc2Layout, SorInfo, VoxelGridInfo, check
 
 NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = 0, 1, 2, 3, 4
@@ -100,6 +100,39 @@ def default_context():
     if _default_ctx is None:
         _default_ctx = Context(0)
     return _default_ctx
+
+
+PC2_INT8, PC2_UINT8, PC2_INT16, PC2_UINT16, PC2_INT32, PC2_UINT32, PC2_FLOAT32, PC2_FLOAT64 = range(1, 9)
+
+
+def from_pointcloud2(data, width, height, point_step, fields, row_step=0, is_bigendian=False, ctx=None):
+    """pcl::fromROSMsg<pcl::PointXYZI> on the GPU (PPF:65-70): `data` is the message's byte payload, `fields` maps a
+    field name to (offset, datatype) as in sensor_msgs/PointField.  Returns a CUDA float32 tensor (N, 4) xyzi that the
+    device-resident entry points take (VoxelGrid / StatisticalOutlierRemoval / setInputSource / setInputTarget)."""
+    import torch
+    ctx = ctx or default_context()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).ravel()
+    n = int(width) * int(height)
+    if buf.size < n * int(point_step):
+        raise ValueError("payload shorter than width * height * point_step")
+    L = Pc2Layout()
+    L.width, L.height, L.point_step, L.row_step = int(width), int(height), int(point_step), int(row_step)
+    for name in ("x", "y", "z"):
+        if name not in fields:
+            raise ValueError("PointCloud2 has no field %r" % name)
+    L.offset_x, L.offset_y, L.offset_z = (int(fields[k][0]) for k in ("x", "y", "z"))
+    dts = {int(fields[k][1]) for k in ("x", "y", "z")}
+    L.datatype_xyz = dts.pop() if len(dts) == 1 else 0
+    L.offset_intensity, L.datatype_intensity = (int(fields["intensity"][0]), int(fields["intensity"][1])) if "intensity" in fields else (-1, 0)
+    L.is_bigendian = 1 if is_bigendian else 0
+    out = torch.empty((max(n, 1), 4), dtype=torch.float32, device="cuda:%d" % ctx.device)
+    if not ctx.shares_torch_stream(out.device):
+        torch.cuda.current_stream(out.device).synchronize()
+    cnt = C.c_int64()
+    check(ctx._L.lgs_cloud_from_pointcloud2(ctx._h, buf.ctypes.data_as(C.c_void_p), C.byref(L), C.c_void_p(out.data_ptr()), C.byref(cnt)))
+    if not ctx.shares_torch_stream(out.device):
+        ctx.synchronize()
+    return out[:n]
 
 
 class VoxelGrid:

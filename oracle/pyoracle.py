@@ -388,6 +388,21 @@ class GeneralizedIterativeClosestPoint:
         return dict(f=out[0], df=out[1:7].copy(), fdf_f=out[7], fdf_g=out[8:14].copy(), n_corr=int(out[14]), corr=corr, mahal=mahal)
 
 
+def from_pointcloud2(data, width, height, point_step, fields):
+    """ORACLE of pcl::fromROSMsg<pcl::PointXYZI> (called at PPF:65-70, LSM:122-130): numpy restatement of PCL's field
+    mapping (pcl/conversions.h createMapping / fromPCLPointCloud2: a message field is copied only when its name and
+    datatype equal the point type's, FLOAT32 = 7 for x, y, z, intensity; unmatched point fields keep their default 0).
+    `fields`: name -> (offset, datatype).  Returns (N, 4) float32 xyzi."""
+    n = int(width) * int(height)
+    raw = np.frombuffer(data, dtype=np.uint8, count=n * int(point_step)).reshape(n, int(point_step))
+    out = np.zeros((n, 4), np.float32)
+    for col, name in enumerate(("x", "y", "z", "intensity")):
+        if name in fields and int(fields[name][1]) == 7:
+            off = int(fields[name][0])
+            out[:, col] = np.ascontiguousarray(raw[:, off:off + 4]).view("<f4")[:, 0]
+    return out
+
+
 def knn(pts, queries, k, num_threads=0):
     pts, queries = _pts(pts), _pts(queries)
     m = queries.shape[0]

@@ -400,6 +400,62 @@ def test_gicp_velodyne_align_parity(api, oracle, velodyne_pair):
     _compare_gicp_align(g, o, guess)
 
 
+def _pc2_message(pts, layout, rng):
+    """Packs (N,4) xyzi into a sensor_msgs/PointCloud2-style payload: (point_step, fields) with random filler bytes."""
+    point_step, fields = layout
+    n = pts.shape[0]
+    raw = rng.integers(0, 256, size=(n, point_step), dtype=np.uint8)
+    for col, name in enumerate(("x", "y", "z", "intensity")):
+        if name not in fields:
+            continue
+        off, dt = fields[name]
+        if dt == 7:
+            raw[:, off:off + 4] = np.ascontiguousarray(pts[:, col]).view(np.uint8).reshape(n, 4)
+        elif dt == 2:
+            raw[:, off] = np.clip(pts[:, col], 0, 255).astype(np.uint8)
+    return raw.tobytes()
+
+
+@pytest.mark.parametrize("layout", [
+    (22, {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (12, 7), "ring": (16, 4), "time": (18, 7)}),    # velodyne_pointcloud PointXYZIRT
+    (48, {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (16, 7), "t": (20, 6), "reflectivity": (24, 4)}),  # ouster-ros
+    (16, {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (12, 7)}),
+    (13, {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (12, 2)}),     # UINT8 intensity: not mapped by fromROSMsg -> 0
+    (12, {"x": (0, 7), "y": (4, 7), "z": (8, 7)}),
+    (255, {"x": (101, 7), "y": (3, 7), "z": (250, 7), "intensity": (77, 7)}),
+], ids=["velodyne22", "ouster48", "packed16", "u8_intensity13", "xyz12", "odd255"])
+def test_pointcloud2_ingest_bit_exact(api, oracle, velodyne_pair, layout):
+    """sensor_msgs/PointCloud2 payload -> device xyzi (pcl::fromROSMsg, PPF:65-70): every float is copied bit for bit."""
+    rng = np.random.default_rng(5)
+    point_step, fields = layout
+    for n in (0, 1, 255, 256, 257, 69088):
+        pts = velodyne_pair["target"][:n].copy()
+        if n > 10:
+            pts[3] = [np.nan, np.inf, -0.0, 1e-42]  # payload bits travel untouched, denormals and NaN included
+        msg = _pc2_message(pts, layout, rng)
+        dev = api.from_pointcloud2(msg, n, 1, point_step, fields)
+        ref = oracle.from_pointcloud2(msg, n, 1, point_step, fields)
+        assert dev.shape == (n, 4)
+        assert np.array_equal(dev.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    # organised cloud (height > 1) and the device result feeding the prefilter: same voxels as the host path
+    pts = velodyne_pair["target"][:64 * 1024]
+    msg = _pc2_message(pts, layout, rng)
+    dev = api.from_pointcloud2(msg, 1024, 64, point_step, fields, row_step=1024 * point_step)
+    ref = oracle.from_pointcloud2(msg, 1024, 64, point_step, fields)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    vg = api.VoxelGrid()
+    vg.setLeafSize(0.2)
+    vg.setRangeCrop(1.0)
+    vg.setInputCloud(dev)
+    out = vg.filter()
+    out = out.cpu().numpy() if hasattr(out, "cpu") else out
+    r = oracle.voxel_grid(ref, 0.2, range_min=1.0)
+    assert out.shape == r["points"].shape
+    np.testing.assert_allclose(out, r["points"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        api.from_pointcloud2(msg, 1024, 64, point_step, dict(fields, x=(fields["x"][0], 8)))  # FLOAT64 x: refused, never guessed
+
+
 def _gicp_omp_pair(api, oracle, target, source, **kw):
     g, o = api.GeneralizedIterativeClosestPoint(), oracle.GeneralizedIterativeClosestPoint()
     for x in (g, o):
