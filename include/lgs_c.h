@@ -289,6 +289,27 @@ int lgs_knn(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, cons
 int lgs_sort_pairs(lgs_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int32_t bits);
 
 /* ------------------------------------------------------------------------------------------- */
+/* key-frame array + sub-map assembly, device resident                                            */
+/*   replaces the per-key-frame fromROSMsg + transform_point_cloud + `*cloud += ...` loops and the */
+/*   re-upload of the assembled map: LSM:196-212 (local map, newest first) and GBS:297-313         */
+/*   (candidate neighbourhood, ascending index, then VoxelGrid).  A key frame is uploaded once.    */
+typedef struct lgs_keyframes lgs_keyframes;
+
+int lgs_keyframes_create(lgs_ctx* ctx, lgs_keyframes** out);
+void lgs_keyframes_destroy(lgs_keyframes* kf);
+/* key_frame_array_.keyframes.emplace_back (LSM:196-197): the cloud in its own frame + its pose (column-major
+ * Matrix4f, what geometry_pose_to_matrix returns at LSM:205); id = index in the array */
+int lgs_keyframes_push(lgs_keyframes* kf, const void* pts, int64_t n, int32_t stride_bytes, const float* pose16, int32_t* id);
+int lgs_keyframes_push_dev(lgs_keyframes* kf, const float* pts_dev, int64_t n, const float* pose16, int32_t* id);
+/* a pose-graph update moved the key frame (the optimised poses the back end publishes, GBS:343-352) */
+int lgs_keyframes_set_pose(lgs_keyframes* kf, int32_t id, const float* pose16);
+int lgs_keyframes_size(lgs_keyframes* kf, int64_t* count, int64_t* total_points);
+/* sub-map = concatenation, in the order of ids[], of pcl::transformPointCloud(key frame, pose); leaf > 0 applies
+ * pcl::VoxelGrid(leaf) to the result (GBS:311-313).  *out_dev is a packed xyzi device cloud owned by kf, valid
+ * until the next assemble call; feed it to lgs_*_set_target_dev / set_source_dev. */
+int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids, float leaf, float** out_dev, int64_t* n_out);
+
+/* ------------------------------------------------------------------------------------------- */
 /* batched loop-closure verification: GBS:297-322 for a list of (scan, submap) pairs              */
 #define LGS_METHOD_NDT 0
 #define LGS_METHOD_GICP 1

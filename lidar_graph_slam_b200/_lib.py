@@ -126,6 +126,13 @@ SYMBOLS = {
     "lgs_gicp_omp_functor": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lgs_knn": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "lgs_sort_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32]),
+    "lgs_keyframes_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_keyframes_destroy": (None, [_vp]),
+    "lgs_keyframes_push": (_i32, [_vp, _vp, _i64, _i32, _vp, C.POINTER(_i32)]),
+    "lgs_keyframes_push_dev": (_i32, [_vp, _vp, _i64, _vp, C.POINTER(_i32)]),
+    "lgs_keyframes_set_pose": (_i32, [_vp, _i32, _vp]),
+    "lgs_keyframes_size": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "lgs_keyframes_assemble": (_i32, [_vp, _vp, _i32, _f32, C.POINTER(_vp), C.POINTER(_i64)]),
     "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lgs_batch_release": (None, []),
 }

@@ -44,6 +44,17 @@ def _dev_cloud(t, ctx=None):
     return C.c_void_p(t.data_ptr()), t.shape[0]
 
 
+class _CudaArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _device_view(ptr, n, device):
+    """torch view of a library-owned packed xyzi device cloud (no copy)."""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, (int(n), 4)), device="cuda:%d" % device)
+
+
 def _mat_to_c(T):
     if T is None:
         return None, None
@@ -469,6 +480,60 @@ class GeneralizedIterativeClosestPoint(_Registration):
         check(self._L.lgs_gicp_omp_functor(self._h, vp(gc), vp(tc), vp(x), vp(out), vp(corr), vp(mahal)))
         return dict(f=out[0], df=out[1:7].copy(), fdf_f=out[7], fdf_g=out[8:14].copy(), n_corr=int(out[14]), corr=corr[: self._ns],
                     mahal=mahal[: self._ns])
+
+
+class KeyFrameArray:
+    """Device-resident key_frame_array_ of the scan matcher / graph SLAM nodes (LSM:196-212, GBS:297-313): key frames are
+    uploaded once; `assemble` returns the transformed, concatenated (and optionally voxel-filtered) sub-map as a CUDA
+    tensor that setInputTarget takes without leaving the GPU."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_keyframes_create(self.ctx._h, C.byref(h)))
+        self._h = h
+
+    def push(self, cloud, pose):
+        _, pp = _mat_to_c(pose)
+        kid = C.c_int32()
+        if _is_torch(cloud):
+            p, n = _dev_cloud(cloud, self.ctx)
+            check(self._L.lgs_keyframes_push_dev(self._h, p, n, pp, C.byref(kid)))
+        else:
+            _, p, n, stride = _host_cloud(cloud)
+            check(self._L.lgs_keyframes_push(self._h, p, n, stride, pp, C.byref(kid)))
+        return kid.value
+
+    def set_pose(self, kid, pose):
+        _, pp = _mat_to_c(pose)
+        check(self._L.lgs_keyframes_set_pose(self._h, int(kid), pp))
+
+    def __len__(self):
+        c = C.c_int64()
+        check(self._L.lgs_keyframes_size(self._h, C.byref(c), None))
+        return c.value
+
+    def assemble(self, ids, leaf=0.0):
+        """Returns a CUDA float32 tensor (N, 4): a copy of the library's sub-map buffer."""
+        import torch
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out, n = C.c_void_p(), C.c_int64()
+        check(self._L.lgs_keyframes_assemble(self._h, ids.ctypes.data_as(C.c_void_p), int(ids.size), float(leaf), C.byref(out), C.byref(n)))
+        self.ctx.synchronize()
+        t = torch.empty((n.value, 4), dtype=torch.float32, device="cuda:%d" % self.ctx.device)
+        if n.value:
+            t.copy_(_device_view(out.value, n.value, self.ctx.device))
+            torch.cuda.current_stream(t.device).synchronize()
+        return t
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.lgs_keyframes_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def knn(pts, queries, k, ctx=None):

@@ -240,6 +240,13 @@ void orc_pgicp_functor(void* h, const float* guess16, const float* transformatio
   if (mahal) std::memcpy(mahal, g->mahalanobis.data(), g->mahalanobis.size() * sizeof(float));
 }
 
+// pcl::transformPointCloud(Matrix4f) (transform_point_cloud of the nodes, LSM:206, GBS:305): out may alias pts
+void orc_transform_cloud(const float* pts, long n, const float* T16, float* out) {
+  const P4* p = reinterpret_cast<const P4*>(pts);
+  P4* o = reinterpret_cast<P4*>(out);
+  for (long i = 0; i < n; i++) o[i] = transform_point(T16, p[i]);
+}
+
 // ---- exact k-NN (tree built per call) -----------------------------------------------------------
 void orc_knn(const float* pts, long n, const float* queries, long m, int k, int* idx, float* d2, int num_threads) {
   KdTree t;

@@ -82,6 +82,7 @@ def lib():
         L.orc_pgicp_fitness.argtypes = [vp, C.c_double]
         L.orc_pgicp_covariances.argtypes = [vp, C.c_int, vp]
         L.orc_pgicp_functor.argtypes = [vp] * 7
+        L.orc_transform_cloud.argtypes = [vp, C.c_long, vp, vp]
         L.orc_knn.argtypes = [vp, C.c_long, vp, C.c_long, C.c_int, vp, vp, C.c_int]
         L.orc_fitness.restype = C.c_double
         L.orc_fitness.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_double, C.c_int]
@@ -401,6 +402,25 @@ def from_pointcloud2(data, width, height, point_step, fields):
             off = int(fields[name][0])
             out[:, col] = np.ascontiguousarray(raw[:, off:off + 4]).view("<f4")[:, 0]
     return out
+
+
+def transform_point_cloud(pts, T):
+    """pcl::transformPointCloud with an Eigen::Matrix4f (lidar_graph_slam_utils transform_point_cloud, LSM:206, GBS:305)."""
+    pts = _pts(pts)
+    Tc = np.asarray(T, np.float32).reshape(4, 4).ravel(order="F").copy()
+    out = np.empty_like(pts)
+    lib().orc_transform_cloud(_p(pts), pts.shape[0], _p(Tc), _p(out))
+    return out
+
+
+def assemble_submap(clouds, poses, ids, leaf=0.0):
+    """The sub-map loops of LSM:199-208 / GBS:297-313: transform each key frame by its pose, concatenate in the order of
+    ids, optionally pcl::VoxelGrid(leaf)."""
+    parts = [transform_point_cloud(clouds[i], poses[i]) for i in ids]
+    cat = np.concatenate(parts, axis=0) if parts else np.zeros((0, 4), np.float32)
+    if leaf > 0 and cat.shape[0]:
+        return voxel_grid(cat, leaf)["points"]
+    return cat
 
 
 def knn(pts, queries, k, num_threads=0):

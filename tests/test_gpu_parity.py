@@ -456,6 +456,77 @@ def test_pointcloud2_ingest_bit_exact(api, oracle, velodyne_pair, layout):
         api.from_pointcloud2(msg, 1024, 64, point_step, dict(fields, x=(fields["x"][0], 8)))  # FLOAT64 x: refused, never guessed
 
 
+def _pose(x, y, z, yaw, pitch=0.0):
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[cy * cp, -sy, cy * sp], [sy * cp, cy, sy * sp], [-sp, 0, cp]], np.float32)
+    T[:3, 3] = [x, y, z]
+    return T
+
+
+def test_keyframe_array_submap_assembly(api, oracle, velodyne_pair):
+    """Device-resident key_frame_array_ (LSM:196-212, GBS:297-313): the assembled sub-map is bit-identical to transforming
+    and concatenating on the host, in both loop orders, across arena chunks, after pose updates, and through VoxelGrid."""
+    rng = np.random.default_rng(11)
+    base = [velodyne_pair["target"], velodyne_pair["source"]]
+    kf = api.KeyFrameArray()
+    clouds, poses = [], []
+    for i in range(70):  # 70 x ~69 k points: crosses the 4 Mi-point arena chunk
+        c = base[i % 2][: 69000 - 137 * i] if i != 5 else base[0][:0]  # key frame 5 is empty
+        P = _pose(0.9 * i, 0.05 * i * i / 70, 0.01 * i, 0.02 * i, 0.001 * i)
+        assert kf.push(c if i % 3 else np.ascontiguousarray(np.pad(c, ((0, 0), (0, 4)))[:, [0, 1, 2, 7, 3, 4, 5, 6]]), P) == i  # every third as 32-byte PointXYZI
+        clouds.append(c)
+        poses.append(P)
+    assert len(kf) == 70
+    # scan matcher order: the newest 20, newest first (LSM:199-208)
+    ids = [69 - k for k in range(20)]
+    got = kf.assemble(ids).cpu().numpy()
+    ref = oracle.assemble_submap(clouds, poses, ids)
+    assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # graph SLAM order: min_id +- 20 ascending (GBS:297-309), then VoxelGrid 0.5 (GBS:61,311-313)
+    ids = list(range(0, 41))
+    got = kf.assemble(ids, leaf=0.5).cpu().numpy()
+    ref = oracle.assemble_submap(clouds, poses, ids, leaf=0.5)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    # a pose-graph update moves key frames
+    for i in (3, 40):
+        poses[i] = _pose(*rng.normal(size=3), 0.3)
+        kf.set_pose(i, poses[i])
+    got = kf.assemble(ids).cpu().numpy()
+    ref = oracle.assemble_submap(clouds, poses, ids)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # more key frames than one launch takes (96), repeated ids, tiny frames; and the empty selections
+    small = api.KeyFrameArray()
+    sc = [base[0][1000 * i: 1000 * i + 1 + (i * 37) % 200] for i in range(30)]
+    sp = [_pose(i, -i, 0.1 * i, 0.1 * i) for i in range(30)]
+    for c, P in zip(sc, sp):
+        small.push(c, P)
+    ids = [int(v) for v in rng.integers(0, 30, size=250)]
+    got = small.assemble(ids).cpu().numpy()
+    ref = oracle.assemble_submap(sc, sp, ids)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert small.assemble([]).shape == (0, 4) and kf.assemble([5]).shape == (0, 4)
+    with pytest.raises(RuntimeError):
+        small.assemble([30])
+    # the sub-map never leaves the GPU: NDT on the device sub-map == NDT on the host-assembled one
+    ids = [69 - k for k in range(20)]
+    target_dev = kf.assemble(ids)
+    target_host = oracle.assemble_submap(clouds, poses, ids)
+    src = oracle.transform_point_cloud(clouds[69][::4], poses[69] @ _pose(0.2, -0.1, 0.0, 0.01))
+    res = []
+    for tgt in (target_dev, target_host):
+        n = api.NormalDistributionsTransform()
+        n.setResolution(1.0)
+        n.setTransformationEpsilon(0.01)
+        n.setMaximumIterations(30)
+        n.setInputTarget(tgt)
+        n.setInputSource(src)
+        n.align()
+        res.append((n.getFinalTransformation().copy(), n.result.iterations, n.getTransformationProbability()))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and res[0][2] == res[1][2]
+
+
 def _gicp_omp_pair(api, oracle, target, source, **kw):
     g, o = api.GeneralizedIterativeClosestPoint(), oracle.GeneralizedIterativeClosestPoint()
     for x in (g, o):
