@@ -5,6 +5,7 @@
 //   lgs::VoxelGrid                      <- pcl::VoxelGrid<pcl::PointXYZI>            (PPF:118-120, GBS:61,311-313,490-493)
 //   lgs::NormalDistributionsTransform   <- pclomp::NormalDistributionsTransform      (LSM:56-72, GBS:101-119)
 //   lgs::FastGICP                       <- fast_gicp::FastGICP                       (LSM:38-54, GBS:82-100)
+//   lgs::IterativeClosestPoint          <- pcl::IterativeClosestPoint                (GBS:142-151, the default method)
 //   lgs::GeneralizedIterativeClosestPoint <- pclomp::GeneralizedIterativeClosestPoint (LSM:73-96, GBS:120-141)
 //
 // Clouds are std::vector<lgs::PointXYZI> with pcl::PointXYZI's 32-byte layout; transforms are float[16]
@@ -313,6 +314,44 @@ class GeneralizedIterativeClosestPoint : public Registration {
   lgs_gicp_omp* h_ = nullptr;
   int k_ = 20, max_inner_ = 20;
   double rot_eps_ = 2e-3;
+};
+
+// pcl::IterativeClosestPoint<PointXYZI, PointXYZI>: the default loop-closure method (GBS:142-151)
+class IterativeClosestPoint : public Registration {
+ public:
+  explicit IterativeClosestPoint(std::shared_ptr<Context> ctx = defaultContext()) : ctx_(std::move(ctx)) {
+    if (lgs_icp_create(ctx_->get(), &h_) != LGS_OK) throw std::runtime_error(lgs_last_error());
+  }
+  ~IterativeClosestPoint() override { lgs_icp_destroy(h_); }
+  void setMaxCorrespondenceDistance(double d) { check(lgs_icp_set_max_correspondence_distance(h_, d)); }
+  void setMaximumIterations(int n) { check(lgs_icp_set_maximum_iterations(h_, n)); }
+  void setTransformationEpsilon(double e) { check(lgs_icp_set_transformation_epsilon(h_, e)); }
+  void setTransformationRotationEpsilon(double e) { check(lgs_icp_set_transformation_rotation_epsilon(h_, e)); }
+  void setEuclideanFitnessEpsilon(double e) { check(lgs_icp_set_euclidean_fitness_epsilon(h_, e)); }
+  void setRANSACIterations(int) {}  // GBS:149: no rejector is installed, PCL never reads it
+  void setInputTarget(const std::shared_ptr<const PointCloud>& c) override {
+    check(lgs_icp_set_target(h_, c->data(), static_cast<int64_t>(c->size()), sizeof(PointXYZI)));
+  }
+  void setInputSource(const std::shared_ptr<const PointCloud>& c) override {
+    n_source_ = c->size();
+    check(lgs_icp_set_source(h_, c->data(), static_cast<int64_t>(c->size()), sizeof(PointXYZI)));
+  }
+  void align(PointCloud& output, const Matrix4f& guess = Identity4f()) override {
+    ok_ = true;
+    std::vector<float> packed((n_source_ ? n_source_ : 1) * 4);
+    check(lgs_icp_align(h_, guess.data(), &result_, packed.data()));
+    if (ok_) fill_output(output, packed, n_source_);
+  }
+  double getFitnessScore(double max_range = DBL_MAX) override {
+    double f = DBL_MAX;
+    check(lgs_icp_fitness(h_, max_range, &f));
+    return f;
+  }
+  lgs_icp* handle() const { return h_; }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  lgs_icp* h_ = nullptr;
 };
 
 }  // namespace lgs

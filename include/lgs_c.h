@@ -279,6 +279,39 @@ int lgs_gicp_omp_export_covariances(lgs_gicp_omp* g, int32_t which, double* covs
 int lgs_gicp_omp_functor(lgs_gicp_omp* g, const float* guess16, const float* transformation16, const double* x6, double* out15,
                          int32_t* corr, float* mahal);
 
+/* ------------------------------------------------------------------------------------------- */
+/* ICP: pcl::IterativeClosestPoint<PointXYZI, PointXYZI> behind pcl::Registration                 */
+/*   the graph SLAM node's default loop-closure method (graph_based_slam.param.yaml:9), built at  */
+/*   GBS:142-151 with setMaxCorrespondenceDistance(30) / setMaximumIterations(100) /              */
+/*   setTransformationEpsilon(1e-8) / setEuclideanFitnessEpsilon(1e-6) / setRANSACIterations(0)   */
+typedef struct lgs_icp lgs_icp;
+
+#define LGS_ICP_NOT_CONVERGED 0 /* pcl::registration::DefaultConvergenceCriteria::ConvergenceState */
+#define LGS_ICP_ITERATIONS 1
+#define LGS_ICP_TRANSFORM 2
+#define LGS_ICP_ABS_MSE 3
+#define LGS_ICP_REL_MSE 4
+#define LGS_ICP_NO_CORRESPONDENCES 5
+
+int lgs_icp_create(lgs_ctx* ctx, lgs_icp** out);   /* PCL defaults: 10 iterations, epsilons 0, distance sqrt(DBL_MAX) */
+void lgs_icp_destroy(lgs_icp* icp);
+int lgs_icp_set_max_correspondence_distance(lgs_icp* icp, double d);       /* GBS:145 */
+int lgs_icp_set_maximum_iterations(lgs_icp* icp, int32_t n);               /* GBS:146 */
+int lgs_icp_set_transformation_epsilon(lgs_icp* icp, double eps);          /* GBS:147 (compared with the SQUARED translation, as in PCL) */
+int lgs_icp_set_transformation_rotation_epsilon(lgs_icp* icp, double eps); /* cos(angle) threshold; 0 = 1 - transformation_epsilon */
+int lgs_icp_set_euclidean_fitness_epsilon(lgs_icp* icp, double eps);       /* GBS:148 (relative MSE threshold) */
+int lgs_icp_set_source(lgs_icp* icp, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_icp_set_target(lgs_icp* icp, const void* pts, int64_t n, int32_t stride_bytes);
+int lgs_icp_set_source_dev(lgs_icp* icp, const float* pts_dev, int64_t n);
+int lgs_icp_set_target_dev(lgs_icp* icp, const float* pts_dev, int64_t n);
+/* result: iterations = nr_iterations_, evaluations = correspondence/estimation steps, line_search_trials = the
+ * LGS_ICP_* convergence state, trans_probability = MSE of the last correspondence set */
+int lgs_icp_align(lgs_icp* icp, const float* guess16, lgs_align_result* result, float* out_cloud);
+int lgs_icp_fitness(lgs_icp* icp, double max_range, double* fitness);
+/* parity hook: one step on guess * source: sums17 = {n, sum d2, sum p[3], sum q[3], sum q p^T[9]}, T16 = the estimated
+ * transformation_ (pcl::umeyama), *ok = 0 when fewer than 3 correspondences were found */
+int lgs_icp_step(lgs_icp* icp, const float* guess16, double* sums17, float* T16, int32_t* ok);
+
 /* exact k-NN of `queries` in `pts` (the search behind FG:133 and FG:254); idx/d2 are m x k, ascending */
 int lgs_knn(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const void* queries, int64_t m, int32_t qstride_bytes,
             int32_t k, int32_t* idx, float* d2);

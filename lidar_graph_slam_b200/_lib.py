@@ -124,6 +124,20 @@ SYMBOLS = {
     "lgs_gicp_omp_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
     "lgs_gicp_omp_export_covariances": (_i32, [_vp, _i32, _vp]),
     "lgs_gicp_omp_functor": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lgs_icp_create": (_i32, [_vp, C.POINTER(_vp)]),
+    "lgs_icp_destroy": (None, [_vp]),
+    "lgs_icp_set_max_correspondence_distance": (_i32, [_vp, _f64]),
+    "lgs_icp_set_maximum_iterations": (_i32, [_vp, _i32]),
+    "lgs_icp_set_transformation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_icp_set_transformation_rotation_epsilon": (_i32, [_vp, _f64]),
+    "lgs_icp_set_euclidean_fitness_epsilon": (_i32, [_vp, _f64]),
+    "lgs_icp_set_source": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_icp_set_target": (_i32, [_vp, _vp, _i64, _i32]),
+    "lgs_icp_set_source_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_icp_set_target_dev": (_i32, [_vp, _vp, _i64]),
+    "lgs_icp_align": (_i32, [_vp, _vp, C.POINTER(AlignResult), _vp]),
+    "lgs_icp_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
+    "lgs_icp_step": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_i32)]),
     "lgs_knn": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "lgs_sort_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32]),
     "lgs_keyframes_create": (_i32, [_vp, C.POINTER(_vp)]),

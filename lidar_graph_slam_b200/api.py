@@ -536,6 +536,34 @@ class KeyFrameArray:
             pass
 
 
+class IterativeClosestPoint(_Registration):
+    """pcl::IterativeClosestPoint<PointXYZI, PointXYZI>, the graph SLAM node's default loop-closure method (GBS:142-151)."""
+
+    _prefix = "icp"
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._L = self.ctx._L
+        h = C.c_void_p()
+        check(self._L.lgs_icp_create(self.ctx._h, C.byref(h)))
+        self._h = h
+        self._ns = self._nt = 0
+
+    def setMaxCorrespondenceDistance(self, d): check(self._L.lgs_icp_set_max_correspondence_distance(self._h, float(d)))
+    def setMaximumIterations(self, n): check(self._L.lgs_icp_set_maximum_iterations(self._h, int(n)))
+    def setTransformationEpsilon(self, e): check(self._L.lgs_icp_set_transformation_epsilon(self._h, float(e)))
+    def setTransformationRotationEpsilon(self, e): check(self._L.lgs_icp_set_transformation_rotation_epsilon(self._h, float(e)))
+    def setEuclideanFitnessEpsilon(self, e): check(self._L.lgs_icp_set_euclidean_fitness_epsilon(self._h, float(e)))
+    def setRANSACIterations(self, n): pass  # GBS:149; PCL's ICP installs no rejector by default, the value is never read
+
+    def step(self, guess):
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        gc = np.asarray(guess, np.float32).reshape(4, 4).ravel(order="F").copy()
+        sums, T, ok = np.zeros(17), np.zeros(16, np.float32), C.c_int32()
+        check(self._L.lgs_icp_step(self._h, vp(gc), vp(sums), vp(T), C.byref(ok)))
+        return bool(ok.value), sums, T.reshape(4, 4, order="F").copy()
+
+
 def knn(pts, queries, k, ctx=None):
     """Exact k-NN of `queries` in `pts` (the search behind FG:133 / FG:254).  Returns (idx (m,k) int32, d2 (m,k) f32)."""
     ctx = ctx or default_context()

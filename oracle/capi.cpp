@@ -247,6 +247,45 @@ void orc_transform_cloud(const float* pts, long n, const float* T16, float* out)
   for (long i = 0; i < n; i++) o[i] = transform_point(T16, p[i]);
 }
 
+// ---- pcl::IterativeClosestPoint -------------------------------------------------------------------
+void* orc_icp_create() { return new PclICP; }
+void orc_icp_destroy(void* h) { delete static_cast<PclICP*>(h); }
+void orc_icp_set_params(void* h, double max_corr_dist, int max_iter, double trans_eps, double rot_eps, double fitness_eps, int num_threads) {
+  PclICP* g = static_cast<PclICP*>(h);
+  g->corr_dist_threshold = max_corr_dist;
+  g->max_iterations = max_iter;
+  g->transformation_epsilon = trans_eps;
+  g->transformation_rotation_epsilon = rot_eps;
+  g->euclidean_fitness_epsilon = fitness_eps;
+  if (num_threads > 0) g->num_threads = num_threads;
+}
+void orc_icp_set_source(void* h, const float* pts, long n) { static_cast<PclICP*>(h)->setInputSource(reinterpret_cast<const P4*>(pts), n); }
+void orc_icp_set_target(void* h, const float* pts, long n) { static_cast<PclICP*>(h)->setInputTarget(reinterpret_cast<const P4*>(pts), n); }
+// stats: {convergence state, correspondences of the last iteration}; mse: MSE of the last iteration
+void orc_icp_align(void* h, const float* guess16, float* T16, int* iters, int* converged, float* out_cloud, long* stats2, double* mse) {
+  PclICP* g = static_cast<PclICP*>(h);
+  std::vector<P4> out;
+  g->align(guess16, out_cloud ? &out : nullptr);
+  std::memcpy(T16, g->final_transformation, 16 * sizeof(float));
+  *iters = g->nr_iterations;
+  *converged = g->converged ? 1 : 0;
+  if (out_cloud) std::memcpy(out_cloud, out.data(), out.size() * sizeof(P4));
+  if (stats2) {
+    stats2[0] = g->convergence_state;
+    stats2[1] = g->last_correspondences;
+  }
+  if (mse) *mse = g->last_mse;
+}
+double orc_icp_fitness(void* h, double max_range) { return static_cast<PclICP*>(h)->getFitnessScore(max_range); }
+// one correspondence + umeyama step on guess * source: the 17 sums and the estimated transformation; returns 0 when
+// there are fewer than min_number_correspondences
+int orc_icp_step(void* h, const float* guess16, double* sums17, float* T16) {
+  PclICP* g = static_cast<PclICP*>(h);
+  std::vector<P4> cloud(g->source.size());
+  for (size_t i = 0; i < cloud.size(); i++) cloud[i] = transform_point(guess16, g->source[i]);
+  return g->estimate_step(cloud, sums17, T16) ? 1 : 0;
+}
+
 // ---- exact k-NN (tree built per call) -----------------------------------------------------------
 void orc_knn(const float* pts, long n, const float* queries, long m, int k, int* idx, float* d2, int num_threads) {
   KdTree t;

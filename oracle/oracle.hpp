@@ -276,4 +276,43 @@ struct PclGICP {
   bool estimateRigidTransformationBFGS(float* transformation_colmajor);
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// pcl::IterativeClosestPoint<PointXYZI, PointXYZI> as GBS:142-151 configures it (the DEFAULT loop-closure method,
+// graph_based_slam.param.yaml:9): un-vendored PCL 1.12 (registration/impl/icp.hpp, correspondence_estimation.hpp,
+// transformation_estimation_svd.hpp -> pcl::umeyama, default_convergence_criteria.hpp), restated from the published
+// sources.  PARITY UNPINNED, and one deliberate deviation: Eigen's f32 column sums and its 3 x n GEMM inside umeyama
+// have no specified summation order, so the means and the cross-covariance are accumulated in f64 here and
+// rounded to f32 where Eigen holds f32 values; everything after them (JacobiSVD, R, t) is f32 as in PCL.
+enum { ICP_NOT_CONVERGED = 0, ICP_ITERATIONS = 1, ICP_TRANSFORM = 2, ICP_ABS_MSE = 3, ICP_REL_MSE = 4, ICP_NO_CORRESPONDENCES = 5 };
+
+struct PclICP {
+  // pcl::Registration / IterativeClosestPoint defaults (registration.h, icp.h)
+  int max_iterations = 10;
+  double transformation_epsilon = 0.0;
+  double transformation_rotation_epsilon = 0.0;
+  double euclidean_fitness_epsilon = -1.7976931348623157e308;
+  double corr_dist_threshold = 1.3407807929942596e154;   // sqrt(DBL_MAX)
+  int min_number_correspondences = 3;
+  int num_threads = 1;
+
+  std::vector<P4> source, target;
+  KdTree target_tree;
+  float final_transformation[16], transformation[16], previous_transformation[16];
+  int nr_iterations = 0;
+  bool converged = false;
+  int convergence_state = ICP_NOT_CONVERGED;
+  double last_mse = 0;
+  long last_correspondences = 0;
+
+  PclICP();
+  void setInputSource(const P4* p, size_t n);
+  void setInputTarget(const P4* p, size_t n);
+  void align(const float* guess_colmajor, std::vector<P4>* out);
+  double getFitnessScore(double max_range);
+  // one correspondence + estimation step on `cloud` (the current input_transformed): the 17 sums
+  // {count, sum d2, sum p[3], sum q[3], sum q p^T[9]} and the estimated transformation_ (column-major)
+  bool estimate_step(const std::vector<P4>& cloud, double sums[17], float* T_colmajor) const;
+};
+
 }  // namespace lgs_oracle

@@ -82,6 +82,15 @@ def lib():
         L.orc_pgicp_fitness.argtypes = [vp, C.c_double]
         L.orc_pgicp_covariances.argtypes = [vp, C.c_int, vp]
         L.orc_pgicp_functor.argtypes = [vp] * 7
+        L.orc_icp_create.restype = vp
+        L.orc_icp_destroy.argtypes = [vp]
+        L.orc_icp_set_params.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_icp_set_source.argtypes = [vp, vp, C.c_long]
+        L.orc_icp_set_target.argtypes = [vp, vp, C.c_long]
+        L.orc_icp_align.argtypes = [vp] * 8
+        L.orc_icp_fitness.restype = C.c_double
+        L.orc_icp_fitness.argtypes = [vp, C.c_double]
+        L.orc_icp_step.argtypes = [vp] * 4
         L.orc_transform_cloud.argtypes = [vp, C.c_long, vp, vp]
         L.orc_knn.argtypes = [vp, C.c_long, vp, C.c_long, C.c_int, vp, vp, C.c_int]
         L.orc_fitness.restype = C.c_double
@@ -387,6 +396,67 @@ class GeneralizedIterativeClosestPoint:
         mahal = np.empty((self._ns, 9), np.float32)
         self._L.orc_pgicp_functor(self._h, _p(gc), _p(tc), _p(x), _p(out), _p(corr), _p(mahal))
         return dict(f=out[0], df=out[1:7].copy(), fdf_f=out[7], fdf_g=out[8:14].copy(), n_corr=int(out[14]), corr=corr, mahal=mahal)
+
+
+class IterativeClosestPoint:
+    """Oracle of pcl::IterativeClosestPoint<PointXYZI, PointXYZI> (PCL defaults; GBS:142-151 sets 30 / 100 / 1e-8 / 1e-6)."""
+
+    def __init__(self):
+        self._L = lib()
+        self._h = self._L.orc_icp_create()
+        self.params = dict(max_corr_dist=float(np.sqrt(np.finfo(np.float64).max)), max_iter=10, trans_eps=0.0, rot_eps=0.0,
+                           fitness_eps=-float(np.finfo(np.float64).max), num_threads=0)
+        self._ns = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_icp_destroy(self._h)
+            self._h = None
+
+    def _push(self):
+        p = self.params
+        self._L.orc_icp_set_params(self._h, p["max_corr_dist"], p["max_iter"], p["trans_eps"], p["rot_eps"], p["fitness_eps"], p["num_threads"])
+
+    def setMaxCorrespondenceDistance(self, d): self.params["max_corr_dist"] = float(d); self._push()
+    def setMaximumIterations(self, n): self.params["max_iter"] = int(n); self._push()
+    def setTransformationEpsilon(self, e): self.params["trans_eps"] = float(e); self._push()
+    def setTransformationRotationEpsilon(self, e): self.params["rot_eps"] = float(e); self._push()
+    def setEuclideanFitnessEpsilon(self, e): self.params["fitness_eps"] = float(e); self._push()
+    def setRANSACIterations(self, n): pass  # no rejector is installed by default: never read
+    def setNumThreads(self, n): self.params["num_threads"] = int(n); self._push()
+
+    def setInputSource(self, pts):
+        pts = _pts(pts)
+        self._ns = pts.shape[0]
+        self._L.orc_icp_set_source(self._h, _p(pts), pts.shape[0])
+
+    def setInputTarget(self, pts):
+        pts = _pts(pts)
+        self._L.orc_icp_set_target(self._h, _p(pts), pts.shape[0])
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.asarray(guess, dtype=np.float32)
+        gc = g.ravel(order="F").copy()
+        T = np.empty(16, np.float32)
+        it, cv = C.c_int(), C.c_int()
+        out = np.empty((self._ns, 4), np.float32)
+        st = np.zeros(2, np.int64)
+        mse = C.c_double()
+        self._L.orc_icp_align(self._h, _p(gc), _p(T), C.addressof(it), C.addressof(cv), _p(out), _p(st), C.addressof(mse))
+        self.final_transformation = T.reshape(4, 4, order="F").copy()
+        self.nr_iterations, self.converged = it.value, bool(cv.value)
+        self.stats = dict(convergence_state=int(st[0]), correspondences=int(st[1]), mse=mse.value)
+        return out
+
+    def hasConverged(self): return self.converged
+    def getFinalTransformation(self): return self.final_transformation
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max): return self._L.orc_icp_fitness(self._h, float(max_range))
+
+    def step(self, guess):
+        gc = np.asarray(guess, np.float32).ravel(order="F").copy()
+        sums, T = np.zeros(17), np.zeros(16, np.float32)
+        ok = self._L.orc_icp_step(self._h, _p(gc), _p(sums), _p(T))
+        return bool(ok), sums, T.reshape(4, 4, order="F").copy()
 
 
 def from_pointcloud2(data, width, height, point_step, fields):

@@ -78,6 +78,18 @@ def main():
     te, re = pose_error(rel, go.final_transformation)
     g["gicp_omp_gtest_recipe"] = dict(iterations=go.nr_iterations, converged=bool(go.converged), stats=go.stats, t_err=te, r_err_deg=re,
                                       fitness=go.getFitnessScore(), T=[float(x) for x in go.final_transformation.ravel()])
+    ic = O.IterativeClosestPoint()
+    ic.setNumThreads(1)
+    ic.setMaxCorrespondenceDistance(30)
+    ic.setMaximumIterations(100)
+    ic.setTransformationEpsilon(1e-8)
+    ic.setEuclideanFitnessEpsilon(1e-6)
+    ic.setInputTarget(t2)
+    ic.setInputSource(s2)
+    ic.align()
+    te, re = pose_error(rel, ic.final_transformation)
+    g["icp_gbs_config"] = dict(iterations=ic.nr_iterations, converged=bool(ic.converged), state=ic.stats["convergence_state"], t_err=te, r_err_deg=re,
+                               mse=ic.stats["mse"], fitness=ic.getFitnessScore(), T=[float(x) for x in ic.final_transformation.ravel()])
     with open(os.path.join(HERE, "oracle_golden.json"), "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(json.dumps(g, indent=1, sort_keys=True)[:1500])

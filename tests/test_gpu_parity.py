@@ -612,6 +612,68 @@ def test_gicp_omp_velodyne_align_parity(api, oracle, velodyne_pair):
         g.align()
 
 
+def _icp_pair(api, oracle, target, source, gbs=True, **kw):
+    g, o = api.IterativeClosestPoint(), oracle.IterativeClosestPoint()
+    for x in (g, o):
+        if gbs:  # GBS:145-149
+            x.setMaxCorrespondenceDistance(30)
+            x.setMaximumIterations(100)
+            x.setTransformationEpsilon(1e-8)
+            x.setEuclideanFitnessEpsilon(1e-6)
+            x.setRANSACIterations(0)
+        if "max_corr" in kw:
+            x.setMaxCorrespondenceDistance(kw["max_corr"])
+        if "max_iter" in kw:
+            x.setMaximumIterations(kw["max_iter"])
+        x.setInputTarget(target)
+        x.setInputSource(source)
+    return g, o
+
+
+def _compare_icp_align(g, o, guess=None):
+    og = o.align(guess)
+    gg = g.align(guess, want_output=True)
+    assert g.result.iterations == o.nr_iterations
+    assert bool(g.result.converged) == o.converged
+    assert g.result.line_search_trials == o.stats["convergence_state"]
+    if o.nr_iterations:
+        assert g.result.trans_probability == pytest.approx(o.stats["mse"], rel=1e-6)
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD
+    assert g.getFitnessScore() == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+    np.testing.assert_allclose(gg, og, atol=2e-4)
+
+
+def test_icp_step_and_align_parity(api, oracle, velodyne_pair):
+    """pcl::IterativeClosestPoint (the default loop-closure method, GBS:142-151): correspondence sums and the Umeyama step,
+    then whole aligns with identical iteration counts and convergence states."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _icp_pair(api, oracle, t2, s2)
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.2, -0.1, 0.05]
+    for G in (np.eye(4, dtype=np.float32), guess):
+        okg, sg, Tg = g.step(G)
+        oko, so, To = o.step(G)
+        assert okg and oko and sg[0] == so[0]
+        np.testing.assert_allclose(sg, so, rtol=1e-12)       # f64 sums of identical terms: only the order differs
+        assert np.array_equal(Tg, To)                         # rounded to f32 before the SVD: bit-identical
+    _compare_icp_align(g, o)
+    assert g.hasConverged() and g.result.line_search_trials == 2  # CONVERGENCE_CRITERIA_TRANSFORM
+    _compare_icp_align(g, o, guess)
+    # gated correspondences (FAST_GICP-like 2 m), full-resolution clouds, iteration cap of the PCL defaults
+    g, o = _icp_pair(api, oracle, velodyne_pair["target"], velodyne_pair["source"], max_corr=2.0)
+    _compare_icp_align(g, o)
+    g, o = _icp_pair(api, oracle, t2, s2, gbs=False)
+    _compare_icp_align(g, o)
+    assert g.result.iterations == 10 and g.result.line_search_trials == 1
+    # nothing within reach: not converged, final transformation = guess
+    far = s2 + np.array([500, 0, 0, 0], np.float32)
+    g, o = _icp_pair(api, oracle, t2, far, max_corr=0.5)
+    _compare_icp_align(g, o, guess)
+    assert not g.hasConverged() and g.result.line_search_trials == 5 and np.array_equal(g.getFinalTransformation(), guess)
+
+
 def test_gicp_cfg2_synthetic_odometry(api, oracle):
     """BASELINE configs[2] in miniature: scan-to-scan GICP over consecutive synthetic 64-beam sweeps, VoxelGrid 0.25 m
     (kitti.cpp:80-82), covariance reuse through swapSourceAndTarget (kitti.cpp:115-125)."""

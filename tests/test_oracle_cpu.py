@@ -235,6 +235,60 @@ def test_gicp_omp_oracle_gtest_band_and_gradient(oracle, velodyne_pair, golden):
         assert num == pytest.approx(r["df"][k], rel=2e-2, abs=2e-3 * np.abs(r["df"]).max())
 
 
+def _kabsch(P, Q):
+    """Least-squares rigid transform Q ~ R P + t (Umeyama without scaling), numpy f64."""
+    pm, qm = P.mean(0), Q.mean(0)
+    H = (Q - qm).T @ (P - pm) / len(P)
+    U, _, Vt = np.linalg.svd(H)
+    S = np.diag([1, 1, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+    R = U @ S @ Vt
+    return R, qm - R @ pm
+
+
+def test_icp_oracle_umeyama_and_convergence(oracle, velodyne_pair, golden):
+    """pcl::IterativeClosestPoint restatement: one correspondence + pcl::umeyama step equals numpy's Kabsch solution on
+    the same exact-1-NN pairs; the GBS:142-151 configuration converges on the bundled pair through the transformation
+    criterion; the degenerate exits of DefaultConvergenceCriteria are reachable."""
+    from scipy.spatial import cKDTree
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g = oracle.IterativeClosestPoint()
+    g.setMaxCorrespondenceDistance(30)
+    g.setMaximumIterations(100)
+    g.setTransformationEpsilon(1e-8)
+    g.setEuclideanFitnessEpsilon(1e-6)
+    g.setInputTarget(t2)
+    g.setInputSource(s2)
+    ok, sums, T = g.step(np.eye(4, dtype=np.float32))
+    d, idx = cKDTree(t2[:, :3].astype(np.float64)).query(s2[:, :3].astype(np.float64))
+    assert ok and sums[0] == len(s2)
+    assert sums[1] == pytest.approx((d ** 2).sum(), rel=1e-5)
+    R, t = _kabsch(s2[:, :3].astype(np.float64), t2[idx, :3].astype(np.float64))
+    np.testing.assert_allclose(T[:3, :3], R, atol=2e-6)
+    np.testing.assert_allclose(T[:3, 3], t, atol=2e-5)
+    g.align()
+    gold = golden["icp_gbs_config"]
+    assert g.converged and g.nr_iterations == gold["iterations"] and g.stats["convergence_state"] == gold["state"] == 2
+    np.testing.assert_allclose(g.final_transformation.ravel(), gold["T"], atol=1e-6)
+    t_err, r_err = pose_error(velodyne_pair["relative"], g.final_transformation)
+    assert t_err < 0.1 and np.degrees(r_err) < 1.5  # point-to-point ICP: looser than the GICP gtest band
+    assert g.getFitnessScore() == pytest.approx(g.stats["mse"], rel=1e-4)
+    # iteration cap (PCL default 10 iterations, epsilons 0) -> CONVERGENCE_CRITERIA_ITERATIONS, reported as converged
+    d10 = oracle.IterativeClosestPoint()
+    d10.setInputTarget(t2)
+    d10.setInputSource(s2)
+    d10.align()
+    assert d10.nr_iterations == 10 and d10.converged and d10.stats["convergence_state"] == 1
+    # nothing within reach -> CONVERGENCE_CRITERIA_NO_CORRESPONDENCES, not converged, final transformation = guess
+    far = oracle.IterativeClosestPoint()
+    far.setMaxCorrespondenceDistance(0.5)
+    far.setInputTarget(t2)
+    far.setInputSource(s2 + np.array([500, 0, 0, 0], np.float32))
+    far.align()
+    assert not far.converged and far.nr_iterations == 0 and far.stats["convergence_state"] == 5
+    assert np.array_equal(far.final_transformation, np.eye(4, dtype=np.float32))
+
+
 def test_knn_against_scipy(oracle, velodyne_pair):
     from scipy.spatial import cKDTree
     pts = oracle.voxel_grid(velodyne_pair["target"], 0.3)["points"]
