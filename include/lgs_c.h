@@ -344,8 +344,10 @@ int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids,
 
 /* ------------------------------------------------------------------------------------------- */
 /* batched loop-closure verification: GBS:297-322 for a list of (scan, submap) pairs              */
-#define LGS_METHOD_NDT 0
-#define LGS_METHOD_GICP 1
+#define LGS_METHOD_NDT 0      /* pclomp::NormalDistributionsTransform (GBS:101-119) */
+#define LGS_METHOD_GICP 1     /* fast_gicp::FastGICP (GBS:82-100) */
+#define LGS_METHOD_ICP 2      /* pcl::IterativeClosestPoint, the YAML default (GBS:142-151) */
+#define LGS_METHOD_GICP_OMP 3 /* pclomp::GeneralizedIterativeClosestPoint (GBS:120-141) */
 
 typedef struct lgs_batch_params {
   int32_t method;                 /* LGS_METHOD_* */
@@ -358,7 +360,8 @@ typedef struct lgs_batch_params {
   float submap_leaf;              /* VoxelGrid leaf applied to each submap before setInputTarget (GBS:61: 0.5); <= 0 disables */
   double fitness_max_range;       /* getFitnessScore(max_range); <= 0 means DBL_MAX (GBS:321) */
   int32_t n_workers;              /* concurrent pairs per GPU (each on its own stream); <= 0 picks a default */
-  int32_t reserved;
+  int32_t max_optimizer_iterations; /* GICP_OMP: BFGS inner iterations (GBS:136); <= 0 keeps 20 */
+  double euclidean_fitness_epsilon; /* ICP (GBS:148); 0 keeps PCL's default (-DBL_MAX) */
 } lgs_batch_params;
 
 /* Each pair i: scan = scans[i] (n_scan[i] points), submap = submaps[i] (n_submap[i] points), all with the

@@ -46,7 +46,7 @@ class BatchParams(C.Structure):
     _fields_ = [("method", C.c_int32), ("max_iterations", C.c_int32), ("transformation_epsilon", C.c_double),
                 ("max_correspondence_distance", C.c_double), ("k_correspondences", C.c_int32), ("ndt_resolution", C.c_float),
                 ("ndt_step_size", C.c_double), ("submap_leaf", C.c_float), ("fitness_max_range", C.c_double),
-                ("n_workers", C.c_int32), ("reserved", C.c_int32)]
+                ("n_workers", C.c_int32), ("max_optimizer_iterations", C.c_int32), ("euclidean_fitness_epsilon", C.c_double)]
 
 
 # every symbol include/lgs_c.h declares: name -> (restype, argtypes)

@@ -17,7 +17,7 @@ from ._lib import AlignResult, BatchParams, NdtGridInfo, Pc2Layout, SorInfo, Vox
 
 NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = 0, 1, 2, 3, 4
-METHOD_NDT, METHOD_GICP = 0, 1
+METHOD_NDT, METHOD_GICP, METHOD_ICP, METHOD_GICP_OMP = 0, 1, 2, 3
 VG_OK, VG_REFUSED_OVERFLOW = 0, 1
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -588,7 +588,7 @@ def sort_pairs(keys, vals, bits=32, ctx=None):
 
 def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stream=None, pair_id0=0, records_dev=None, max_iterations=100,
                 transformation_epsilon=0.01, max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0, ndt_step_size=0.1,
-                submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0):
+                submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0, max_optimizer_iterations=0, euclidean_fitness_epsilon=0.0):
     """Batched loop-closure verification (GBS:297-322 for a list of pairs).  scans / submaps: lists of (N,4) float32
     numpy arrays.  Returns a numpy structured view of lgs_align_result records."""
     L = _lib.load()
@@ -606,7 +606,8 @@ def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stre
     bp = BatchParams(method=method, max_iterations=max_iterations, transformation_epsilon=transformation_epsilon,
                      max_correspondence_distance=max_correspondence_distance, k_correspondences=k_correspondences,
                      ndt_resolution=ndt_resolution, ndt_step_size=ndt_step_size, submap_leaf=submap_leaf,
-                     fitness_max_range=fitness_max_range, n_workers=n_workers, reserved=0)
+                     fitness_max_range=fitness_max_range, n_workers=n_workers, max_optimizer_iterations=max_optimizer_iterations,
+                     euclidean_fitness_epsilon=euclidean_fitness_epsilon)
     recs = (AlignResult * max(n, 1))()
     check(L.lgs_batch_align(int(device), C.c_void_p(stream) if stream else None, C.byref(bp), n, sp, ns, mp, nm, 16,
                             g.ctypes.data_as(C.c_void_p) if g is not None else None, int(pair_id0), recs,

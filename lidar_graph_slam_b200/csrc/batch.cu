@@ -57,7 +57,7 @@ struct StageClock {
   }
 };
 
-int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, DevBuf* sub_raw, DevBuf* sub_ds, BatchShared* S, int64_t i) {
+int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_omp* gomp, DevBuf* sub_raw, DevBuf* sub_ds, BatchShared* S, int64_t i) {
   const lgs_batch_params& bp = *S->bp;
   lgs_align_result& rec = S->records[i];
   memset(&rec, 0, sizeof(rec));
@@ -87,6 +87,24 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, DevBuf* sub_raw, DevBuf
     clk.lap(4);
     LGS_TRY(lgs_gicp_fitness(gicp, max_range, &rec.fitness));
     clk.lap(5);
+  } else if (bp.method == LGS_METHOD_ICP) {
+    LGS_TRY(lgs_icp_set_target_dev(icp, tgt_dev, n_tgt));
+    clk.lap(2);
+    LGS_TRY(lgs_icp_set_source(icp, S->scans[i], S->n_scan[i], S->stride));
+    clk.lap(3);
+    LGS_TRY(lgs_icp_align(icp, guess, &rec, nullptr));
+    clk.lap(4);
+    LGS_TRY(lgs_icp_fitness(icp, max_range, &rec.fitness));
+    clk.lap(5);
+  } else if (bp.method == LGS_METHOD_GICP_OMP) {
+    LGS_TRY(lgs_gicp_omp_set_target_dev(gomp, tgt_dev, n_tgt));
+    clk.lap(2);
+    LGS_TRY(lgs_gicp_omp_set_source(gomp, S->scans[i], S->n_scan[i], S->stride));
+    clk.lap(3);
+    LGS_TRY(lgs_gicp_omp_align(gomp, guess, &rec, nullptr));
+    clk.lap(4);
+    LGS_TRY(lgs_gicp_omp_fitness(gomp, max_range, &rec.fitness));
+    clk.lap(5);
   } else {
     LGS_TRY(lgs_ndt_set_target_dev(ndt, tgt_dev, n_tgt));
     clk.lap(2);
@@ -112,6 +130,8 @@ struct WorkerSlot {
   lgs_ctx* ctx = nullptr;
   lgs_gicp* gicp = nullptr;
   lgs_ndt* ndt = nullptr;
+  lgs_icp* icp = nullptr;
+  lgs_gicp_omp* gomp = nullptr;
   DevBuf sub_raw, sub_ds;
   void destroy() {
     if (ctx) {
@@ -122,10 +142,14 @@ struct WorkerSlot {
     sub_ds.release();
     if (gicp) lgs_gicp_destroy(gicp);
     if (ndt) lgs_ndt_destroy(ndt);
+    if (icp) lgs_icp_destroy(icp);
+    if (gomp) lgs_gicp_omp_destroy(gomp);
     if (ctx) lgs_ctx_destroy(ctx);
     ctx = nullptr;
     gicp = nullptr;
     ndt = nullptr;
+    icp = nullptr;
+    gomp = nullptr;
   }
 };
 
@@ -167,6 +191,24 @@ void worker(BatchShared* S) {
         lgs_gicp_set_max_correspondence_distance(w->gicp, bp.max_correspondence_distance > 0 ? bp.max_correspondence_distance
                                                                                               : static_cast<double>(std::numeric_limits<float>::max()));
       }
+    } else if (bp.method == LGS_METHOD_ICP) {
+      if (!w->icp) rc = lgs_icp_create(w->ctx, &w->icp);
+      if (rc == LGS_OK) {  // PCL defaults, then the batch's settings (GBS:145-148)
+        lgs_icp_set_maximum_iterations(w->icp, bp.max_iterations > 0 ? bp.max_iterations : 10);
+        lgs_icp_set_transformation_epsilon(w->icp, bp.transformation_epsilon > 0 ? bp.transformation_epsilon : 0.0);
+        lgs_icp_set_max_correspondence_distance(w->icp, bp.max_correspondence_distance > 0 ? bp.max_correspondence_distance : 1.3407807929942596e154);
+        lgs_icp_set_euclidean_fitness_epsilon(w->icp, bp.euclidean_fitness_epsilon != 0 ? bp.euclidean_fitness_epsilon : -std::numeric_limits<double>::max());
+        lgs_icp_set_transformation_rotation_epsilon(w->icp, 0.0);
+      }
+    } else if (bp.method == LGS_METHOD_GICP_OMP) {
+      if (!w->gomp) rc = lgs_gicp_omp_create(w->ctx, &w->gomp);
+      if (rc == LGS_OK) {  // gicp_omp.h:116-126 defaults, then the batch's settings (GBS:134-137)
+        lgs_gicp_omp_set_correspondence_randomness(w->gomp, bp.k_correspondences > 0 ? bp.k_correspondences : 20);
+        lgs_gicp_omp_set_maximum_iterations(w->gomp, bp.max_iterations > 0 ? bp.max_iterations : 200);
+        lgs_gicp_omp_set_transformation_epsilon(w->gomp, bp.transformation_epsilon > 0 ? bp.transformation_epsilon : 5e-4);
+        lgs_gicp_omp_set_max_correspondence_distance(w->gomp, bp.max_correspondence_distance > 0 ? bp.max_correspondence_distance : 5.0);
+        lgs_gicp_omp_set_maximum_optimizer_iterations(w->gomp, bp.max_optimizer_iterations > 0 ? bp.max_optimizer_iterations : 20);
+      }
     } else {
       if (!w->ndt) rc = lgs_ndt_create(w->ctx, &w->ndt);
       if (rc == LGS_OK) {
@@ -180,7 +222,7 @@ void worker(BatchShared* S) {
   while (rc == LGS_OK && !S->failed.load()) {
     const int64_t i = S->next.fetch_add(1);
     if (i >= S->n_pairs) break;
-    rc = run_pair(w->ctx, w->gicp, w->ndt, &w->sub_raw, &w->sub_ds, S, i);
+    rc = run_pair(w->ctx, w->gicp, w->ndt, w->icp, w->gomp, &w->sub_raw, &w->sub_ds, S, i);
   }
   if (rc != LGS_OK) {
     std::lock_guard<std::mutex> lk(S->err_mu);
@@ -205,7 +247,7 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
                                const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev) {
   LGS_REQUIRE(params && records, "null argument");
   LGS_REQUIRE(n_pairs >= 0, "negative pair count");
-  LGS_REQUIRE(params->method == LGS_METHOD_GICP || params->method == LGS_METHOD_NDT, "unknown method");
+  LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
   LGS_REQUIRE(n_pairs == 0 || (scans && n_scan && submaps && n_submap), "null pair arrays");
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {

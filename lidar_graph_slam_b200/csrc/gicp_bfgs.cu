@@ -9,8 +9,10 @@
 //                      (GO:458-474) are the ascending valid entries of corr[]: nothing is compacted, every functor
 //                      kernel walks corr[] and skips the holes.
 //   functor kernels -> OptimizationFunctorWithIndices::operator() / df / fdf (GO:245-367): streaming passes over
-//                      (output[i], target[corr[i]], M_i) with 1 / 12 / 13 f64 sums, block reduction, fixed-order
-//                      last-block pass, result published to the host mailbox (no D2H copy, no stream synchronisation).
+//                      (output[i], target[corr[i]], M_i) with 1 / 12 / 13 sums.  The sums are EXACT (128-bit fixed point,
+//                      fixsum.cuh), hence independent of the reduction order: the line search compares costs that differ
+//                      by less than the rounding noise of an f64 sum, and only exact sums make its path reproducible.
+//                      Result published to the host mailbox (no D2H copy, no stream synchronisation).
 //   BFGS + outer loop-> host (GO:180-242, 370-516; pcl/registration/bfgs.h restated: Fletcher line search of GSL's
 //                      vector_bfgs2).  About 40 functor evaluations per outer iteration, each one kernel + one mailbox
 //                      round trip.
@@ -19,6 +21,7 @@
 #include <limits>
 #include <memory>
 
+#include "fixsum.cuh"
 #include "gicp.cuh"
 
 namespace lgs {
@@ -94,25 +97,31 @@ __global__ void __launch_bounds__(kPCorrBlock) pgicp_correspondence_kernel(NNVie
   }
 }
 
-// block reduction of K per-thread doubles, per-block partials, last block adds them in block order and publishes
+// Reduction of K per-thread exact sums (fixsum.cuh): warp shuffles, CTA, per-CTA partials, last CTA adds them and
+// publishes the K doubles.  Integer addition: the result does not depend on the order of any of these steps.
 template <int K>
-__device__ __forceinline__ void fun_reduce_and_publish(double (&acc)[K], double* __restrict__ partials, unsigned* __restrict__ counter,
+__device__ __forceinline__ void fun_reduce_and_publish(Fix128 (&acc)[K], Fix128* __restrict__ partials, unsigned* __restrict__ counter,
                                                       const Mailbox& mb) {
-  __shared__ double sm[kFunBlock / 32][K];
+  __shared__ Fix128 sm[kFunBlock / 32][K];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    double v = acc[k];
+    Fix128 v = acc[k];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    for (int off = 16; off > 0; off >>= 1) {
+      Fix128 o;
+      o.lo = __shfl_xor_sync(0xffffffffu, v.lo, off);
+      o.hi = __shfl_xor_sync(0xffffffffu, v.hi, off);
+      fix_add(v, o);
+    }
     if (lane == 0) sm[warp][k] = v;
   }
   __syncthreads();
   if (threadIdx.x < K) {
-    double v = 0;
+    Fix128 v = sm[0][threadIdx.x];
 #pragma unroll
-    for (int w = 0; w < kFunBlock / 32; w++) v += sm[w][threadIdx.x];
+    for (int w = 1; w < kFunBlock / 32; w++) fix_add(v, sm[w][threadIdx.x]);
     partials[static_cast<size_t>(blockIdx.x) * K + threadIdx.x] = v;
   }
   __threadfence();
@@ -121,20 +130,26 @@ __device__ __forceinline__ void fun_reduce_and_publish(double (&acc)[K], double*
   __syncthreads();
   if (is_last) {
     __threadfence();
-    double v = 0;
+    Fix128 v = fix_zero();
     if (threadIdx.x < K)
-      for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(partials + static_cast<size_t>(b) * K + threadIdx.x);
+      for (unsigned b = 0; b < gridDim.x; b++) {
+        const volatile Fix128* p = partials + static_cast<size_t>(b) * K + threadIdx.x;
+        Fix128 t;
+        t.lo = p->lo;
+        t.hi = p->hi;
+        fix_add(v, t);
+      }
     if (threadIdx.x == 0) *counter = 0;
-    mailbox_publish<K>(mb, v);
+    mailbox_publish<K>(mb, fix_value(v));
   }
 }
 
 // M_i = (R C1 R^T + C2)^-1, cast to f32 (GO:439-452); publishes the number of correspondences
 __global__ void __launch_bounds__(kFunBlock) pgicp_mahalanobis_kernel(int n, PgicpParams P, const double* __restrict__ cov_src,
                                                                      const double* __restrict__ cov_tgt, const int* __restrict__ corr,
-                                                                     float* __restrict__ mahal, double* __restrict__ partials,
+                                                                     float* __restrict__ mahal, Fix128* __restrict__ partials,
                                                                      unsigned* __restrict__ counter, const Mailbox mb) {
-  double acc[1] = {0.0};
+  Fix128 acc[1] = {fix_zero()};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int c = corr[i];
     if (c < 0) continue;
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_mahalanobis_kernel(int n, Pgi
     m::inv3(temp, inv);
 #pragma unroll
     for (int t = 0; t < 9; t++) mahal[static_cast<size_t>(i) * 9 + t] = static_cast<float>(inv[t]);
-    acc[0] += 1.0;
+    fix_add(acc[0], 1.0);
   }
   fun_reduce_and_publish<1>(acc, partials, counter, mb);
 }
@@ -167,11 +182,11 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_mahalanobis_kernel(int n, Pgi
 template <int MODE>
 __global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* __restrict__ out_cloud, const float4* __restrict__ tgt, int n,
                                                                  PgicpParams P, const int* __restrict__ corr, const float* __restrict__ mahal,
-                                                                 double* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox mb) {
+                                                                 Fix128* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox mb) {
   constexpr int K = MODE == 0 ? 1 : (MODE == 1 ? 12 : 13);
-  double acc[K];
+  Fix128 acc[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = 0.0;
+  for (int k = 0; k < K; k++) acc[k] = fix_zero();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int c = corr[i];
     if (c < 0) continue;
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* 
       const float t1 = __fadd_rn(__fadd_rn(__fmul_rn(M[3], r0), __fmul_rn(M[4], r1)), __fmul_rn(M[5], r2));
       const float t2 = __fadd_rn(__fadd_rn(__fmul_rn(M[6], r0), __fmul_rn(M[7], r1)), __fmul_rn(M[8], r2));
       // 4-lane SSE dot product, lane 3 is zero: (r0 t0 + r2 t2) + (r1 t1 + 0)
-      acc[0] += static_cast<double>(__fadd_rn(__fadd_rn(__fmul_rn(r0, t0), __fmul_rn(r2, t2)), __fmul_rn(r1, t1)));
+      fix_add(acc[0], static_cast<double>(__fadd_rn(__fadd_rn(__fmul_rn(r0, t0), __fmul_rn(r2, t2)), __fmul_rn(r1, t1))));
     } else {
       const double res[3] = {static_cast<double>(r0), static_cast<double>(r1), static_cast<double>(r2)};
       double temp[3];
@@ -197,14 +212,14 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* 
         temp[r] = __dadd_rn(__dadd_rn(__dmul_rn(static_cast<double>(M[r * 3]), res[0]), __dmul_rn(static_cast<double>(M[r * 3 + 1]), res[1])),
                             __dmul_rn(static_cast<double>(M[r * 3 + 2]), res[2]));
       constexpr int o = MODE == 2 ? 1 : 0;
-      if (MODE == 2) acc[0] += __dadd_rn(__dadd_rn(__dmul_rn(res[0], temp[0]), __dmul_rn(res[1], temp[1])), __dmul_rn(res[2], temp[2]));
+      if (MODE == 2) fix_add(acc[0], __dadd_rn(__dadd_rn(__dmul_rn(res[0], temp[0]), __dmul_rn(res[1], temp[1])), __dmul_rn(res[2], temp[2])));
       const double ps[3] = {static_cast<double>(a.x), static_cast<double>(a.y), static_cast<double>(a.z)};
 #pragma unroll
-      for (int r = 0; r < 3; r++) acc[o + r] += temp[r];
+      for (int r = 0; r < 3; r++) fix_add(acc[o + r], temp[r]);
 #pragma unroll
       for (int r = 0; r < 3; r++)
 #pragma unroll
-        for (int cc = 0; cc < 3; cc++) acc[o + 3 + r * 3 + cc] += __dmul_rn(ps[r], temp[cc]);
+        for (int cc = 0; cc < 3; cc++) fix_add(acc[o + 3 + r * 3 + cc], __dmul_rn(ps[r], temp[cc]));
     }
   }
   fun_reduce_and_publish<K>(acc, partials, counter, mb);
@@ -314,7 +329,7 @@ int functor_eval(lgs_gicp_omp* g, const double* x, int mode, double* f, double* 
   memcpy(P.T, g->base_T, sizeof(P.T));
   apply_state(P.T, x);
   const int n = static_cast<int>(g->source->n);
-  double* partials = g->partials.as<double>();
+  Fix128* partials = g->partials.as<Fix128>();
   unsigned* counter = g->state.as<unsigned>();
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
@@ -686,7 +701,7 @@ int ensure_ready(lgs_gicp_omp* g) {
   LGS_TRY(g->output.reserve(n * 16));
   LGS_TRY(g->corr.reserve(n * 4));
   LGS_TRY(g->mahal.reserve(n * 36));
-  LGS_TRY(g->partials.reserve(static_cast<size_t>(fun_grid(g->source->n)) * 13 * 8));
+  LGS_TRY(g->partials.reserve(static_cast<size_t>(fun_grid(g->source->n)) * 13 * sizeof(Fix128)));
   if (!g->state.p) {
     LGS_TRY(g->state.reserve(64));
     LGS_CUDA(cudaMemsetAsync(g->state.p, 0, 64, g->ctx->stream));
@@ -722,7 +737,7 @@ int update_correspondences(lgs_gicp_omp* g) {
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
   pgicp_mahalanobis_kernel<<<fun_grid(n), kFunBlock, 0, ctx->stream>>>(n, P, g->source->covs.as<double>(), g->target->covs.as<double>(), g->corr.as<int>(),
-                                                                      g->mahal.as<float>(), g->partials.as<double>(), g->state.as<unsigned>(), mb);
+                                                                      g->mahal.as<float>(), g->partials.as<Fix128>(), g->state.as<unsigned>(), mb);
   ctx->launches += 2;
   LGS_CUDA(cudaGetLastError());
   double cnt = 0;

@@ -3,8 +3,9 @@
 // plus the un-vendored PCL pieces it stands on: pcl::Registration::align (registration.hpp), pcl::transformPointCloud and
 // BFGS (pcl/registration/bfgs.h, a port of GSL multimin vector_bfgs2 + linear_minimize: Fletcher's line search with
 // bracketing / sectioning and cubic interpolation).  PARITY UNPINNED for those: restated from the published algorithm.
-// Transforms are column-major 4x4 floats (Eigen::Matrix4f).  The f / df sums are taken in ascending source index
-// (the reference's per-thread partial sums make the low bits depend on the thread count, GO:251,274; fdf is serial).
+// Transforms are column-major 4x4 floats (Eigen::Matrix4f).  The f / df / fdf sums are EXACT (exactsum.hpp): the
+// reference's per-thread partial sums make the low bits depend on the thread count (GO:251,274,291-314), and the
+// line search is sensitive to them; an order-independent sum is the reproducible statement of the same quantity.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -13,6 +14,7 @@
 #include <omp.h>
 #endif
 
+#include "exactsum.hpp"
 #include "linalg.hpp"
 #include "oracle.hpp"
 
@@ -507,7 +509,7 @@ double PclGICP::functor_f(const double x[6]) {
   std::memcpy(T, base_transformation, sizeof(T));
   applyState(T, x);
   const size_t m = corr_src.size();
-  double f = 0;
+  ExactSum f;
   for (size_t i = 0; i < m; i++) {
     const int si = corr_src[i];
     const P4& ps = output[si];
@@ -519,9 +521,9 @@ double PclGICP::functor_f(const double x[6]) {
     float t[3];
     for (int r = 0; r < 3; r++) t[r] = (M[r * 3 + 0] * res[0] + M[r * 3 + 1] * res[1]) + M[r * 3 + 2] * res[2];
     const float ret = (res[0] * t[0] + res[2] * t[2]) + res[1] * t[1];
-    f += static_cast<double>(ret);
+    f.add(static_cast<double>(ret));
   }
-  return f / static_cast<double>(static_cast<int>(m));
+  return f.value() / static_cast<double>(static_cast<int>(m));
 }
 
 namespace {
@@ -544,7 +546,7 @@ void PclGICP::functor_df(const double x[6], double g[6]) {
   std::memcpy(T, base_transformation, sizeof(T));
   applyState(T, x);
   const size_t m = corr_src.size();
-  double gs[3] = {0, 0, 0}, R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  ExactSum gs[3], Rs[9];
   for (size_t i = 0; i < m; i++) {
     const int si = corr_src[i];
     const P4& ps = output[si];
@@ -552,14 +554,15 @@ void PclGICP::functor_df(const double x[6], double g[6]) {
     grad_term(T, ps, target[corr_tgt[i]], &mahalanobis[static_cast<size_t>(si) * 9], res, temp);
     float bp[3];
     mul4f_point(base_transformation, ps, bp);  // pp = base_transformation_ * p_src
-    for (int a = 0; a < 3; a++) gs[a] += temp[a];
+    for (int a = 0; a < 3; a++) gs[a].add(temp[a]);
     for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) R[a * 3 + b] += static_cast<double>(bp[a]) * temp[b];
+      for (int b = 0; b < 3; b++) Rs[a * 3 + b].add(static_cast<double>(bp[a]) * temp[b]);
   }
   const double s = 2.0 / static_cast<int>(m);
+  double R[9];
   for (int a = 0; a < 6; a++) g[a] = 0;
-  for (int a = 0; a < 3; a++) g[a] = gs[a] * s;
-  for (int t = 0; t < 9; t++) R[t] *= s;
+  for (int a = 0; a < 3; a++) g[a] = gs[a].value() * s;
+  for (int t = 0; t < 9; t++) R[t] = Rs[t].value() * s;
   computeRDerivative(x, R, g);
 }
 
@@ -570,25 +573,25 @@ void PclGICP::functor_fdf(const double x[6], double& f, double g[6]) {
   std::memcpy(T, base_transformation, sizeof(T));
   applyState(T, x);
   const size_t m = corr_src.size();
-  f = 0;
-  double gs[3] = {0, 0, 0}, R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  ExactSum fs, gs[3], Rs[9];
   for (size_t i = 0; i < m; i++) {
     const int si = corr_src[i];
     const P4& ps = output[si];
     double res[3], temp[3];
     grad_term(T, ps, target[corr_tgt[i]], &mahalanobis[static_cast<size_t>(si) * 9], res, temp);
-    f += (res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2];
+    fs.add((res[0] * temp[0] + res[1] * temp[1]) + res[2] * temp[2]);
     float bp[3];
     mul4f_point(base_transformation, ps, bp);
-    for (int a = 0; a < 3; a++) gs[a] += temp[a];
+    for (int a = 0; a < 3; a++) gs[a].add(temp[a]);
     for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) R[a * 3 + b] += static_cast<double>(bp[a]) * temp[b];
+      for (int b = 0; b < 3; b++) Rs[a * 3 + b].add(static_cast<double>(bp[a]) * temp[b]);
   }
-  f /= static_cast<double>(static_cast<int>(m));
+  f = fs.value() / static_cast<double>(static_cast<int>(m));
   const double s = 2.0 / static_cast<int>(m);
+  double R[9];
   for (int a = 0; a < 6; a++) g[a] = 0;
-  for (int a = 0; a < 3; a++) g[a] = gs[a] * s;
-  for (int t = 0; t < 9; t++) R[t] *= s;
+  for (int a = 0; a < 3; a++) g[a] = gs[a].value() * s;
+  for (int t = 0; t < 9; t++) R[t] = Rs[t].value() * s;
   computeRDerivative(x, R, g);
 }
 

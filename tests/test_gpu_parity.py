@@ -740,6 +740,50 @@ def test_batch_loop_closure_matches_single_pair_runs(api, oracle):
         assert r.fitness == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
 
 
+def test_batch_loop_closure_icp_and_gicp_omp_methods(api, oracle):
+    """The node's other two loop-closure methods through the batch entry point: pcl::IterativeClosestPoint with the
+    GBS:142-151 settings (the YAML default) and pclomp::GeneralizedIterativeClosestPoint with GBS:120-141's."""
+    from lidar_graph_slam_b200 import synth
+    scans, submaps, corrections = synth.loop_pairs(n_pairs=3, n_keyframes=9, n_unique=2)
+    recs = api.batch_align(scans, submaps, method=api.METHOD_ICP, n_workers=2, max_iterations=100, transformation_epsilon=1e-8,
+                           max_correspondence_distance=30.0, euclidean_fitness_epsilon=1e-6)
+    recs1 = api.batch_align(scans, submaps, method=api.METHOD_ICP, n_workers=1, max_iterations=100, transformation_epsilon=1e-8,
+                            max_correspondence_distance=30.0, euclidean_fitness_epsilon=1e-6)
+    for i, r in enumerate(recs):
+        assert list(r.T) == list(recs1[i].T) and r.fitness == recs1[i].fitness  # bitwise independent of the worker count
+        o = oracle.IterativeClosestPoint()
+        o.setMaxCorrespondenceDistance(30)
+        o.setMaximumIterations(100)
+        o.setTransformationEpsilon(1e-8)
+        o.setEuclideanFitnessEpsilon(1e-6)
+        o.setInputTarget(oracle.voxel_grid(submaps[i], 0.5)["points"])
+        o.setInputSource(scans[i])
+        o.align()
+        T = np.array(r.T, np.float32).reshape(4, 4, order="F")
+        t_err, r_err = pose_error(o.final_transformation, T)
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD
+        assert (r.iterations, bool(r.converged), r.line_search_trials) == (o.nr_iterations, o.converged, o.stats["convergence_state"])
+        assert r.fitness == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+    recs = api.batch_align(scans, submaps, method=api.METHOD_GICP_OMP, n_workers=2, max_iterations=100, transformation_epsilon=0.01,
+                           max_correspondence_distance=2.0, max_optimizer_iterations=20)
+    for i, r in enumerate(recs):
+        o = oracle.GeneralizedIterativeClosestPoint()
+        o.setMaxCorrespondenceDistance(2.0)
+        o.setMaximumIterations(100)
+        o.setMaximumOptimizerIterations(20)
+        o.setTransformationEpsilon(0.01)
+        o.setInputTarget(oracle.voxel_grid(submaps[i], 0.5)["points"])
+        o.setInputSource(scans[i])
+        o.align()
+        T = np.array(r.T, np.float32).reshape(4, 4, order="F")
+        t_err, r_err = pose_error(o.final_transformation, T)
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD
+        assert (r.iterations, bool(r.converged)) == (o.nr_iterations, o.converged)
+        assert r.fitness == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
+        t_err, r_err = pose_error(corrections[i], T)
+        assert t_err < 0.1 and r_err < np.radians(0.5)
+
+
 def test_device_resident_inputs(api, oracle, velodyne_pair):
     """_dev entry points: clouds already in HBM (torch tensors) give the same results as host uploads."""
     import torch
