@@ -366,7 +366,11 @@ def main():
                        "voxels": int(gi.n_voxels), "valid_voxels": int(gi.n_valid), "cell_table": "dense" if gi.dense else "hash",
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pairs); within an align the 1.9 MB sweep and the voxel table are re-read from L2 by design",
                        "parallelism": "1 sequence per GPU (replicas, no collective)" if world > 1 else "single GPU",
-                       "evaluations_per_align": evals_dev / K, "target_build_ms": target_build_ms, "pose_error_m": t_err},
+                       "evaluations_per_align": evals_dev / K, "launches_per_align": launches / K,
+                       "evaluator": ("persistent grid: one resident ndt_persistent_kernel serves a run of evaluations, commands and results cross PCIe "
+                                     "through mapped pinned memory (LGS_NDT_PERSISTENT=0 launches one kernel per evaluation); the roofline pass below "
+                                     "times the same evaluation body launched once per evaluation, CUDA events around each launch"),
+                       "target_build_ms": target_build_ms, "pose_error_m": t_err},
             "e2e": {"value": total_steps / (ms_host_max * 1e-3), "unit": "aligns/s", "h2d_bytes_per_step": int(n_src) * 16 + 64,
                     "d2h_bytes_per_step": int(round(evals_host / K * 44 * 8))},
             "gpu_launches": int(launches),

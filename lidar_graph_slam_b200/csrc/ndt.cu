@@ -12,7 +12,10 @@
 //   align        -> computeTransformation (NDT:80-171) + computeStepLengthMT (NDT:771-931) driven from the host;
 //                   each evaluation is one kernel launch + one 352-byte D2H.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <utility>
 #include <vector>
@@ -310,6 +313,14 @@ struct lgs_ndt {
   EvalParams P;
   int evals = 0, trials = 0, hess_recomputes = 0;
   double last_terms = 0;
+  // persistent evaluator (ndt_deriv.cuh): a run of evaluations served by one resident grid, inside lgs_ndt_align only
+  bool allow_session = false, session_active = false;
+  int session_device = -1;
+  lgs::NdtCommandHost* cmd_host = nullptr;  // mapped pinned memory
+  lgs::DevBuf cmd_dev;
+  unsigned long long cmd_seq = 0;
+  int session_evals = 0, session_launches = 0;
+  double trace_roundtrip_us[3] = {0, 0, 0};
   // optional per-kernel timing (bench.py roofline): CUDA event pairs around each evaluation launch
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];
@@ -558,6 +569,56 @@ int build_grid(lgs_ndt* n) {
   return LGS_OK;
 }
 
+// ---- persistent evaluator sessions -------------------------------------------------------------------------------
+// Two resident grids that each need every SM would wait for one another's SMs forever, so at most one session per
+// device exists in the process (batch workers that lose the race simply launch per evaluation).
+std::atomic<int> g_session_owner[64];
+
+bool session_env_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LGS_NDT_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// host side of the command protocol (ndt_deriv.cuh): payload word first, sequence word second, chunk by chunk
+void send_command(lgs_ndt* n, const NdtPose& pose) {
+  const unsigned long long seq = ++n->cmd_seq;
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&pose);
+  volatile NdtCommandChunk* c = n->cmd_host->c;
+  for (int i = 0; i < kCmdWords; i++) {
+    c[i].data = w[i];
+    std::atomic_thread_fence(std::memory_order_release);
+    c[i].seq = seq;
+  }
+}
+
+void end_session(lgs_ndt* n) {
+  if (!n->session_active) return;
+  NdtPose quit;
+  memset(&quit, 0, sizeof(quit));
+  quit.mode = -1;
+  send_command(n, quit);
+  n->session_active = false;
+  g_session_owner[n->session_device].store(0, std::memory_order_release);
+}
+
+// everything a session needs that may allocate or synchronise happens here, before the grid becomes resident
+int prepare_session(lgs_ndt* n) {
+  if (!n->cmd_host) {
+    void* p = nullptr;
+    LGS_CUDA(cudaHostAlloc(&p, sizeof(NdtCommandHost), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, sizeof(NdtCommandHost));
+    n->cmd_host = static_cast<NdtCommandHost*>(p);
+  }
+  if (!n->cmd_dev.p) {
+    LGS_TRY(n->cmd_dev.reserve(sizeof(NdtCommandDev)));
+    LGS_CUDA(cudaMemsetAsync(n->cmd_dev.p, 0, sizeof(NdtCommandDev), n->ctx->stream));
+  }
+  return LGS_OK;
+}
+
 // one computeDerivatives / computeHessian evaluation.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian
 int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* score, double* g, double* H) {
   lgs_ctx* ctx = n->ctx;
@@ -588,12 +649,6 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   const int ns = static_cast<int>(n->n_source);
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (n->profiling) {
-    LGS_CUDA(cudaEventCreate(&ev0));
-    LGS_CUDA(cudaEventCreate(&ev1));
-    LGS_CUDA(cudaEventRecord(ev0, st));
-  }
   static bool smem_opt_in = false;  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per process)
   if (!smem_opt_in) {
     const int smem = static_cast<int>(sizeof(DerivSmem));
@@ -603,7 +658,83 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_opt_in = true;
+  }
+  // ---- persistent evaluator: every evaluation of an align, full-size grids only
+  const bool want_session = n->allow_session && !n->profiling && session_env_enabled() && ns >= 32 * kNumSMs && ctx->device < 64;
+  if (!want_session) end_session(n);
+  if (want_session && !n->session_active) {
+    LGS_TRY(prepare_session(n));
+    int expected = 0;
+    if (g_session_owner[ctx->device].compare_exchange_strong(expected, 1, std::memory_order_acquire)) {
+      void* dv = nullptr;
+      LGS_CUDA(cudaHostGetDevicePointer(&dv, n->cmd_host, 0));
+      const u64 one2 = 0x3f8000003f800000ull;
+      const unsigned long long first = n->cmd_seq + 1;
+      if (n->search == LGS_NDT_DIRECT7)
+        ndt_persistent_kernel<true><<<kNumSMs, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->ex_mean.as<double>(),
+                                                                                      n->ex_icov.as<double>(), n->partials.as<double>(), result, counter, one2,
+                                                                                      mb.r, static_cast<const NdtCommandHost*>(dv), n->cmd_dev.as<NdtCommandDev>(),
+                                                                                      first);
+      else
+        ndt_persistent_kernel<false><<<kNumSMs, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->ex_mean.as<double>(),
+                                                                                       n->ex_icov.as<double>(), n->partials.as<double>(), result, counter, one2,
+                                                                                       mb.r, static_cast<const NdtCommandHost*>(dv), n->cmd_dev.as<NdtCommandDev>(),
+                                                                                       first);
+      ctx->launches++;
+      n->session_launches++;
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) {
+        g_session_owner[ctx->device].store(0, std::memory_order_release);
+        set_error("ndt_persistent_kernel launch failed: %s", cudaGetErrorString(le));
+        return LGS_ERR_CUDA;
+      }
+      n->session_active = true;
+      n->session_device = ctx->device;
+    }
+  }
+  if (n->session_active) {
+    NdtPose pose;
+    memcpy(pose.T, P.T, sizeof(pose.T));
+    memcpy(pose.j_ang, P.j_ang, sizeof(pose.j_ang));
+    memcpy(pose.h_ang, P.h_ang, sizeof(pose.h_ang));
+    pose.mode = mode;
+    pose.pad = 0;
+    pose.token = mb.token;
+    memcpy(pose.j_ang_d, P.j_ang_d, sizeof(pose.j_ang_d));
+    memcpy(pose.h_ang_d, P.h_ang_d, sizeof(pose.h_ang_d));
+    static const bool trace = getenv("LGS_NDT_TRACE") != nullptr;  // development aid: device round trip per evaluation
+    const auto t_send = std::chrono::steady_clock::now();
+    send_command(n, pose);
+    n->session_evals++;
+    double h[kMailboxRecords];
+    const int rc = mailbox_wait(ctx, mb, K, h);
+    if (trace) n->trace_roundtrip_us[mode] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_send).count();
+    if (rc != LGS_OK) {
+      end_session(n);
+      return rc;
+    }
+    if (mode == 2) {
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[tri(i, j)];
+      return LGS_OK;
+    }
+    *score = h[0];
+    memcpy(g, h + 1, 6 * sizeof(double));
+    if (mode == 0) {
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[7 + tri(i, j)];
+    }
+    n->last_terms = h[mode == 0 ? 28 : 7];
+    return LGS_OK;
+  }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (n->profiling) {
+    LGS_CUDA(cudaEventCreate(&ev0));
+    LGS_CUDA(cudaEventCreate(&ev1));
+    LGS_CUDA(cudaEventRecord(ev0, st));
   }
   {
     // one CTA per SM (fewer when the cloud has fewer rounds of 32 points than SMs)
@@ -776,8 +907,11 @@ int lgs_ndt_create(lgs_ctx* ctx, lgs_ndt** out) {
 
 void lgs_ndt_destroy(lgs_ndt* n) {
   if (!n) return;
+  end_session(n);
   cudaSetDevice(n->ctx->device);
   cudaStreamSynchronize(n->ctx->stream);
+  if (n->cmd_host) cudaFreeHost(n->cmd_host);
+  n->cmd_dev.release();
   for (DevBuf* b : {&n->target, &n->source, &n->out_cloud, &n->table, &n->hkeys, &n->recs, &n->ex_idx, &n->ex_n, &n->ex_mean, &n->ex_cov, &n->ex_icov,
                     &n->small, &n->partials, &n->result})
     b->release();
@@ -846,8 +980,24 @@ int lgs_ndt_set_source_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
 }
 
 // pcl::Registration::align shell + computeTransformation (NDT:80-171)
+static int ndt_align_body(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud);
+
 int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
   LGS_REQUIRE(n && res, "null argument");
+  n->allow_session = true;
+  const auto t0 = std::chrono::steady_clock::now();
+  n->trace_roundtrip_us[0] = n->trace_roundtrip_us[1] = n->trace_roundtrip_us[2] = 0;
+  const int rc = ndt_align_body(n, guess16, res, out_cloud);
+  end_session(n);  // every exit path releases the resident grid
+  n->allow_session = false;
+  if (getenv("LGS_NDT_TRACE"))
+    fprintf(stderr, "[lgs ndt] align %.1f us: %d evaluations (%d trials, %d f64 Hessians), device round trips mode0 %.1f us, mode1 %.1f us, mode2 %.1f us in total\n",
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), res->evaluations, res->line_search_trials,
+            res->hessian_recomputes, n->trace_roundtrip_us[0], n->trace_roundtrip_us[1], n->trace_roundtrip_us[2]);
+  return rc;
+}
+
+static int ndt_align_body(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
   memset(res, 0, sizeof(*res));
   if (!n->have_target || !n->have_source) {
     set_error("lgs_ndt_align: setInputTarget and setInputSource must be called first");
@@ -895,6 +1045,7 @@ int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float
     nr_iterations++;
   }
   if (!early_exit) trans_probability = score / n_in;  // NDT:170
+  end_session(n);  // the optimiser is done: what follows (output cloud, fitness) are ordinary launches
   memcpy(res->T, n->final_T, sizeof(float) * 16);
   res->trans_probability = trans_probability;
   res->iterations = nr_iterations;
