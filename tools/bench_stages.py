@@ -143,6 +143,60 @@ def main():
     med, mn = timed(lambda: g.getFitnessScore())
     emit("cfg2 GICP getFitnessScore", med, mn, 32 * n_s)
 
+    # ---- PointCloud2 ingest: Velodyne PointXYZIRT payload, point_step 22
+    n = 262144
+    rs = np.random.RandomState(3)
+    raw = rs.randint(0, 256, size=(n, 22)).astype(np.uint8)
+    raw[:, 0:16] = np.ascontiguousarray(sweeps[0][:n]).view(np.uint8).reshape(n, 16)
+    msg = raw.tobytes()
+    fields = {"x": (0, 7), "y": (4, 7), "z": (8, 7), "intensity": (12, 7), "ring": (16, 4), "time": (18, 7)}
+    med, mn = timed(lambda: api.from_pointcloud2(msg, n, 1, 22, fields, ctx=ctx))
+    emit("PointCloud2 ingest, point_step 22 (pageable host payload in, device xyzi out; H2D of %d bytes included)" % (n * 22), med, mn, n * (22 + 16), n=n,
+         sweeps_per_s=1e3 / med)
+
+    # ---- key-frame array: sub-map assembly: 20 key frames of ~50 k points, newest first, then + VoxelGrid 0.5
+    kf = api.KeyFrameArray(ctx)
+    for i in range(24):
+        P = np.eye(4, dtype=np.float32)
+        P[:3, 3] = [1.0 * i, 0.1 * i, 0]
+        kf.push(sw[i * 1000: i * 1000 + 50000], P)
+    ids = [23 - k for k in range(20)]
+    import ctypes as C
+    out_p, out_n = C.c_void_p(), C.c_int64()
+    idarr = np.asarray(ids, np.int32)
+
+    def assemble(leaf):
+        api.check(kf._L.lgs_keyframes_assemble(kf._h, idarr.ctypes.data_as(C.c_void_p), len(ids), float(leaf), C.byref(out_p), C.byref(out_n)))
+    med, mn = timed(lambda: assemble(0.0))
+    emit("sub-map assembly: 20 key frames x 50 000 points (transform + concatenate, device resident)", med, mn, 32 * 20 * 50000, n=20 * 50000)
+    med, mn = timed(lambda: assemble(0.5))
+    emit("sub-map assembly + VoxelGrid 0.5 m (GBS:297-313)", med, mn, 32 * 20 * 50000 + (16 + 8) * 20 * 50000 + 16 * int(out_n.value), n=20 * 50000, voxels=int(out_n.value))
+
+    # ---- the node's other two registration methods on the cfg 2 clouds
+    icp = api.IterativeClosestPoint(ctx)
+    icp.setMaxCorrespondenceDistance(30)
+    icp.setMaximumIterations(100)
+    icp.setTransformationEpsilon(1e-8)
+    icp.setEuclideanFitnessEpsilon(1e-6)
+    icp.setInputTarget(clouds[0])
+    icp.setInputSource(clouds[1])
+    icp.align()
+    it = int(icp.result.iterations)
+    med, mn = timed(lambda: icp.align())
+    emit("cfg2 clouds, pcl::IterativeClosestPoint (GBS:142-151 settings): align, %d iterations" % it, med, mn, it * n_s * 48, n_source=n_s, n_target=n_t,
+         aligns_per_s=1e3 / med, us_per_iteration=1e3 * med / max(it, 1))
+    go = api.GeneralizedIterativeClosestPoint(ctx)
+    go.setMaxCorrespondenceDistance(2.0)
+    go.setMaximumIterations(100)
+    go.setTransformationEpsilon(0.01)
+    go.setInputTarget(clouds[0])
+    go.setInputSource(clouds[1])
+    go.align()
+    nf = int(go.result.evaluations + go.result.line_search_trials)
+    med, mn = timed(lambda: go.align())
+    emit("cfg2 clouds, pclomp GICP (BFGS): align with kept covariances, %d outer iterations, %d functor evaluations" % (int(go.result.iterations), nf), med, mn,
+         nf * n_s * (16 + 16 + 36 + 4), n_source=n_s, n_target=n_t, aligns_per_s=1e3 / med, us_per_functor_evaluation=1e3 * med / max(nf, 1))
+
 
 if __name__ == "__main__":
     main()
