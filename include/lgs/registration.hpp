@@ -439,5 +439,91 @@ class PclGicpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> 
   }
 };
 
+// pclomp::GeneralizedIterativeClosestPoint ("GICP", LSM:73-96 / GBS:120-141) and pcl::IterativeClosestPoint ("ICP",
+// GBS:142-151) behind the same pcl::Registration base.  The pcl::Registration members the nodes set
+// (max_iterations_, transformation_epsilon_, corr_dist_threshold_, euclidean_fitness_epsilon_) are forwarded at align time.
+class PclGicpOmpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> {
+ public:
+  using Base = pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>;
+  GeneralizedIterativeClosestPoint impl;
+  PclGicpOmpAdapter() {
+    reg_name_ = "lgs::GeneralizedIterativeClosestPoint";
+    max_iterations_ = 200;            // gicp_omp.h:121-125
+    transformation_epsilon_ = 5e-4;
+    corr_dist_threshold_ = 5.;
+  }
+  void setInputTarget(const Base::PointCloudTargetConstPtr& cloud) override {
+    Base::setInputTarget(cloud);
+    lgs_gicp_omp_set_target(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
+  }
+  void setInputSource(const Base::PointCloudSourceConstPtr& cloud) override {
+    Base::setInputSource(cloud);
+    lgs_gicp_omp_set_source(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
+  }
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+    double f = std::numeric_limits<double>::max();
+    lgs_gicp_omp_fitness(impl.handle(), max_range, &f);
+    return f;
+  }
+
+ protected:
+  void computeTransformation(Base::PointCloudSource& output, const Eigen::Matrix4f& guess) override {
+    lgs_gicp_omp_set_transformation_epsilon(impl.handle(), transformation_epsilon_);
+    lgs_gicp_omp_set_maximum_iterations(impl.handle(), max_iterations_);
+    lgs_gicp_omp_set_max_correspondence_distance(impl.handle(), corr_dist_threshold_);
+    lgs_align_result r{};
+    std::vector<float> packed(output.size() * 4 + 4);
+    const int rc = lgs_gicp_omp_align(impl.handle(), guess.data(), &r, packed.data());
+    converged_ = rc == LGS_OK && r.converged != 0;
+    nr_iterations_ = r.iterations;
+    final_transformation_ = Eigen::Map<const Eigen::Matrix4f>(r.T);
+    for (size_t i = 0; i < output.size(); i++) {
+      output[i].x = packed[4 * i];
+      output[i].y = packed[4 * i + 1];
+      output[i].z = packed[4 * i + 2];
+    }
+  }
+};
+
+class PclIcpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> {
+ public:
+  using Base = pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>;
+  IterativeClosestPoint impl;
+  PclIcpAdapter() { reg_name_ = "lgs::IterativeClosestPoint"; }
+  void setInputTarget(const Base::PointCloudTargetConstPtr& cloud) override {
+    Base::setInputTarget(cloud);
+    lgs_icp_set_target(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
+  }
+  void setInputSource(const Base::PointCloudSourceConstPtr& cloud) override {
+    Base::setInputSource(cloud);
+    lgs_icp_set_source(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
+  }
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+    double f = std::numeric_limits<double>::max();
+    lgs_icp_fitness(impl.handle(), max_range, &f);
+    return f;
+  }
+
+ protected:
+  void computeTransformation(Base::PointCloudSource& output, const Eigen::Matrix4f& guess) override {
+    lgs_icp_set_transformation_epsilon(impl.handle(), transformation_epsilon_);
+    lgs_icp_set_transformation_rotation_epsilon(impl.handle(), transformation_rotation_epsilon_);
+    lgs_icp_set_euclidean_fitness_epsilon(impl.handle(), euclidean_fitness_epsilon_);
+    lgs_icp_set_maximum_iterations(impl.handle(), max_iterations_);
+    lgs_icp_set_max_correspondence_distance(impl.handle(), corr_dist_threshold_);
+    lgs_align_result r{};
+    std::vector<float> packed(output.size() * 4 + 4);
+    const int rc = lgs_icp_align(impl.handle(), guess.data(), &r, packed.data());
+    converged_ = rc == LGS_OK && r.converged != 0;
+    nr_iterations_ = r.iterations;
+    final_transformation_ = Eigen::Map<const Eigen::Matrix4f>(r.T);
+    for (size_t i = 0; i < output.size(); i++) {
+      output[i].x = packed[4 * i];
+      output[i].y = packed[4 * i + 1];
+      output[i].z = packed[4 * i + 2];
+    }
+  }
+};
+
 }  // namespace lgs
 #endif
