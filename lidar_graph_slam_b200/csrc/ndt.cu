@@ -314,7 +314,7 @@ struct lgs_ndt {
   int evals = 0, trials = 0, hess_recomputes = 0;
   double last_terms = 0;
   // persistent evaluator (ndt_deriv.cuh): a run of evaluations served by one resident grid, inside lgs_ndt_align only
-  bool allow_session = false, session_active = false;
+  bool allow_session = false, session_active = false, session_broken = false;
   int session_device = -1;
   lgs::NdtCommandHost* cmd_host = nullptr;  // mapped pinned memory
   lgs::DevBuf cmd_dev;
@@ -574,10 +574,17 @@ int build_grid(lgs_ndt* n) {
 // device exists in the process (batch workers that lose the race simply launch per evaluation).
 std::atomic<int> g_session_owner[64];
 
+// LGS_NDT_PERSISTENT=0 turns the resident grid off.  It is also off under an injected CUDA tool (Nsight Compute
+// serialises kernels and blocks the host inside the launch call until the kernel has finished - a grid that waits
+// for a host command would only end by its time-out).
 bool session_env_enabled() {
   static const bool on = [] {
     const char* e = getenv("LGS_NDT_PERSISTENT");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    for (const char* v : {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"})
+      if (getenv(v)) return false;
+    return true;
   }();
   return on;
 }
@@ -663,7 +670,7 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     smem_opt_in = true;
   }
   // ---- persistent evaluator: every evaluation of an align, full-size grids only
-  const bool want_session = n->allow_session && !n->profiling && session_env_enabled() && ns >= 32 * kNumSMs && ctx->device < 64;
+  const bool want_session = n->allow_session && !n->profiling && !n->session_broken && session_env_enabled() && ns >= 32 * kNumSMs && ctx->device < 64;
   if (!want_session) end_session(n);
   if (want_session && !n->session_active) {
     LGS_TRY(prepare_session(n));
@@ -713,8 +720,15 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     const int rc = mailbox_wait(ctx, mb, K, h);
     if (trace) n->trace_roundtrip_us[mode] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_send).count();
     if (rc != LGS_OK) {
+      // The grid ended without answering (its command time-out: the host was held up for longer than that, e.g. by a tool
+      // that blocks in the launch call).  If the stream is healthy, evaluate this pose with a plain launch and keep doing
+      // so for the rest of this object's life; a real CUDA error is reported as it is.
       end_session(n);
-      return rc;
+      if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return rc;
+      n->session_broken = true;
+      n->evals -= mode == 2 ? 0 : 1;
+      n->hess_recomputes -= mode == 2 ? 1 : 0;
+      return evaluate(n, T, p, mode, score, g, H);
     }
     if (mode == 2) {
       for (int i = 0; i < 6; i++)
