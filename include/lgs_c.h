@@ -337,6 +337,12 @@ int lgs_keyframes_push_dev(lgs_keyframes* kf, const float* pts_dev, int64_t n, c
 /* a pose-graph update moved the key frame (the optimised poses the back end publishes, GBS:343-352) */
 int lgs_keyframes_set_pose(lgs_keyframes* kf, int32_t id, const float* pose16);
 int lgs_keyframes_size(lgs_keyframes* kf, int64_t* count, int64_t* total_points);
+/* key_frame.accum_distance (LSM:193) and detect_loop_with_accum_dist (GBS:157-187): all key frames at least
+ * accumulate_distance_threshold of path behind `latest_id` and closer to it than search_for_candidate_threshold;
+ * *nearest = the single candidate optimization_callback picks (GBS:263-280), -1 if none.  candidates may be NULL. */
+int lgs_keyframes_set_accum_distance(lgs_keyframes* kf, int32_t id, double accum_distance);
+int lgs_keyframes_detect_loop(lgs_keyframes* kf, int32_t latest_id, double accumulate_distance_threshold, double search_for_candidate_threshold,
+                              int32_t* candidates, int32_t capacity, int32_t* n_candidates, int32_t* nearest);
 /* sub-map = concatenation, in the order of ids[], of pcl::transformPointCloud(key frame, pose); leaf > 0 applies
  * pcl::VoxelGrid(leaf) to the result (GBS:311-313).  *out_dev is a packed xyzi device cloud owned by kf, valid
  * until the next assemble call; feed it to lgs_*_set_target_dev / set_source_dev. */
@@ -371,6 +377,14 @@ typedef struct lgs_batch_params {
 int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
                     const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
                     const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev);
+
+/* The same with both clouds of every pair taken from the device-resident key-frame array (optimization_callback,
+ * GBS:247-251 + 297-322, for a list of candidates): pair i aligns key frame scan_ids[i], transformed by its pose, to the
+ * submap_leaf-filtered concatenation of key frames center_ids[i] - K .. center_ids[i] + K (K = search_key_frame_num,
+ * graph_based_slam.param.yaml:4), ascending, clipped to the array.  Only the records cross PCIe. */
+int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs,
+                              const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
+                              const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev);
 
 /* The per-worker device state of lgs_batch_align (stream, registration objects, staging buffers) is kept in a
  * process-wide pool between calls, the way the reference keeps one registration_ object per node for its lifetime

@@ -514,6 +514,40 @@ class KeyFrameArray:
         check(self._L.lgs_keyframes_size(self._h, C.byref(c), None))
         return c.value
 
+    def set_accum_distance(self, kid, accum_distance):
+        check(self._L.lgs_keyframes_set_accum_distance(self._h, int(kid), float(accum_distance)))
+
+    def detect_loop(self, latest_id, accumulate_distance_threshold=100.0, search_for_candidate_threshold=15.0):
+        """detect_loop_with_accum_dist (GBS:157-187; defaults of graph_based_slam.param.yaml): (candidate ids, nearest id or -1)."""
+        cap = max(len(self), 1)
+        cand = np.empty(cap, np.int32)
+        n, best = C.c_int32(), C.c_int32()
+        check(self._L.lgs_keyframes_detect_loop(self._h, int(latest_id), float(accumulate_distance_threshold), float(search_for_candidate_threshold),
+                                                cand.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(best)))
+        return cand[: n.value].copy(), best.value
+
+    def batch_align(self, scan_ids, center_ids, search_key_frame_num=20, method=METHOD_GICP, guesses=None, pair_id0=0, records_dev=None,
+                    max_iterations=100, transformation_epsilon=0.01, max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0,
+                    ndt_step_size=0.1, submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0, max_optimizer_iterations=0, euclidean_fitness_epsilon=0.0):
+        """Loop-closure verification of (key frame, neighbourhood) candidates without leaving the GPU (lgs_batch_align_keyframes)."""
+        sid = np.ascontiguousarray(scan_ids, np.int32)
+        cid = np.ascontiguousarray(center_ids, np.int32)
+        n = int(sid.size)
+        assert cid.size == n
+        g = None
+        if guesses is not None:
+            g = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).reshape(4, 4).ravel(order="F") for T in guesses]))
+        bp = BatchParams(method=method, max_iterations=max_iterations, transformation_epsilon=transformation_epsilon,
+                         max_correspondence_distance=max_correspondence_distance, k_correspondences=k_correspondences,
+                         ndt_resolution=ndt_resolution, ndt_step_size=ndt_step_size, submap_leaf=submap_leaf,
+                         fitness_max_range=fitness_max_range, n_workers=n_workers, max_optimizer_iterations=max_optimizer_iterations,
+                         euclidean_fitness_epsilon=euclidean_fitness_epsilon)
+        recs = (AlignResult * max(n, 1))()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self._L.lgs_batch_align_keyframes(self._h, None, C.byref(bp), n, vp(sid), vp(cid), int(search_key_frame_num),
+                                                vp(g) if g is not None else None, int(pair_id0), recs, C.c_void_p(records_dev) if records_dev else None))
+        return [recs[i] for i in range(n)]
+
     def assemble(self, ids, leaf=0.0):
         """Returns a CUDA float32 tensor (N, 4): a copy of the library's sub-map buffer."""
         import torch

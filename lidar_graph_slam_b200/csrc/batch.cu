@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "gicp.cuh"
+#include "keyframes.cuh"
 #include "voxel_common.cuh"
 
 using namespace lgs;
@@ -32,6 +33,11 @@ struct BatchShared {
   const float* guesses;
   int32_t pair_id0;
   lgs_align_result* records;
+  // key-frame mode (lgs_batch_align_keyframes): pair i = key frame scan_ids[i] against the neighbourhood of center_ids[i]
+  const lgs_keyframes* kf = nullptr;
+  const int32_t* scan_ids = nullptr;
+  const int32_t* center_ids = nullptr;
+  int32_t search_key_frame_num = 0;
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
   std::mutex err_mu;
@@ -57,16 +63,30 @@ struct StageClock {
   }
 };
 
-int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_omp* gomp, DevBuf* sub_raw, DevBuf* sub_ds, BatchShared* S, int64_t i) {
+int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_omp* gomp, DevBuf* sub_raw, DevBuf* sub_ds, DevBuf* scan_buf, BatchShared* S, int64_t i) {
   const lgs_batch_params& bp = *S->bp;
   lgs_align_result& rec = S->records[i];
   memset(&rec, 0, sizeof(rec));
   StageClock clk(ctx->stream);
   // submap -> (optional) VoxelGrid -> device-resident target
-  LGS_TRY(upload_cloud(ctx, S->submaps[i], S->n_submap[i], S->stride, sub_raw));
+  int64_t n_tgt = 0;
+  const float* scan_dev = nullptr;  // key-frame mode: the scan is a device cloud as well
+  int64_t n_scan_dev = 0;
+  if (S->kf) {
+    // GBS:297-309: key frames min_id - K .. min_id + K that exist, ascending; GBS:247-251: the scan in the map frame
+    std::vector<int32_t> ids;
+    const int64_t count = keyframes_count(S->kf);
+    for (int32_t d = -S->search_key_frame_num; d <= S->search_key_frame_num; d++) {
+      const int64_t id = static_cast<int64_t>(S->center_ids[i]) + d;
+      if (id >= 0 && id < count) ids.push_back(static_cast<int32_t>(id));
+    }
+    LGS_TRY(keyframes_assemble_into(S->kf, ctx, ids.data(), static_cast<int32_t>(ids.size()), &ctx->tmp[2], sub_raw, &n_tgt));
+  } else {
+    LGS_TRY(upload_cloud(ctx, S->submaps[i], S->n_submap[i], S->stride, sub_raw));
+    n_tgt = S->n_submap[i];
+  }
   clk.lap(0);
   const float* tgt_dev = sub_raw->as<float>();
-  int64_t n_tgt = S->n_submap[i];
   if (bp.submap_leaf > 0 && n_tgt > 0) {
     LGS_TRY(sub_ds->reserve(static_cast<size_t>(n_tgt) * 16));
     const float leaf[3] = {bp.submap_leaf, bp.submap_leaf, bp.submap_leaf};
@@ -76,12 +96,20 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     n_tgt = info.n_out;
   }
   clk.lap(1);
+  if (S->kf) {
+    // into the worker's own buffer: setInputTarget may voxelise at once and use every scratch arena of the context
+    LGS_TRY(keyframes_assemble_into(S->kf, ctx, S->scan_ids + i, 1, &ctx->tmp[2], scan_buf, &n_scan_dev));
+    scan_dev = scan_buf->as<float>();
+  }
   const float* guess = S->guesses ? S->guesses + 16 * i : nullptr;
   const double max_range = bp.fitness_max_range > 0 ? bp.fitness_max_range : std::numeric_limits<double>::max();
   if (bp.method == LGS_METHOD_GICP) {
     LGS_TRY(lgs_gicp_set_target_dev(gicp, tgt_dev, n_tgt));
     clk.lap(2);
-    LGS_TRY(lgs_gicp_set_source(gicp, S->scans[i], S->n_scan[i], S->stride));
+    if (scan_dev)
+      LGS_TRY(lgs_gicp_set_source_dev(gicp, scan_dev, n_scan_dev));
+    else
+      LGS_TRY(lgs_gicp_set_source(gicp, S->scans[i], S->n_scan[i], S->stride));
     clk.lap(3);
     LGS_TRY(lgs_gicp_align(gicp, guess, &rec, nullptr));
     clk.lap(4);
@@ -90,7 +118,10 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
   } else if (bp.method == LGS_METHOD_ICP) {
     LGS_TRY(lgs_icp_set_target_dev(icp, tgt_dev, n_tgt));
     clk.lap(2);
-    LGS_TRY(lgs_icp_set_source(icp, S->scans[i], S->n_scan[i], S->stride));
+    if (scan_dev)
+      LGS_TRY(lgs_icp_set_source_dev(icp, scan_dev, n_scan_dev));
+    else
+      LGS_TRY(lgs_icp_set_source(icp, S->scans[i], S->n_scan[i], S->stride));
     clk.lap(3);
     LGS_TRY(lgs_icp_align(icp, guess, &rec, nullptr));
     clk.lap(4);
@@ -99,7 +130,10 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
   } else if (bp.method == LGS_METHOD_GICP_OMP) {
     LGS_TRY(lgs_gicp_omp_set_target_dev(gomp, tgt_dev, n_tgt));
     clk.lap(2);
-    LGS_TRY(lgs_gicp_omp_set_source(gomp, S->scans[i], S->n_scan[i], S->stride));
+    if (scan_dev)
+      LGS_TRY(lgs_gicp_omp_set_source_dev(gomp, scan_dev, n_scan_dev));
+    else
+      LGS_TRY(lgs_gicp_omp_set_source(gomp, S->scans[i], S->n_scan[i], S->stride));
     clk.lap(3);
     LGS_TRY(lgs_gicp_omp_align(gomp, guess, &rec, nullptr));
     clk.lap(4);
@@ -108,7 +142,10 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
   } else {
     LGS_TRY(lgs_ndt_set_target_dev(ndt, tgt_dev, n_tgt));
     clk.lap(2);
-    LGS_TRY(lgs_ndt_set_source(ndt, S->scans[i], S->n_scan[i], S->stride));
+    if (scan_dev)
+      LGS_TRY(lgs_ndt_set_source_dev(ndt, scan_dev, n_scan_dev));
+    else
+      LGS_TRY(lgs_ndt_set_source(ndt, S->scans[i], S->n_scan[i], S->stride));
     clk.lap(3);
     LGS_TRY(lgs_ndt_align(ndt, guess, &rec, nullptr));
     clk.lap(4);
@@ -132,7 +169,7 @@ struct WorkerSlot {
   lgs_ndt* ndt = nullptr;
   lgs_icp* icp = nullptr;
   lgs_gicp_omp* gomp = nullptr;
-  DevBuf sub_raw, sub_ds;
+  DevBuf sub_raw, sub_ds, scan_buf;
   void destroy() {
     if (ctx) {
       cudaSetDevice(device);
@@ -140,6 +177,7 @@ struct WorkerSlot {
     }
     sub_raw.release();
     sub_ds.release();
+    scan_buf.release();
     if (gicp) lgs_gicp_destroy(gicp);
     if (ndt) lgs_ndt_destroy(ndt);
     if (icp) lgs_icp_destroy(icp);
@@ -222,7 +260,7 @@ void worker(BatchShared* S) {
   while (rc == LGS_OK && !S->failed.load()) {
     const int64_t i = S->next.fetch_add(1);
     if (i >= S->n_pairs) break;
-    rc = run_pair(w->ctx, w->gicp, w->ndt, w->icp, w->gomp, &w->sub_raw, &w->sub_ds, S, i);
+    rc = run_pair(w->ctx, w->gicp, w->ndt, w->icp, w->gomp, &w->sub_raw, &w->sub_ds, &w->scan_buf, S, i);
   }
   if (rc != LGS_OK) {
     std::lock_guard<std::mutex> lk(S->err_mu);
@@ -242,6 +280,8 @@ void worker(BatchShared* S) {
 
 }  // namespace
 
+static int run_batch(BatchShared& S, void* cuda_stream, void* records_dev);
+
 extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
                                const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
                                const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev) {
@@ -249,11 +289,6 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
   LGS_REQUIRE(n_pairs >= 0, "negative pair count");
   LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
   LGS_REQUIRE(n_pairs == 0 || (scans && n_scan && submaps && n_submap), "null pair arrays");
-  int count = 0;
-  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
-    set_error("no CUDA device available; this library has no CPU fallback");
-    return LGS_ERR_CUDA;
-  }
   BatchShared S;
   S.bp = params;
   S.device = device;
@@ -266,6 +301,52 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
   S.guesses = guesses16;
   S.pair_id0 = pair_id0;
   S.records = records;
+  return run_batch(S, cuda_stream, records_dev);
+}
+
+// The same verification with both clouds of every pair taken from the device-resident key-frame array: pair i aligns key
+// frame scan_ids[i] (in the map frame, GBS:247-251) to the VoxelGrid-filtered neighbourhood center_ids[i] +- search_key_frame_num
+// (GBS:297-313).  Nothing but the 96-byte records crosses PCIe.
+extern "C" int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs,
+                                         const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
+                                         const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev) {
+  LGS_REQUIRE(kf && params && records, "null argument");
+  LGS_REQUIRE(n_pairs >= 0 && search_key_frame_num >= 0, "negative count");
+  LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
+  LGS_REQUIRE(n_pairs == 0 || (scan_ids && center_ids), "null pair arrays");
+  const int64_t count = keyframes_count(kf);
+  for (int64_t i = 0; i < n_pairs; i++)
+    LGS_REQUIRE(scan_ids[i] >= 0 && scan_ids[i] < count && center_ids[i] >= 0 && center_ids[i] < count, "key frame id out of range");
+  LGS_TRY(keyframes_wait_resident(kf));
+  BatchShared S;
+  S.bp = params;
+  S.device = keyframes_device(kf);
+  S.n_pairs = n_pairs;
+  S.scans = nullptr;
+  S.n_scan = nullptr;
+  S.submaps = nullptr;
+  S.n_submap = nullptr;
+  S.stride = 16;
+  S.guesses = guesses16;
+  S.pair_id0 = pair_id0;
+  S.records = records;
+  S.kf = kf;
+  S.scan_ids = scan_ids;
+  S.center_ids = center_ids;
+  S.search_key_frame_num = search_key_frame_num;
+  return run_batch(S, cuda_stream, records_dev);
+}
+
+static int run_batch(BatchShared& S, void* cuda_stream, void* records_dev) {
+  const lgs_batch_params* params = S.bp;
+  const int64_t n_pairs = S.n_pairs;
+  const int device = S.device;
+  lgs_align_result* records = S.records;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    set_error("no CUDA device available; this library has no CPU fallback");
+    return LGS_ERR_CUDA;
+  }
   int W = params->n_workers > 0 ? params->n_workers : 4;
   if (W > n_pairs) W = static_cast<int>(std::max<int64_t>(n_pairs, 1));
   if (W > 32) W = 32;

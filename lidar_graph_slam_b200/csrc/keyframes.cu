@@ -13,8 +13,11 @@
 // host, refreshed by lgs_keyframes_set_pose after a pose-graph update (GBS:343-352 feeds corrected poses back).
 // Algorithmic bytes of an assembly: 32 per output point (float4 in, float4 out); HBM-bound.
 #include <algorithm>
+#include <cmath>
+#include <limits>
 #include <vector>
 
+#include "keyframes.cuh"
 #include "voxel_common.cuh"
 
 namespace lgs {
@@ -63,6 +66,7 @@ struct lgs_keyframes {
     size_t offset = 0;  // points into the chunk
     int64_t n = 0;
     float pose[16];
+    double accum_distance = 0;  // key_frame.accum_distance (LSM:193): path length at this key frame
   };
   std::vector<Chunk*> chunks;
   std::vector<Frame> frames;
@@ -122,6 +126,59 @@ int push(lgs_keyframes* kf, const void* pts, const float* pts_dev, int64_t n, in
 
 }  // namespace
 
+namespace lgs {
+
+int keyframes_wait_resident(const lgs_keyframes* kf) {
+  LGS_CUDA(cudaSetDevice(kf->ctx->device));
+  LGS_CUDA(cudaStreamSynchronize(kf->ctx->stream));
+  return LGS_OK;
+}
+int64_t keyframes_count(const lgs_keyframes* kf) { return static_cast<int64_t>(kf->frames.size()); }
+int keyframes_device(const lgs_keyframes* kf) { return kf->ctx->device; }
+
+int keyframes_assemble_into(const lgs_keyframes* kf, lgs_ctx* ctx, const int32_t* ids, int32_t n_ids, DevBuf* poses_dev, DevBuf* out, int64_t* n_out) {
+  LGS_REQUIRE(n_ids >= 0, "negative id count");
+  int64_t total = 0;
+  for (int i = 0; i < n_ids; i++) {
+    LGS_REQUIRE(ids[i] >= 0 && ids[i] < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
+    total += kf->frames[ids[i]].n;
+  }
+  LGS_REQUIRE(total < (int64_t(1) << 31), "sub-map larger than 2^31 points");
+  LGS_TRY(out->reserve(static_cast<size_t>(std::max<int64_t>(total, 1)) * 16));
+  *n_out = total;
+  if (total == 0) return LGS_OK;
+  cudaStream_t st = ctx->stream;
+  LGS_TRY(poses_dev->reserve(static_cast<size_t>(n_ids) * 64));
+  LGS_TRY(ctx->pin_up.reserve(static_cast<size_t>(n_ids) * 64));
+  float* hp = ctx->pin_up.as<float>();
+  LGS_CUDA(cudaStreamSynchronize(st));  // the pinned staging block may still be in flight from an earlier call on this stream
+  for (int i = 0; i < n_ids; i++) memcpy(hp + 16 * i, kf->frames[ids[i]].pose, 64);
+  LGS_CUDA(cudaMemcpyAsync(poses_dev->p, hp, static_cast<size_t>(n_ids) * 64, cudaMemcpyHostToDevice, st));
+  int64_t row = 0;
+  for (int s0 = 0; s0 < n_ids; s0 += kMaxSegments) {
+    SubmapSegments S;
+    S.count = std::min(kMaxSegments, n_ids - s0);
+    int acc = 0;
+    for (int s = 0; s < S.count; s++) {
+      const auto& f = kf->frames[ids[s0 + s]];
+      S.src[s] = kf->chunks[f.chunk]->buf.as<float4>() + f.offset;
+      S.begin[s] = acc;
+      acc += static_cast<int>(f.n);
+    }
+    S.begin[S.count] = acc;
+    if (acc > 0) {
+      const int grid = std::max(1, std::min(grid_for(acc, 256), kNumSMs * 8));
+      submap_assemble_kernel<<<grid, 256, 0, st>>>(S, poses_dev->as<float>() + 16 * s0, out->as<float4>() + row);
+      ctx->launches++;
+      LGS_CUDA(cudaGetLastError());
+    }
+    row += acc;
+  }
+  return LGS_OK;
+}
+
+}  // namespace lgs
+
 extern "C" {
 
 int lgs_keyframes_create(lgs_ctx* ctx, lgs_keyframes** out) {
@@ -172,48 +229,13 @@ int lgs_keyframes_size(lgs_keyframes* kf, int64_t* count, int64_t* total_points)
 
 int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids, float leaf, float** out_dev, int64_t* n_out) {
   LGS_REQUIRE(kf && out_dev && n_out && (ids || n_ids == 0), "null argument");
-  LGS_REQUIRE(n_ids >= 0, "negative id count");
   lgs_ctx* ctx = kf->ctx;
   LGS_TRY(use_device(ctx));
   int64_t total = 0;
-  for (int i = 0; i < n_ids; i++) {
-    LGS_REQUIRE(ids[i] >= 0 && ids[i] < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
-    total += kf->frames[ids[i]].n;
-  }
-  LGS_REQUIRE(total < (int64_t(1) << 31), "sub-map larger than 2^31 points");
-  LGS_TRY(kf->assembled.reserve(static_cast<size_t>(std::max<int64_t>(total, 1)) * 16));
+  LGS_TRY(keyframes_assemble_into(kf, ctx, ids, n_ids, &kf->poses_dev, &kf->assembled, &total));
   *out_dev = kf->assembled.as<float>();
   *n_out = total;
-  if (total == 0) return LGS_OK;
-  cudaStream_t st = ctx->stream;
-  LGS_TRY(kf->poses_dev.reserve(static_cast<size_t>(n_ids) * 64));
-  LGS_TRY(ctx->pin_up.reserve(static_cast<size_t>(n_ids) * 64));
-  float* hp = ctx->pin_up.as<float>();
-  // the pinned staging block may still be in flight from an earlier call on this stream
-  LGS_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < n_ids; i++) memcpy(hp + 16 * i, kf->frames[ids[i]].pose, 64);
-  LGS_CUDA(cudaMemcpyAsync(kf->poses_dev.p, hp, static_cast<size_t>(n_ids) * 64, cudaMemcpyHostToDevice, st));
-  int64_t row = 0;
-  for (int s0 = 0; s0 < n_ids; s0 += kMaxSegments) {
-    SubmapSegments S;
-    S.count = std::min(kMaxSegments, n_ids - s0);
-    int acc = 0;
-    for (int s = 0; s < S.count; s++) {
-      const auto& f = kf->frames[ids[s0 + s]];
-      S.src[s] = frame_ptr(kf, f);
-      S.begin[s] = acc;
-      acc += static_cast<int>(f.n);
-    }
-    S.begin[S.count] = acc;
-    if (acc > 0) {
-      const int grid = std::max(1, std::min(grid_for(acc, 256), kNumSMs * 8));
-      submap_assemble_kernel<<<grid, 256, 0, st>>>(S, kf->poses_dev.as<float>() + 16 * s0, kf->assembled.as<float4>() + row);
-      ctx->launches++;
-      LGS_CUDA(cudaGetLastError());
-    }
-    row += acc;
-  }
-  if (leaf > 0.0f) {  // GBS:311-313: voxel_grid_.setInputCloud(nearest_key_frame_cloud); filter
+  if (leaf > 0.0f && total > 0) {  // GBS:311-313: voxel_grid_.setInputCloud(nearest_key_frame_cloud); filter
     LGS_TRY(kf->filtered.reserve(static_cast<size_t>(total) * 16));
     const float leaf3[3] = {leaf, leaf, leaf};
     lgs_voxelgrid_info info;
@@ -221,6 +243,43 @@ int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids,
     *out_dev = kf->filtered.as<float>();
     *n_out = info.n_out;
   }
+  return LGS_OK;
+}
+
+int lgs_keyframes_set_accum_distance(lgs_keyframes* kf, int32_t id, double accum_distance) {
+  LGS_REQUIRE(kf, "null argument");
+  LGS_REQUIRE(id >= 0 && id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
+  kf->frames[id].accum_distance = accum_distance;
+  return LGS_OK;
+}
+
+// detect_loop_with_accum_dist (GBS:157-187): every key frame at least accumulate_distance_threshold of path behind the
+// latest one and closer to it than search_for_candidate_threshold; *nearest = the one optimization_callback would
+// pick (GBS:263-280: strictly smallest distance, first wins), -1 if none
+int lgs_keyframes_detect_loop(lgs_keyframes* kf, int32_t latest_id, double accumulate_distance_threshold, double search_for_candidate_threshold,
+                              int32_t* candidates, int32_t capacity, int32_t* n_candidates, int32_t* nearest) {
+  LGS_REQUIRE(kf && n_candidates, "null argument");
+  LGS_REQUIRE(latest_id >= 0 && latest_id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
+  const auto& L = kf->frames[latest_id];
+  const double lp[3] = {L.pose[12], L.pose[13], L.pose[14]};
+  int32_t cnt = 0, best = -1;
+  double min_dist = std::numeric_limits<double>::max();
+  for (int32_t id = 0; id < static_cast<int32_t>(kf->frames.size()); id++) {
+    const auto& f = kf->frames[id];
+    if ((L.accum_distance - f.accum_distance) < accumulate_distance_threshold) continue;
+    const double dx = lp[0] - f.pose[12], dy = lp[1] - f.pose[13], dz = lp[2] - f.pose[14];
+    const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (dist < search_for_candidate_threshold) {
+      if (candidates && cnt < capacity) candidates[cnt] = id;
+      cnt++;
+      if (dist < min_dist) {
+        min_dist = dist;
+        best = id;
+      }
+    }
+  }
+  *n_candidates = cnt;
+  if (nearest) *nearest = best;
   return LGS_OK;
 }
 

@@ -338,6 +338,50 @@ def loop_pairs(n_pairs=8, n_keyframes=41, n_beams=64, n_azimuth=1875, scan_leaf=
     return scans, submaps, corrections
 
 
+def loop_keyframes(n_pairs=8, n_keyframes=41, n_beams=64, n_azimuth=1875, scan_leaf=0.2, key_leaf=0.2, seed=SEED, n_unique=4):
+    """cfg 4 in key-frame form (what graph_based_slam holds): `n_unique` places of `n_keyframes` consecutive key frames
+    (clouds in their own frame, key_leaf-filtered, with their true poses), then one key frame per candidate pair: a
+    scan_leaf-filtered sweep taken in the middle of a place, carrying a drifted pose (offset <= 2 m, 5 deg) the way the
+    latest key frame of the odometry does.  Returns dict(clouds, poses, scan_ids, center_ids, corrections):
+    pair i aligns key frame scan_ids[i] (transformed by its pose) to the neighbourhood of key frame center_ids[i]."""
+
+    def make():
+        w = World(seed)
+        out = {}
+        for u in range(n_unique):
+            base = 30 * u
+            for k in range(n_keyframes):
+                pose = trajectory_pose(base + k)
+                sw = drop_invalid(cast_sweep(w, pose, frame=40_000 + base + k, n_beams=n_beams, n_azimuth=n_azimuth))
+                out["kf%d_%d" % (u, k)] = numpy_voxel_downsample(sw, key_leaf)
+                out["kfpose%d_%d" % (u, k)] = pose
+            pose_s = trajectory_pose(base + n_keyframes // 2 + 0.4)
+            sw = drop_invalid(cast_sweep(w, pose_s, frame=50_000 + u, n_beams=n_beams, n_azimuth=n_azimuth))
+            out["scan%d" % u] = numpy_voxel_downsample(sw, scan_leaf)
+            out["pose%d" % u] = pose_s
+        return out
+
+    d = _cached("loop_keyframes", (n_keyframes, n_beams, n_azimuth, scan_leaf, key_leaf, seed, n_unique, 1), make)
+    clouds, poses = [], []
+    for u in range(n_unique):
+        for k in range(n_keyframes):
+            clouds.append(d["kf%d_%d" % (u, k)])
+            poses.append(d["kfpose%d_%d" % (u, k)].astype(np.float32))
+    scan_ids, center_ids, corrections = [], [], []
+    for i in range(n_pairs):
+        u = i % n_unique
+        rs = np.random.RandomState(1000 + i)
+        dxy = rs.uniform(-1, 1, 2) * 2.0 / np.sqrt(2)
+        yaw = np.radians(5.0) * rs.uniform(-1, 1)
+        off = pose_matrix(dxy[0], dxy[1], yaw, z=0.0)
+        clouds.append(d["scan%d" % u])
+        poses.append((off @ d["pose%d" % u]).astype(np.float32))
+        scan_ids.append(len(clouds) - 1)
+        center_ids.append(u * n_keyframes + n_keyframes // 2)
+        corrections.append(np.linalg.inv(off))
+    return dict(clouds=clouds, poses=poses, scan_ids=scan_ids, center_ids=center_ids, corrections=corrections)
+
+
 def rolling_map(n_points=20_000_000, seed=SEED):
     """cfg 3: a large rolling map of exactly `n_points` points: the cfg 0 local map (20 keyframes of the synthetic
     world) laid out again and again along the drive (60 m apart, alternate rows 35 m to the side, each copy with its own

@@ -784,6 +784,60 @@ def test_batch_loop_closure_icp_and_gicp_omp_methods(api, oracle):
         assert t_err < 0.1 and r_err < np.radians(0.5)
 
 
+def test_batch_loop_closure_from_keyframe_array(api, oracle):
+    """optimization_callback for a list of candidates with every cloud already in HBM (lgs_batch_align_keyframes): the
+    records are bit-identical to the host-array batch fed with the oracle's transformed / assembled clouds, for the GICP
+    and ICP methods; and detect_loop_with_accum_dist (GBS:157-187) picks the reference's candidates."""
+    from lidar_graph_slam_b200 import synth
+    K = 4
+    d = synth.loop_keyframes(n_pairs=3, n_keyframes=2 * K + 1, n_azimuth=900, n_unique=2)
+    kf = api.KeyFrameArray()
+    for c, P in zip(d["clouds"], d["poses"]):
+        kf.push(c, P)
+    n_kf = len(kf)
+    scans, submaps = [], []
+    for sid, cid in zip(d["scan_ids"], d["center_ids"]):
+        ids = [j for j in range(cid - K, cid + K + 1) if 0 <= j < n_kf]
+        scans.append(oracle.transform_point_cloud(d["clouds"][sid], d["poses"][sid]))
+        submaps.append(oracle.assemble_submap(d["clouds"], d["poses"], ids))
+    for method, kw in ((api.METHOD_GICP, {}), (api.METHOD_ICP, dict(max_correspondence_distance=30.0, transformation_epsilon=1e-8,
+                                                                      euclidean_fitness_epsilon=1e-6))):
+        a = kf.batch_align(d["scan_ids"], d["center_ids"], search_key_frame_num=K, method=method, n_workers=2, **kw)
+        b = api.batch_align(scans, submaps, method=method, n_workers=2, **kw)
+        for ra, rb in zip(a, b):
+            assert list(ra.T) == list(rb.T) and ra.fitness == rb.fitness and ra.iterations == rb.iterations and ra.converged == rb.converged
+        if method == api.METHOD_GICP:
+            for r, corr in zip(a, d["corrections"]):
+                t_err, r_err = pose_error(corr, np.array(r.T, np.float32).reshape(4, 4, order="F"))
+                assert r.converged and t_err < 0.1 and r_err < np.radians(0.5)
+    # the clipped neighbourhood at the ends of the array (GBS:299: ids outside [0, size) are skipped)
+    a = kf.batch_align([d["scan_ids"][0]], [1], search_key_frame_num=K, n_workers=1)
+    ids = [j for j in range(1 - K, 1 + K + 1) if 0 <= j < n_kf]
+    b = api.batch_align([scans[0]], [oracle.assemble_submap(d["clouds"], d["poses"], ids)], n_workers=1)
+    assert list(a[0].T) == list(b[0].T) and a[0].fitness == b[0].fitness
+    with pytest.raises(RuntimeError):
+        kf.batch_align([n_kf], [0])
+    # candidate search: key frames along a loop, 2 m apart, the latest one back near the start
+    loop = api.KeyFrameArray()
+    pts = d["clouds"][0][:100]
+    pos = [(2.0 * i, 0.0) for i in range(60)] + [(3.0, 4.0)]
+    acc = 0.0
+    for i, (x, y) in enumerate(pos):
+        if i:
+            acc += float(np.hypot(x - pos[i - 1][0], y - pos[i - 1][1]))
+        P = np.eye(4, dtype=np.float32)
+        P[:3, 3] = [x, y, 0.0]
+        loop.set_accum_distance(loop.push(pts, P), acc)
+    cand, nearest = loop.detect_loop(60, accumulate_distance_threshold=100.0, search_for_candidate_threshold=15.0)
+    dist = np.array([np.hypot(3.0 - x, 4.0 - y) for x, y in pos[:60]])
+    accd = np.concatenate([[0.0], np.cumsum(np.hypot(np.diff([p[0] for p in pos]), np.diff([p[1] for p in pos])))])
+    want = [i for i in range(61) if accd[60] - accd[i] >= 100.0 and np.hypot(3.0 - pos[i][0], 4.0 - pos[i][1]) < 15.0]
+    assert list(cand) == want and len(want) > 3
+    assert nearest == want[int(np.argmin(dist[want]))]
+    cand, nearest = loop.detect_loop(10)
+    assert len(cand) == 0 and nearest == -1
+
+
 def test_device_resident_inputs(api, oracle, velodyne_pair):
     """_dev entry points: clouds already in HBM (torch tensors) give the same results as host uploads."""
     import torch
