@@ -206,7 +206,10 @@ def loop_closure_bench(rank, world, device, pairs_per_rank):
     sizes = [len(a) + len(b) for a, b in zip(scans, submaps)]
     mine = partition_pairs(sizes, rank, world)
     my_scans, my_subs = [scans[i] for i in mine], [submaps[i] for i in mine]
-    n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", 2)
+    # concurrent pairs per GPU, each a host thread on its own stream: 4 when the box has the cores for it (1211 / 1133 / 970 /
+    # 724 pairs/s at 8 / 4 / 2 / 1 workers on one B200, tools/dev_loop_workers.sh); the workers spin on result mailboxes,
+    # so never more than the host cores per rank
+    n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", max(1, min(4, host_threads() // max(world, 1))))
     api.batch_align(my_scans[:2 * n_workers], my_subs[:2 * n_workers], n_workers=n_workers, device=device)  # warm-up: every worker allocates its device state once
     if world > 1:
         dist.barrier()
@@ -252,7 +255,7 @@ def loop_closure_bench(rank, world, device, pairs_per_rank):
         kfres = {"error": repr(e)}
     return {"pairs_per_sec": n_total / tmax.item(), "n_pairs": n_total, "converged": conv, "method": "FastGICP k=20, max_corr 2.0, submap VoxelGrid 0.5 m",
             "from_keyframe_array": kfres,
-            "gather": "all_gather of %d x 26 f32 records (%s)" % (n_total, "nccl" if world > 1 else "single rank"),
+            "gather": "all_gather of %d x 26 f32 records (%s)" % (n_total, "nccl" if world > 1 else "single rank"), "workers_per_gpu": n_workers,
             "mean_scan_pts": float(np.mean([len(s) for s in scans])), "mean_submap_pts": float(np.mean([len(s) for s in submaps]))}
 
 
