@@ -124,7 +124,7 @@ constexpr int kLinBlock = 128;
 
 template <int K>
 __device__ __forceinline__ void lin_block_reduce_and_finish(double (&acc)[K], double* __restrict__ partials, double* __restrict__ result,
-                                                           unsigned* __restrict__ counter) {
+                                                           unsigned* __restrict__ counter, const Mailbox& mb) {
   __shared__ double sm[kLinBlock / 32][K];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,12 +148,19 @@ __device__ __forceinline__ void lin_block_reduce_and_finish(double (&acc)[K], do
   __syncthreads();
   if (is_last) {
     __threadfence();
+    double v = 0;
     if (threadIdx.x < K) {
-      double v = 0;
-      for (unsigned b = 0; b < gridDim.x; b++) v += partials[static_cast<size_t>(b) * K + threadIdx.x];
+      for (unsigned b0 = 0; b0 < gridDim.x; b0 += 8) {  // eight independent loads in flight, added in block order
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = b0 + u < gridDim.x ? __ldcg(partials + static_cast<size_t>(b0 + u) * K + threadIdx.x) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) v += t[u];
+      }
       result[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *counter = 0;
+    mailbox_publish<K>(mb, v);  // the host reads the sums from mapped pinned memory: no D2H copy, no stream synchronisation
   }
 }
 
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(kLinBlock) gicp_linearize_kernel(const float4*
                                                                   LinParams P, const double* __restrict__ cov_src,
                                                                   const double* __restrict__ cov_tgt, const int* __restrict__ corr,
                                                                   double* __restrict__ mahal, int want_hb, double* __restrict__ partials,
-                                                                  double* __restrict__ result, unsigned* __restrict__ counter) {
+                                                                  double* __restrict__ result, unsigned* __restrict__ counter, const Mailbox mb) {
   double acc[43];
 #pragma unroll
   for (int k = 0; k < 43; k++) acc[k] = 0.0;
@@ -243,13 +250,13 @@ __global__ void __launch_bounds__(kLinBlock) gicp_linearize_kernel(const float4*
     else
       gicp_point_terms<false>(P, a, b, M, acc);
   }
-  lin_block_reduce_and_finish<43>(acc, partials, result, counter);
+  lin_block_reduce_and_finish<43>(acc, partials, result, counter, mb);
 }
 
 __global__ void __launch_bounds__(kLinBlock) gicp_error_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, int n, LinParams P,
                                                               const int* __restrict__ corr, const double* __restrict__ mahal,
                                                               double* __restrict__ partials, double* __restrict__ result,
-                                                              unsigned* __restrict__ counter) {
+                                                              unsigned* __restrict__ counter, const Mailbox mb) {
   double acc[1] = {0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int c = corr[i];
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(kLinBlock) gicp_error_kernel(const float4* __r
     for (int t = 0; t < 9; t++) M[t] = mahal[static_cast<size_t>(i) * 9 + t];
     gicp_point_terms<false>(P, a, b, M, acc);
   }
-  lin_block_reduce_and_finish<1>(acc, partials, result, counter);
+  lin_block_reduce_and_finish<1>(acc, partials, result, counter, mb);
 }
 
 __global__ void __launch_bounds__(256) gicp_transform_cloud_kernel(const float4* __restrict__ src, int64_t n, const float* __restrict__ Tdev,
@@ -366,16 +373,16 @@ int linearize(lgs_gicp* g, const double* T, double* cost, double* H, double* b) 
   double* result = g->result.as<double>();
   unsigned* counter = reinterpret_cast<unsigned*>(result + 44);
   const int cgrid = std::max(1, std::min(grid_for(n, kCorrBlock / 32), kNumSMs * 8));
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
   gicp_correspondence_kernel<<<cgrid, kCorrBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), n, P, g->corr.as<int>());
   gicp_linearize_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P,
                                                           g->source->covs.as<double>(), g->target->covs.as<double>(), g->corr.as<int>(),
-                                                          g->mahal.as<double>(), (H && b) ? 1 : 0, g->partials.as<double>(), result, counter);
+                                                          g->mahal.as<double>(), (H && b) ? 1 : 0, g->partials.as<double>(), result, counter, mb);
   ctx->launches += 2;
   LGS_CUDA(cudaGetLastError());
-  LGS_TRY(ctx->pin.reserve(44 * 8));
-  double* h = ctx->pin.as<double>();
-  LGS_CUDA(cudaMemcpyAsync(h, result, 43 * 8, cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
+  double h[kMailboxRecords];
+  LGS_TRY(mailbox_wait(ctx, mb, 43, h));
   *cost = h[0];
   if (H && b) {
     memcpy(b, h + 1, 6 * 8);
@@ -396,14 +403,13 @@ int compute_error(lgs_gicp* g, const double* T, double* cost) {
   fill_lin_params(g, T, &P);
   double* result = g->result.as<double>();
   unsigned* counter = reinterpret_cast<unsigned*>(result + 44);
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
   gicp_error_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P, g->corr.as<int>(),
-                                                      g->mahal.as<double>(), g->partials.as<double>(), result, counter);
+                                                      g->mahal.as<double>(), g->partials.as<double>(), result, counter, mb);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
-  LGS_TRY(ctx->pin.reserve(64));
-  LGS_CUDA(cudaMemcpyAsync(ctx->pin.p, result, 8, cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
-  *cost = ctx->pin.as<double>()[0];
+  LGS_TRY(mailbox_wait(ctx, mb, 1, cost));
   return LGS_OK;
 }
 
