@@ -354,6 +354,53 @@ class IterativeClosestPoint : public Registration {
   lgs_icp* h_ = nullptr;
 };
 
+// Device-resident key_frame_array_ (LSM:196-212, GBS:297-313): key frames are uploaded once; sub-maps are assembled on the
+// GPU and handed to a registration as device clouds; loop candidates are verified without the clouds leaving the GPU.
+class KeyFrameArray {
+ public:
+  explicit KeyFrameArray(std::shared_ptr<Context> ctx = defaultContext()) : ctx_(std::move(ctx)) {
+    if (lgs_keyframes_create(ctx_->get(), &h_) != LGS_OK) throw std::runtime_error(lgs_last_error());
+  }
+  ~KeyFrameArray() { lgs_keyframes_destroy(h_); }
+  KeyFrameArray(const KeyFrameArray&) = delete;
+  KeyFrameArray& operator=(const KeyFrameArray&) = delete;
+  // key_frame_array_.keyframes.emplace_back(key_frame): returns the key frame's id, -1 on failure
+  int push(const PointCloud& cloud, const Matrix4f& pose, double accum_distance = 0.0) {
+    int32_t id = -1;
+    if (lgs_keyframes_push(h_, cloud.data(), static_cast<int64_t>(cloud.size()), sizeof(PointXYZI), pose.data(), &id) != LGS_OK) return -1;
+    lgs_keyframes_set_accum_distance(h_, id, accum_distance);
+    return id;
+  }
+  bool setPose(int id, const Matrix4f& pose) { return lgs_keyframes_set_pose(h_, id, pose.data()) == LGS_OK; }
+  size_t size() const {
+    int64_t n = 0;
+    lgs_keyframes_size(h_, &n, nullptr);
+    return static_cast<size_t>(n);
+  }
+  // detect_loop_with_accum_dist (GBS:157-187); returns the nearest candidate (the one GBS:263-280 picks) or -1
+  int detectLoop(int latest_id, double accumulate_distance_threshold, double search_for_candidate_threshold, std::vector<int32_t>* candidates = nullptr) {
+    std::vector<int32_t> c(size() ? size() : 1);
+    int32_t n = 0, nearest = -1;
+    if (lgs_keyframes_detect_loop(h_, latest_id, accumulate_distance_threshold, search_for_candidate_threshold, c.data(), static_cast<int32_t>(c.size()), &n,
+                                  &nearest) != LGS_OK)
+      return -1;
+    if (candidates) candidates->assign(c.begin(), c.begin() + n);
+    return nearest;
+  }
+  // the sub-map of `ids` (in that order), optionally VoxelGrid-filtered: a device cloud valid until the next call
+  bool assemble(const std::vector<int32_t>& ids, float leaf, const float** cloud_dev, int64_t* n) {
+    float* p = nullptr;
+    const int rc = lgs_keyframes_assemble(h_, ids.data(), static_cast<int32_t>(ids.size()), leaf, &p, n);
+    *cloud_dev = p;
+    return rc == LGS_OK;
+  }
+  lgs_keyframes* handle() const { return h_; }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  lgs_keyframes* h_ = nullptr;
+};
+
 }  // namespace lgs
 
 #ifdef LGS_HAVE_PCL

@@ -726,6 +726,8 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
       end_session(n);
       if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return rc;
       n->session_broken = true;
+      // a grid that lost some of its CTAs to the time-out may have left the arrival counter mid-count
+      if (cudaMemsetAsync(counter, 0, sizeof(unsigned), st) != cudaSuccess) return rc;
       n->evals -= mode == 2 ? 0 : 1;
       n->hess_recomputes -= mode == 2 ? 1 : 0;
       return evaluate(n, T, p, mode, score, g, H);

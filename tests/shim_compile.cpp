@@ -58,5 +58,19 @@ int main(int argc, char** argv) {
   registration->align(aligned);
   std::printf("GICP (BFGS): converged %d, outer iterations %d, fitness %.6f\n", int(registration->hasConverged()), registration->result().iterations,
               registration->getFitnessScore());
-  return registration->hasConverged() ? 0 : 3;
+  if (!registration->hasConverged()) return 3;
+  // key-frame array: two key frames 1 m apart, sub-map on the device, handed to the registration as a device cloud
+  lgs::KeyFrameArray key_frames;
+  lgs::Matrix4f pose = lgs::Identity4f();
+  const int id0 = key_frames.push(*cloud, pose, 0.0);
+  pose[12] = 1.0f;
+  const int id1 = key_frames.push(filtered, pose, 1.0);
+  const float* map_dev = nullptr;
+  int64_t n_map = 0;
+  if (id0 != 0 || id1 != 1 || !key_frames.assemble({id1, id0}, 0.0f, &map_dev, &n_map)) return 4;
+  if (n_map != static_cast<int64_t>(cloud->size() + filtered.size())) return 5;
+  if (lgs_ndt_set_target_dev(ndt->handle(), map_dev, n_map) != LGS_OK) return 6;
+  if (key_frames.detectLoop(id1, 100.0, 15.0) != -1) return 7;  // 1 m of path: no loop yet
+  std::printf("key-frame array: %zu key frames, sub-map of %lld points resident on the GPU\n", key_frames.size(), static_cast<long long>(n_map));
+  return 0;
 }
