@@ -129,7 +129,8 @@ int lgs_cloud_from_pointcloud2(lgs_ctx* ctx, const void* data, const lgs_pc2_lay
   LGS_TRY(ctx->raw.reserve(bytes + 16));
   LGS_CUDA(cudaMemcpyAsync(ctx->raw.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
   const int smem = 2 * kTileRecs * F.point_step;
-  static int smem_set = 0;  // dynamic shared memory above 48 KB needs the opt-in attribute (largest value seen so far)
+  static int smem_set_dev[64] = {};  // dynamic shared memory above 48 KB needs the opt-in attribute, per device
+  int& smem_set = smem_set_dev[ctx->device & 63];
   if (smem > 48 * 1024 && smem > smem_set) {
     LGS_CUDA(cudaFuncSetAttribute(pc2_repack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileRecs * 256));
     smem_set = 2 * kTileRecs * 256;

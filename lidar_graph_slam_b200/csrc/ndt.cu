@@ -656,7 +656,8 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   const int ns = static_cast<int>(n->n_source);
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
-  static bool smem_opt_in = false;  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per process)
+  static bool smem_opt_in_dev[64] = {};  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per device: function attributes live in the device's context)
+  bool& smem_opt_in = smem_opt_in_dev[ctx->device & 63];
   if (!smem_opt_in) {
     const int smem = static_cast<int>(sizeof(DerivSmem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

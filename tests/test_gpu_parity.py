@@ -185,6 +185,27 @@ def test_ndt_velodyne_align_parity(api, oracle, velodyne_pair):
         _compare_align(g, o)
 
 
+def test_ndt_large_source_multi_tile(api, oracle):
+    """A 262 144-point source (cfg 1's 128-beam sweep, unfiltered): every CTA of the evaluator walks several 1024-point
+    tiles, in the persistent grid as well as with one launch per evaluation (derivatives hook)."""
+    from lidar_graph_slam_b200 import synth
+    sweep = synth.prefilter_sweeps(n_sweeps=1)[0]
+    tgt = oracle.voxel_grid(synth.drop_invalid(sweep), 0.2)["points"]
+    guess = _pose(0.25, -0.2, 0.03, 0.01)
+    g, o = _ndt_pair(api, oracle, tgt, sweep, res=1.0, eps=0.01, it=30)
+    p = np.array([0.25, -0.2, 0.03, 0.0, 0.0, 0.01])
+    T = oracle.ndt_convert_transform(p)
+    for mode in (0, 1, 2):
+        so, go, Ho = o.derivatives(T, p, mode)
+        sg, gg, Hg = g.derivatives(T, p, mode)
+        if mode != 2:
+            assert sg == pytest.approx(so, rel=1e-12)
+            np.testing.assert_allclose(gg, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+        if mode != 1:
+            np.testing.assert_allclose(np.triu(Hg), np.triu(Ho), rtol=1e-9, atol=1e-10 * np.abs(Ho).max())
+    _compare_align(g, o, guess)
+
+
 def test_ndt_cfg0_synthetic_scan_to_map(api, oracle):
     """BASELINE configs[0]: 120 000-point 64-beam sweep against a 1 000 000-point local map, DIRECT7, 1.0 m."""
     from lidar_graph_slam_b200 import synth
