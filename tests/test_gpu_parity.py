@@ -859,6 +859,43 @@ def test_batch_loop_closure_from_keyframe_array(api, oracle):
     assert len(cand) == 0 and nearest == -1
 
 
+def test_loop_closure_cfg4_full_size_properties(api):
+    """BASELINE configs[4] at its full size: 4096 (scan, 41-key-frame sub-map) candidates verified from the device
+    key-frame array.  The oracle needs seconds per pair, so this checks size-independent properties: every candidate
+    that passes the node's fitness gate sits on its known correction (and at least 99 % pass), and a record does not depend on the worker count, on the order of the batch, or
+    on the shard (rank) it is dealt to - bit for bit."""
+    from lidar_graph_slam_b200 import synth
+    from lidar_graph_slam_b200.distributed import partition_pairs
+    n_pairs = 4096
+    d = synth.loop_keyframes(n_pairs=n_pairs, n_keyframes=41, n_azimuth=900, n_unique=2)
+    kf = api.KeyFrameArray()
+    for c, P in zip(d["clouds"], d["poses"]):
+        kf.push(c, P)
+    assert len(kf) == 2 * 41 + n_pairs
+    recs = kf.batch_align(d["scan_ids"], d["center_ids"], search_key_frame_num=20, n_workers=4)
+    assert [r.pair_id for r in recs] == list(range(n_pairs))
+    assert all(r.converged for r in recs)
+    # GBS:328 accepts a candidate iff it converged and fitness <= score_threshold_ (0.3, graph_based_slam.param.yaml:6).
+    # Every accepted candidate sits on its known correction (no false loop closure); the few that GICP drags into a wrong
+    # basin from a 2 m / 5 deg offset have a fitness ten times the threshold and are rejected.
+    accepted = 0
+    for r, corr in zip(recs, d["corrections"]):
+        t_err, r_err = pose_error(corr, np.array(r.T, np.float32).reshape(4, 4, order="F"))
+        if r.fitness <= 0.3:
+            accepted += 1
+            assert t_err < 0.1 and r_err < np.radians(0.5)
+        else:
+            assert t_err > 0.5 and r.fitness > 1.0
+    assert accepted >= 0.99 * n_pairs
+    # shard 3 of 8 (what rank 3 of an 8-GPU job verifies), shuffled, one worker: the same records
+    mine = partition_pairs([1] * n_pairs, 3, 8)[:48]
+    rng = np.random.default_rng(2)
+    order = [mine[i] for i in rng.permutation(len(mine))]
+    sub = kf.batch_align([d["scan_ids"][i] for i in order], [d["center_ids"][i] for i in order], search_key_frame_num=20, n_workers=1)
+    for r, i in zip(sub, order):
+        assert list(r.T) == list(recs[i].T) and r.fitness == recs[i].fitness and r.iterations == recs[i].iterations
+
+
 def test_device_resident_inputs(api, oracle, velodyne_pair):
     """_dev entry points: clouds already in HBM (torch tensors) give the same results as host uploads."""
     import torch
