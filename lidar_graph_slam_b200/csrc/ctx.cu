@@ -1,7 +1,9 @@
 // Context, error reporting and cloud upload (host AoS records -> packed float4 xyzi in HBM).
 #include <atomic>
 
-#include "common.cuh"
+#include <cstdlib>
+
+#include "persist.cuh"
 
 namespace lgs {
 
@@ -55,6 +57,33 @@ int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst) 
   LGS_TRY(dst->reserve(static_cast<size_t>(n > 0 ? n : 1) * 16));
   if (n) LGS_CUDA(cudaMemcpyAsync(dst->p, pts_dev, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToDevice, ctx->stream));
   return LGS_OK;
+}
+
+// ---- persistent evaluators (persist.cuh) ----------------------------------------------------------------------------
+static std::atomic<int> g_persist_owner[64];
+
+bool persist_try_acquire(int device) {
+  if (device < 0 || device >= 64) return false;
+  int expected = 0;
+  return g_persist_owner[device].compare_exchange_strong(expected, 1, std::memory_order_acquire);
+}
+void persist_release(int device) {
+  if (device >= 0 && device < 64) g_persist_owner[device].store(0, std::memory_order_release);
+}
+
+// LGS_NDT_PERSISTENT=0 turns the resident grids off, =1 forces them on.  By default they are off under an injected
+// CUDA tool (Nsight Compute serialises kernels and blocks the host inside the launch call until the kernel has
+// finished - a grid that waits for a host command would only end by its time-out).
+bool persist_env_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LGS_NDT_PERSISTENT");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    for (const char* v : {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"})
+      if (getenv(v)) return false;
+    return true;
+  }();
+  return on;
 }
 
 int mailbox_next(lgs_ctx* ctx, Mailbox* mb) {

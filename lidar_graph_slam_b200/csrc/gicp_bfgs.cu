@@ -23,6 +23,7 @@
 
 #include "fixsum.cuh"
 #include "gicp.cuh"
+#include "persist.cuh"
 
 namespace lgs {
 
@@ -129,16 +130,29 @@ __device__ __forceinline__ void fun_reduce_and_publish(Fix128 (&acc)[K], Fix128*
   if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   __syncthreads();
   if (is_last) {
+    // integer sums: any order gives the same bits, so the per-CTA rows are added by eight groups of threads in parallel
     __threadfence();
+    __shared__ Fix128 fin[kFunBlock / 16][16];
+    static_assert(K <= 16, "one 16-thread group per slice of the rows");
+    const int kk = threadIdx.x & 15, part = threadIdx.x >> 4;
     Fix128 v = fix_zero();
-    if (threadIdx.x < K)
-      for (unsigned b = 0; b < gridDim.x; b++) {
-        const volatile Fix128* p = partials + static_cast<size_t>(b) * K + threadIdx.x;
-        Fix128 t;
-        t.lo = p->lo;
-        t.hi = p->hi;
-        fix_add(v, t);
+    if (kk < K) {
+#pragma unroll 4
+      for (unsigned b = part; b < gridDim.x; b += kFunBlock / 16) {
+        const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(partials + static_cast<size_t>(b) * K + kk));
+        Fix128 u;
+        u.lo = t.x;
+        u.hi = static_cast<long long>(t.y);
+        fix_add(v, u);
       }
+    }
+    fin[part][kk] = v;
+    __syncthreads();
+    v = fix_zero();
+    if (threadIdx.x < K) {
+#pragma unroll
+      for (int p = 0; p < kFunBlock / 16; p++) fix_add(v, fin[p][threadIdx.x]);
+    }
     if (threadIdx.x == 0) *counter = 0;
     mailbox_publish<K>(mb, fix_value(v));
   }
@@ -180,9 +194,9 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_mahalanobis_kernel(int n, Pgi
 // MODE 2: fdf (GO:333-367)                          sums: f, g_t[3], R[9]
 // base_transformation_ is the identity (GO:394), so base_transformation_ * p_src is p_src itself.
 template <int MODE>
-__global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* __restrict__ out_cloud, const float4* __restrict__ tgt, int n,
-                                                                 PgicpParams P, const int* __restrict__ corr, const float* __restrict__ mahal,
-                                                                 Fix128* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox mb) {
+__device__ __forceinline__ void pgicp_functor_body(const float4* __restrict__ out_cloud, const float4* __restrict__ tgt, int n, const float* __restrict__ T,
+                                                   const int* __restrict__ corr, const float* __restrict__ mahal, Fix128* __restrict__ partials,
+                                                   unsigned* __restrict__ counter, const Mailbox& mb) {
   constexpr int K = MODE == 0 ? 1 : (MODE == 1 ? 12 : 13);
   Fix128 acc[K];
 #pragma unroll
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* 
 #pragma unroll
     for (int t = 0; t < 9; t++) M[t] = mahal[static_cast<size_t>(i) * 9 + t];
     float px, py, pz;
-    mul4f_point(P.T, a, px, py, pz);
+    mul4f_point(T, a, px, py, pz);
     const float r0 = __fsub_rn(px, b.x), r1 = __fsub_rn(py, b.y), r2 = __fsub_rn(pz, b.z);
     if (MODE == 0) {
       const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(M[0], r0), __fmul_rn(M[1], r1)), __fmul_rn(M[2], r2));
@@ -223,6 +237,55 @@ __global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* 
     }
   }
   fun_reduce_and_publish<K>(acc, partials, counter, mb);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kFunBlock) pgicp_functor_kernel(const float4* __restrict__ out_cloud, const float4* __restrict__ tgt, int n,
+                                                                 const __grid_constant__ PgicpParams P, const int* __restrict__ corr,
+                                                                 const float* __restrict__ mahal, Fix128* __restrict__ partials,
+                                                                 unsigned* __restrict__ counter, const __grid_constant__ Mailbox mb) {
+  pgicp_functor_body<MODE>(out_cloud, tgt, n, P.T, corr, mahal, partials, counter, mb);
+}
+
+// Persistent functor evaluator: BFGS asks for ~50 cost / gradient evaluations per outer iteration and needs each answer
+// before it can choose the next step, so the grid stays resident between update_correspondences calls and receives
+// {T, mode, mailbox token} per evaluation through the command channel of persist.cuh (one launch + ~13 us of launch
+// latency per evaluation otherwise, for ~10 us of work on a 30 000-point cloud).
+struct PgicpPose {
+  float T[16];
+  int mode;  // 0: operator(), 1: df, 2: fdf, < 0: end of the run
+  int pad;
+  unsigned long long token;
+};
+constexpr int kPgWords = static_cast<int>(sizeof(PgicpPose) / 8);
+static_assert(sizeof(PgicpPose) % 8 == 0, "commands are copied as 64-bit words");
+using PgicpCmdHost = CmdHost<kPgWords>;
+using PgicpCmdDev = CmdDev<kPgWords>;
+constexpr int kFunResident = 4;  // CTAs of the persistent grid per SM (all of them must be co-resident)
+
+__global__ void __launch_bounds__(kFunBlock, kFunResident) pgicp_persistent_kernel(const float4* __restrict__ out_cloud, const float4* __restrict__ tgt, int n,
+                                                                                  const int* __restrict__ corr, const float* __restrict__ mahal,
+                                                                                  Fix128* __restrict__ partials, unsigned* __restrict__ counter,
+                                                                                  MailboxRecord* mailbox, const PgicpCmdHost* __restrict__ cmd_host,
+                                                                                  PgicpCmdDev* __restrict__ cmd_dev, unsigned long long first_seq) {
+  __shared__ __align__(16) PgicpPose pose;
+  __shared__ int give_up;
+  if (threadIdx.x == 0) give_up = 0;
+  __syncthreads();
+  for (unsigned long long seq = first_seq;; seq++) {
+    if (!persist_receive<kPgWords, kFunBlock>(cmd_host, cmd_dev, seq, reinterpret_cast<unsigned long long*>(&pose), &give_up)) return;
+    if (pose.mode < 0) return;
+    Mailbox mb;
+    mb.r = mailbox;
+    mb.token = pose.token;
+    if (pose.mode == 0)
+      pgicp_functor_body<0>(out_cloud, tgt, n, pose.T, corr, mahal, partials, counter, mb);
+    else if (pose.mode == 1)
+      pgicp_functor_body<1>(out_cloud, tgt, n, pose.T, corr, mahal, partials, counter, mb);
+    else
+      pgicp_functor_body<2>(out_cloud, tgt, n, pose.T, corr, mahal, partials, counter, mb);
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) pgicp_transform_kernel(const float4* __restrict__ src, int64_t n, PgicpParams P, float4* __restrict__ out) {
@@ -252,6 +315,12 @@ struct lgs_gicp_omp {
   float base_T[16], T[16], prev_T[16], final_T[16], guess[16];
   int n_corr = 0;
   int f_calls = 0, df_calls = 0, fdf_calls = 0, inner_total = 0;
+  // persistent functor evaluator (between two update_correspondences calls of one align)
+  bool allow_session = false, session_active = false, session_broken = false;
+  int session_device = -1;
+  PgicpCmdHost* cmd_host = nullptr;  // mapped pinned memory
+  DevBuf cmd_dev;
+  unsigned long long cmd_seq = 0;
 };
 
 namespace {
@@ -319,7 +388,33 @@ void r_derivative(const double* x, const double* R, double* g) {
   }
 }
 
-int fun_grid(int64_t n) { return std::max(1, std::min(grid_for(n, kFunBlock), kNumSMs * 4)); }
+// one row of partial sums per CTA goes through the last-CTA pass: no more CTAs than SMs (a 30 000-point cloud is 1.6 points per thread)
+int fun_grid(int64_t n) { return std::max(1, std::min(grid_for(n, kFunBlock), kNumSMs)); }
+
+void end_session(lgs_gicp_omp* g) {
+  if (!g->session_active) return;
+  PgicpPose quit;
+  memset(&quit, 0, sizeof(quit));
+  quit.mode = -1;
+  persist_send<kPgWords>(g->cmd_host, ++g->cmd_seq, &quit);
+  g->session_active = false;
+  persist_release(g->session_device);
+}
+
+// everything the session needs that may allocate or synchronise, before the grid becomes resident
+int prepare_session(lgs_gicp_omp* g) {
+  if (!g->cmd_host) {
+    void* p = nullptr;
+    LGS_CUDA(cudaHostAlloc(&p, sizeof(PgicpCmdHost), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, sizeof(PgicpCmdHost));
+    g->cmd_host = static_cast<PgicpCmdHost*>(p);
+  }
+  if (!g->cmd_dev.p) {
+    LGS_TRY(g->cmd_dev.reserve(sizeof(PgicpCmdDev)));
+    LGS_CUDA(cudaMemsetAsync(g->cmd_dev.p, 0, sizeof(PgicpCmdDev), g->ctx->stream));
+  }
+  return LGS_OK;
+}
 
 // one functor evaluation on the device: mode 0 -> f; 1 -> g; 2 -> f and g
 int functor_eval(lgs_gicp_omp* g, const double* x, int mode, double* f, double* grad) {
@@ -336,17 +431,56 @@ int functor_eval(lgs_gicp_omp* g, const double* x, int mode, double* f, double* 
   const float4* out = g->output.as<float4>();
   const float4* tgt = g->target->pts.as<float4>();
   const int grid = fun_grid(n);
-  if (mode == 0)
-    pgicp_functor_kernel<0><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
-  else if (mode == 1)
-    pgicp_functor_kernel<1><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
-  else
-    pgicp_functor_kernel<2><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
-  ctx->launches++;
-  LGS_CUDA(cudaGetLastError());
   double h[kMailboxRecords];
   const int K = mode == 0 ? 1 : (mode == 1 ? 12 : 13);
-  LGS_TRY(mailbox_wait(ctx, mb, K, h));
+  const bool want_session = g->allow_session && !g->session_broken && persist_env_enabled() && grid <= kNumSMs * kFunResident;
+  if (!want_session) end_session(g);
+  if (want_session && !g->session_active) {
+    LGS_TRY(prepare_session(g));
+    if (persist_try_acquire(ctx->device)) {
+      void* dv = nullptr;
+      LGS_CUDA(cudaHostGetDevicePointer(&dv, g->cmd_host, 0));
+      pgicp_persistent_kernel<<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb.r,
+                                                                 static_cast<const PgicpCmdHost*>(dv), g->cmd_dev.as<PgicpCmdDev>(), g->cmd_seq + 1);
+      ctx->launches++;
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) {
+        persist_release(ctx->device);
+        set_error("pgicp_persistent_kernel launch failed: %s", cudaGetErrorString(le));
+        return LGS_ERR_CUDA;
+      }
+      g->session_active = true;
+      g->session_device = ctx->device;
+    }
+  }
+  if (g->session_active) {
+    PgicpPose pose;
+    memcpy(pose.T, P.T, sizeof(pose.T));
+    pose.mode = mode;
+    pose.pad = 0;
+    pose.token = mb.token;
+    persist_send<kPgWords>(g->cmd_host, ++g->cmd_seq, &pose);
+    const int rc = mailbox_wait(ctx, mb, K, h);
+    if (rc != LGS_OK) {
+      // the grid gave up (command time-out): if the stream is healthy, go on with one launch per evaluation
+      end_session(g);
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return rc;
+      g->session_broken = true;
+      if (cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) return rc;
+      (mode == 0 ? g->f_calls : mode == 1 ? g->df_calls : g->fdf_calls)--;
+      return functor_eval(g, x, mode, f, grad);
+    }
+  } else {
+    if (mode == 0)
+      pgicp_functor_kernel<0><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
+    else if (mode == 1)
+      pgicp_functor_kernel<1><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
+    else
+      pgicp_functor_kernel<2><<<grid, kFunBlock, 0, ctx->stream>>>(out, tgt, n, P, g->corr.as<int>(), g->mahal.as<float>(), partials, counter, mb);
+    ctx->launches++;
+    LGS_CUDA(cudaGetLastError());
+    LGS_TRY(mailbox_wait(ctx, mb, K, h));
+  }
   const int m = g->n_corr;
   if (mode != 1) *f = h[0] / static_cast<double>(m);
   if (mode != 0) {
@@ -721,6 +855,7 @@ int transform_source(lgs_gicp_omp* g, const float* T, float4* dst) {
 
 // the correspondence / Mahalanobis half of one outer iteration (GO:404-474); sets g->n_corr
 int update_correspondences(lgs_gicp_omp* g) {
+  end_session(g);  // the correspondence / Mahalanobis kernels need the SMs; the next functor call opens a new run
   lgs_ctx* ctx = g->ctx;
   PgicpParams P;
   memcpy(P.T, g->T, sizeof(P.T));
@@ -775,8 +910,11 @@ int lgs_gicp_omp_create(lgs_ctx* ctx, lgs_gicp_omp** out) {
 
 void lgs_gicp_omp_destroy(lgs_gicp_omp* g) {
   if (!g) return;
+  end_session(g);
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
+  if (g->cmd_host) cudaFreeHost(g->cmd_host);
+  g->cmd_dev.release();
   g->source.reset();
   g->target.reset();
   for (DevBuf* b : {&g->output, &g->corr, &g->mahal, &g->partials, &g->state, &g->out_cloud}) b->release();
@@ -813,8 +951,18 @@ int lgs_gicp_omp_set_target_dev(lgs_gicp_omp* g, const float* pts_dev, int64_t n
 }
 
 // pcl::Registration::align + computeTransformation (GO:370-516)
+static int gicp_omp_align_body(lgs_gicp_omp* g, const float* guess16, lgs_align_result* res, float* out_cloud);
+
 int lgs_gicp_omp_align(lgs_gicp_omp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
   LGS_REQUIRE(g && res, "null argument");
+  g->allow_session = true;
+  const int rc = gicp_omp_align_body(g, guess16, res, out_cloud);
+  end_session(g);  // every exit path releases the resident grid
+  g->allow_session = false;
+  return rc;
+}
+
+static int gicp_omp_align_body(lgs_gicp_omp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
   memset(res, 0, sizeof(*res));
   LGS_TRY(use_device(g->ctx));
   LGS_TRY(ensure_ready(g));
@@ -844,6 +992,7 @@ int lgs_gicp_omp_align(lgs_gicp_omp* g, const float* guess16, lgs_align_result* 
       memcpy(g->prev_T, g->T, sizeof(g->T));
     }
   }
+  end_session(g);
   mul4f(g->prev_T, g->guess, g->final_T);  // GO:512
   memcpy(res->T, g->final_T, sizeof(g->final_T));
   res->iterations = nr_iterations;

@@ -230,6 +230,7 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double
 
 }  // namespace lgs
 
+#include "persist.cuh"
 #include "ndt_deriv.cuh"
 
 namespace lgs {
@@ -569,37 +570,8 @@ int build_grid(lgs_ndt* n) {
   return LGS_OK;
 }
 
-// ---- persistent evaluator sessions -------------------------------------------------------------------------------
-// Two resident grids that each need every SM would wait for one another's SMs forever, so at most one session per
-// device exists in the process (batch workers that lose the race simply launch per evaluation).
-std::atomic<int> g_session_owner[64];
-
-// LGS_NDT_PERSISTENT=0 turns the resident grid off.  It is also off under an injected CUDA tool (Nsight Compute
-// serialises kernels and blocks the host inside the launch call until the kernel has finished - a grid that waits
-// for a host command would only end by its time-out).
-bool session_env_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("LGS_NDT_PERSISTENT");
-    if (e && e[0] == '0') return false;
-    if (e && e[0] == '1') return true;
-    for (const char* v : {"CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"})
-      if (getenv(v)) return false;
-    return true;
-  }();
-  return on;
-}
-
-// host side of the command protocol (ndt_deriv.cuh): payload word first, sequence word second, chunk by chunk
-void send_command(lgs_ndt* n, const NdtPose& pose) {
-  const unsigned long long seq = ++n->cmd_seq;
-  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&pose);
-  volatile NdtCommandChunk* c = n->cmd_host->c;
-  for (int i = 0; i < kCmdWords; i++) {
-    c[i].data = w[i];
-    std::atomic_thread_fence(std::memory_order_release);
-    c[i].seq = seq;
-  }
-}
+// ---- persistent evaluator sessions (channel and the one-session-per-device rule: persist.cuh) ---------------------
+void send_command(lgs_ndt* n, const NdtPose& pose) { persist_send<kCmdWords>(n->cmd_host, ++n->cmd_seq, &pose); }
 
 void end_session(lgs_ndt* n) {
   if (!n->session_active) return;
@@ -608,7 +580,7 @@ void end_session(lgs_ndt* n) {
   quit.mode = -1;
   send_command(n, quit);
   n->session_active = false;
-  g_session_owner[n->session_device].store(0, std::memory_order_release);
+  persist_release(n->session_device);
 }
 
 // everything a session needs that may allocate or synchronise happens here, before the grid becomes resident
@@ -671,12 +643,11 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     smem_opt_in = true;
   }
   // ---- persistent evaluator: every evaluation of an align, full-size grids only
-  const bool want_session = n->allow_session && !n->profiling && !n->session_broken && session_env_enabled() && ns >= 32 * kNumSMs && ctx->device < 64;
+  const bool want_session = n->allow_session && !n->profiling && !n->session_broken && persist_env_enabled() && ns >= 32 * kNumSMs;
   if (!want_session) end_session(n);
   if (want_session && !n->session_active) {
     LGS_TRY(prepare_session(n));
-    int expected = 0;
-    if (g_session_owner[ctx->device].compare_exchange_strong(expected, 1, std::memory_order_acquire)) {
+    if (persist_try_acquire(ctx->device)) {
       void* dv = nullptr;
       LGS_CUDA(cudaHostGetDevicePointer(&dv, n->cmd_host, 0));
       const u64 one2 = 0x3f8000003f800000ull;
@@ -695,7 +666,7 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
       n->session_launches++;
       cudaError_t le = cudaGetLastError();
       if (le != cudaSuccess) {
-        g_session_owner[ctx->device].store(0, std::memory_order_release);
+        persist_release(ctx->device);
         set_error("ndt_persistent_kernel launch failed: %s", cudaGetErrorString(le));
         return LGS_ERR_CUDA;
       }
