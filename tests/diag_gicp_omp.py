@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Development aid (GPU box): pclomp-GICP parity diagnostics on the synthetic loop pairs: covariances, one functor
+"""Diagnostic (test infrastructure: compares against the oracle, hence lives under tests/).  pclomp-GICP parity diagnostics on the synthetic loop pairs: covariances, one functor
 set-up, and the BFGS call counts of a whole align, GPU vs oracle."""
 import os
 import sys

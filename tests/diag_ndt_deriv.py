@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Development loop for the NDT evaluation kernels on the cfg0 workload (run on the GPU box):
+"""Diagnostic (test infrastructure: compares against the oracle, hence lives under tests/).  Development loop for the NDT evaluation kernels on the cfg0 workload (run on the GPU box):
 parity of one evaluation per mode against the oracle, per-kernel CUDA-event timings, then a full align parity check.
 
-    python tools/dev_ndt_deriv.py [--no-oracle] [--reps 50]
+    python tests/diag_ndt_deriv.py [--no-oracle] [--reps 50]
 """
 import argparse
 import os
