@@ -365,12 +365,14 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_sources_never_touch_the_oracle():
-    pkg = os.path.join(ROOT, "lidar_graph_slam_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
-                src = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "pyoracle" not in src and "liblgs_oracle" not in src and "oracle/" not in src, f
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load the oracle: the package, the public headers and
+    the tools must not mention it."""
+    for top in ("lidar_graph_slam_b200", "include", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", ".sh")):
+                    src = open(os.path.join(dirpath, f), errors="replace").read()
+                    assert "pyoracle" not in src and "liblgs_oracle" not in src and "oracle/" not in src and "from oracle" not in src, f
 
 
 def test_synth_is_deterministic_and_shaped():
