@@ -18,6 +18,7 @@
 
 #include "math.cuh"
 #include "nn.cuh"
+#include "persist.cuh"
 
 namespace lgs {
 
@@ -30,8 +31,8 @@ struct IcpParams {
   double max_dist2;
 };
 
-__global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(NNView tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int n, IcpParams P, double* __restrict__ partials,
-                                                            unsigned* __restrict__ counter, const Mailbox mb) {
+__device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int n, const IcpParams& P,
+                                              double* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox& mb) {
   __shared__ double sm[kIcpBlock / 32][kIcpSums];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -93,6 +94,54 @@ __global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(NNView tv, const fl
   }
 }
 
+__global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(const __grid_constant__ NNView tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int n,
+                                                            const __grid_constant__ IcpParams P, double* __restrict__ partials,
+                                                            unsigned* __restrict__ counter, const __grid_constant__ Mailbox mb) {
+  icp_step_body(tv, tgt, cloud, n, P, partials, counter, mb);
+}
+
+// Persistent form: the grid stays resident for the iterations of one align and receives {transformation_, mailbox token}
+// per iteration through the command channel of persist.cuh (the host needs the 17 sums of an iteration before it can
+// estimate the next transformation).
+struct IcpPose {
+  float T[16];
+  int apply;  // < 0: end of the run
+  int pad;
+  unsigned long long token;
+};
+constexpr int kIcpWords = static_cast<int>(sizeof(IcpPose) / 8);
+static_assert(sizeof(IcpPose) % 8 == 0, "commands are copied as 64-bit words");
+using IcpCmdHost = CmdHost<kIcpWords>;
+using IcpCmdDev = CmdDev<kIcpWords>;
+constexpr int kIcpResident = 4;  // CTAs per SM of the persistent grid (all co-resident)
+
+__global__ void __launch_bounds__(kIcpBlock, kIcpResident) icp_persistent_kernel(const __grid_constant__ NNView tv, const float4* __restrict__ tgt,
+                                                                                float4* __restrict__ cloud, int n, double max_dist2,
+                                                                                double* __restrict__ partials, unsigned* __restrict__ counter,
+                                                                                MailboxRecord* mailbox, const IcpCmdHost* __restrict__ cmd_host,
+                                                                                IcpCmdDev* __restrict__ cmd_dev, unsigned long long first_seq) {
+  __shared__ __align__(16) IcpPose pose;
+  __shared__ IcpParams P;
+  __shared__ int give_up;
+  if (threadIdx.x == 0) give_up = 0;
+  __syncthreads();
+  for (unsigned long long seq = first_seq;; seq++) {
+    if (!persist_receive<kIcpWords, kIcpBlock>(cmd_host, cmd_dev, seq, reinterpret_cast<unsigned long long*>(&pose), &give_up)) return;
+    if (pose.apply < 0) return;
+    if (threadIdx.x < 16) P.T[threadIdx.x] = pose.T[threadIdx.x];
+    if (threadIdx.x == 0) {
+      P.apply = pose.apply;
+      P.max_dist2 = max_dist2;
+    }
+    __syncthreads();
+    Mailbox mb;
+    mb.r = mailbox;
+    mb.token = pose.token;
+    icp_step_body(tv, tgt, cloud, n, P, partials, counter, mb);
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) icp_transform_kernel(const float4* __restrict__ src, int64_t n, IcpParams P, float4* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
@@ -121,6 +170,12 @@ struct lgs_icp {
   int convergence_state = 0;
   double last_mse = 0;
   int64_t last_correspondences = 0;
+  // persistent evaluator (inside lgs_icp_align only)
+  bool allow_session = false, session_active = false, session_broken = false;
+  int session_device = -1;
+  IcpCmdHost* cmd_host = nullptr;  // mapped pinned memory
+  DevBuf cmd_dev;
+  unsigned long long cmd_seq = 0;
 };
 
 namespace {
@@ -214,6 +269,30 @@ int ensure_ready(lgs_icp* g) {
   return LGS_OK;
 }
 
+void end_session(lgs_icp* g) {
+  if (!g->session_active) return;
+  IcpPose quit;
+  memset(&quit, 0, sizeof(quit));
+  quit.apply = -1;
+  persist_send<kIcpWords>(g->cmd_host, ++g->cmd_seq, &quit);
+  g->session_active = false;
+  persist_release(g->session_device);
+}
+
+int prepare_session(lgs_icp* g) {  // whatever allocates or synchronises, before the grid becomes resident
+  if (!g->cmd_host) {
+    void* p = nullptr;
+    LGS_CUDA(cudaHostAlloc(&p, sizeof(IcpCmdHost), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(p, 0, sizeof(IcpCmdHost));
+    g->cmd_host = static_cast<IcpCmdHost*>(p);
+  }
+  if (!g->cmd_dev.p) {
+    LGS_TRY(g->cmd_dev.reserve(sizeof(IcpCmdDev)));
+    LGS_CUDA(cudaMemsetAsync(g->cmd_dev.p, 0, sizeof(IcpCmdDev), g->ctx->stream));
+  }
+  return LGS_OK;
+}
+
 // transforms the working cloud by T (unless null) and returns the 17 sums of the correspondences found after it
 int step(lgs_icp* g, const float* T, double* sums) {
   lgs_ctx* ctx = g->ctx;
@@ -223,8 +302,50 @@ int step(lgs_icp* g, const float* T, double* sums) {
   P.max_dist2 = g->corr_dist_threshold * g->corr_dist_threshold;
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
-  icp_step_kernel<<<step_grid(g->n_source), kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), static_cast<int>(g->n_source), P, g->partials.as<double>(),
-                                                                        g->state.as<unsigned>(), mb);
+  const int grid = step_grid(g->n_source);
+  const int n = static_cast<int>(g->n_source);
+  const bool want_session = g->allow_session && !g->session_broken && persist_env_enabled() && grid <= kNumSMs * kIcpResident;
+  if (!want_session) end_session(g);
+  if (want_session && !g->session_active) {
+    LGS_TRY(prepare_session(g));
+    if (persist_try_acquire(ctx->device)) {
+      void* dv = nullptr;
+      LGS_CUDA(cudaHostGetDevicePointer(&dv, g->cmd_host, 0));
+      icp_persistent_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), n, P.max_dist2,
+                                                               g->partials.as<double>(), g->state.as<unsigned>(), mb.r, static_cast<const IcpCmdHost*>(dv),
+                                                               g->cmd_dev.as<IcpCmdDev>(), g->cmd_seq + 1);
+      ctx->launches++;
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) {
+        persist_release(ctx->device);
+        set_error("icp_persistent_kernel launch failed: %s", cudaGetErrorString(le));
+        return LGS_ERR_CUDA;
+      }
+      g->session_active = true;
+      g->session_device = ctx->device;
+    }
+  }
+  if (g->session_active) {
+    IcpPose pose;
+    memcpy(pose.T, P.T, sizeof(pose.T));
+    pose.apply = P.apply;
+    pose.pad = 0;
+    pose.token = mb.token;
+    persist_send<kIcpWords>(g->cmd_host, ++g->cmd_seq, &pose);
+    const int rc = mailbox_wait(ctx, mb, kIcpSums, sums);
+    if (rc == LGS_OK) return LGS_OK;
+    // The grid gave up (command time-out).  It may have transformed part of the working cloud already, so this align
+    // cannot be continued with plain launches: report it; the next align starts from the source cloud with plain launches.
+    end_session(g);
+    if (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess) {
+      g->session_broken = true;
+      cudaMemsetAsync(g->state.p, 0, sizeof(unsigned), ctx->stream);
+      set_error("IterativeClosestPoint: the resident evaluator timed out waiting for the host; call align again (plain launches from now on)");
+    }
+    return rc;
+  }
+  icp_step_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), n, P, g->partials.as<double>(),
+                                                      g->state.as<unsigned>(), mb);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   return mailbox_wait(ctx, mb, kIcpSums, sums);
@@ -254,8 +375,11 @@ int lgs_icp_create(lgs_ctx* ctx, lgs_icp** out) {
 
 void lgs_icp_destroy(lgs_icp* g) {
   if (!g) return;
+  end_session(g);
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
+  if (g->cmd_host) cudaFreeHost(g->cmd_host);
+  g->cmd_dev.release();
   for (DevBuf* b : {&g->source, &g->target, &g->target_copy, &g->cloud, &g->partials, &g->state, &g->out_cloud}) b->release();
   g->nn.release();
   delete g;
@@ -287,8 +411,23 @@ int lgs_icp_set_target_dev(lgs_icp* g, const float* pts_dev, int64_t n) {
 }
 
 // pcl::Registration::align + IterativeClosestPoint::computeTransformation
+static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* res, float* out_cloud);
+
 int lgs_icp_align(lgs_icp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
   LGS_REQUIRE(g && res, "null argument");
+  g->allow_session = true;
+  int rc = icp_align_body(g, guess16, res, out_cloud);
+  end_session(g);  // every exit path releases the resident grid
+  if (rc != LGS_OK && g->session_broken && g->allow_session) {
+    // the resident grid timed out mid-align (see step()): run the whole align again with plain launches
+    g->allow_session = false;
+    rc = icp_align_body(g, guess16, res, out_cloud);
+  }
+  g->allow_session = false;
+  return rc;
+}
+
+static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
   memset(res, 0, sizeof(*res));
   LGS_TRY(use_device(g->ctx));
   LGS_TRY(ensure_ready(g));
@@ -328,6 +467,7 @@ int lgs_icp_align(lgs_icp* g, const float* guess16, lgs_align_result* res, float
     g->last_mse = sums[1] / sums[0];
     converged = crit.check(nr_iterations, T, g->last_mse);
   } while (crit.state == kNotConverged);
+  end_session(g);
   g->convergence_state = crit.state;
   memcpy(res->T, g->final_T, sizeof(g->final_T));
   res->iterations = nr_iterations;
