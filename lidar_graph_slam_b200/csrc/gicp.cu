@@ -147,7 +147,7 @@ __device__ __forceinline__ void lin_block_reduce_and_finish(double (&acc)[K], do
   if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   __syncthreads();
   if (is_last) {
-    // two groups of 64 threads add the even / odd per-block rows in block order (eight loads in flight each), then the
+    // two groups of 64 threads add the even / odd per-block rows in block order (sixteen loads in flight each), then the
     // two halves are added: a fixed function of the grid size, so the sums are reproducible run to run
     __threadfence();
     static_assert(K <= 64 && kLinBlock == 128, "two groups of 64 threads");
@@ -155,12 +155,12 @@ __device__ __forceinline__ void lin_block_reduce_and_finish(double (&acc)[K], do
     const int kk = threadIdx.x & 63, grp = threadIdx.x >> 6;
     double v = 0;
     if (kk < K) {
-      for (unsigned b0 = grp; b0 < gridDim.x; b0 += 16) {
-        double t[8];
+      for (unsigned b0 = grp; b0 < gridDim.x; b0 += 32) {  // sixteen loads in flight per round: the pass is L2-latency bound
+        double t[16];
 #pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = b0 + 2 * u < gridDim.x ? __ldcg(partials + static_cast<size_t>(b0 + 2 * u) * K + kk) : 0.0;
+        for (int u = 0; u < 16; u++) t[u] = b0 + 2 * u < gridDim.x ? __ldcg(partials + static_cast<size_t>(b0 + 2 * u) * K + kk) : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) v += t[u];
+        for (int u = 0; u < 16; u++) v += t[u];
       }
     }
     if (grp == 1 && kk < K) half[kk] = v;
