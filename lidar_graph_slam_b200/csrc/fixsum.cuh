@@ -4,7 +4,8 @@
 // decomposition of the work over threads, warps, CTAs and GPUs - unlike the reference's per-thread partial sums
 // (gicp_omp_impl.hpp:251,274,291-314), whose low bits depend on the OpenMP thread count.  The BFGS line search of
 // the PCL-style GICP compares cost values that differ by less than the rounding noise of a 30 000-term f64 sum;
-// with exact sums its trajectory is reproducible.  Range: |term| < 2^46 (larger, inf or NaN poisons the sum -> NaN).
+// with exact sums its trajectory is reproducible.  Range: |term| < 2^46 (larger, inf or NaN poisons the sum -> NaN) and |sum| < 2^47 (not checked: the cost terms are
+// below 2^14 and there are fewer than 2^22 of them).
 #pragma once
 #include <cstdint>
 

@@ -3,7 +3,8 @@
 // not depend on the order of the terms.  The reference's own order is unspecified (per-thread partial sums added
 // in thread order, gicp_omp_impl.hpp:251,274,291-314: the low bits change with the OpenMP thread count), and its
 // BFGS line search compares costs closer than the rounding noise of a plain f64 sum; an exact sum is the one
-// statement of "the sum" that every implementation can reproduce bit for bit.  Range |term| < 2^46, else NaN.
+// statement of "the sum" that every implementation can reproduce bit for bit.  Range |term| < 2^46, else NaN; |sum| < 2^47 (not checked: the
+// cost terms are below 2^14 and there are fewer than 2^22 of them).
 #pragma once
 #include <cmath>
 #include <cstdint>

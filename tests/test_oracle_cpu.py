@@ -340,6 +340,17 @@ def test_fitness_definition(oracle, velodyne_pair):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def test_exact_sums_product_equals_oracle(tmp_path):
+    """The order-independent accumulators of the product (csrc/fixsum.cuh, host path) and of the oracle (exactsum.hpp) are
+    the same function of the terms, whatever their order or grouping into partial sums: the pclomp-GICP functor sums
+    (and with them BFGS's path) agree bit for bit because of this."""
+    import subprocess
+    exe = str(tmp_path / "fixsum_check")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "fixsum_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout[-2000:]
+
+
 def test_c_abi_exports_every_declared_symbol():
     """liblgs_b200.so loads on a CPU-only box and exports exactly what include/lgs_c.h declares."""
     from lidar_graph_slam_b200 import _lib
