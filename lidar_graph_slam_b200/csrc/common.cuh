@@ -180,6 +180,12 @@ __device__ __forceinline__ void mailbox_publish(const Mailbox& mb, double v) {
   }
 }
 
+// one value into record `slot` by the calling thread alone (single-thread finishers: look-back scans, atomic accumulators)
+__device__ __forceinline__ void mailbox_publish_one(const Mailbox& mb, int slot, double v) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mb.r + slot), "l"(bits), "l"(mb.token) : "memory");
+}
+
 __device__ __forceinline__ float3 transform_pcl(const float* __restrict__ T, float x, float y, float z) {
   float3 r;
   r.x = __fadd_rn(__fmul_rn(T[0], x), __fadd_rn(__fmul_rn(T[4], y), __fadd_rn(__fmul_rn(T[8], z), T[12])));

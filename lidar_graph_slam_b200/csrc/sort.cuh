@@ -74,7 +74,7 @@ constexpr int kScanTile = kSortThreads * kScanItems;
 
 template <class F>
 __global__ void __launch_bounds__(kSortThreads) scan_select_kernel(F f, int64_t n, u64_t* __restrict__ status, unsigned* __restrict__ ticket,
-                                                                  int* __restrict__ total_out) {
+                                                                  int* __restrict__ total_out, const Mailbox mb) {
   __shared__ unsigned scan32[kSortWarps + 1];
   __shared__ unsigned tile_s;
   __shared__ u64_t excl_s;
@@ -112,7 +112,10 @@ __global__ void __launch_bounds__(kSortThreads) scan_select_kernel(F f, int64_t 
       st_status(status + tile, flag_pre | (excl + tile_n));
     }
     excl_s = excl;
-    if (static_cast<int64_t>(tile + 1) * kScanTile >= n && total_out) *total_out = static_cast<int>(excl + tile_n);
+    if (static_cast<int64_t>(tile + 1) * kScanTile >= n) {  // the last tile knows the total
+      if (total_out) *total_out = static_cast<int>(excl + tile_n);
+      if (mb.r) mailbox_publish_one(mb, 0, static_cast<double>(excl + tile_n));  // the host gets it without a copy + synchronise
+    }
   }
   __syncthreads();
   int64_t pos = static_cast<int64_t>(excl_s) + local;
@@ -135,16 +138,20 @@ int radix_sort_pairs(lgs_ctx* ctx, unsigned* keys, unsigned* vals, unsigned* key
 // reserves and zeroes the look-back scratch for one scan_select launch over n elements
 int scan_select_prepare(lgs_ctx* ctx, int64_t n, u64_t** status, unsigned** ticket);
 
+// mb (optional): a mailbox the total is published to as well; ask for it only with n > 0
 template <class F>
-int scan_select(lgs_ctx* ctx, const F& f, int64_t n, int* total_out_dev) {
+int scan_select(lgs_ctx* ctx, const F& f, int64_t n, int* total_out_dev, const Mailbox* mb = nullptr) {
   if (n <= 0) {
     if (total_out_dev) LGS_CUDA(cudaMemsetAsync(total_out_dev, 0, sizeof(int), ctx->stream));
     return LGS_OK;
   }
+  Mailbox none;
+  none.r = nullptr;
+  none.token = 0;
   u64_t* status;
   unsigned* ticket;
   LGS_TRY(scan_select_prepare(ctx, n, &status, &ticket));
-  scan_select_kernel<F><<<grid_for(n, kScanTile), kSortThreads, 0, ctx->stream>>>(f, n, status, ticket, total_out_dev);
+  scan_select_kernel<F><<<grid_for(n, kScanTile), kSortThreads, 0, ctx->stream>>>(f, n, status, ticket, total_out_dev, mb ? *mb : none);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   return LGS_OK;

@@ -27,7 +27,10 @@ struct BBoxAcc {  // device-side accumulator
   unsigned mn[3];
   unsigned mx[3];
   unsigned long long kept;
+  unsigned done;  // CTAs that have merged their part
+  unsigned pad;
 };
+static_assert(sizeof(BBoxAcc) <= 48, "the segment count lives 48 bytes into the same scratch block");
 
 __global__ void bbox_init_kernel(BBoxAcc* acc) {
   if (threadIdx.x == 0) {
@@ -36,6 +39,7 @@ __global__ void bbox_init_kernel(BBoxAcc* acc) {
       acc->mx[a] = 0u;
     }
     acc->kept = 0ull;
+    acc->done = 0u;
   }
 }
 
@@ -55,7 +59,7 @@ __device__ __forceinline__ bool crop_keep(const float4& p, const CropParams& cp)
 
 // grid-stride, float4 loads; per-thread min/max -> warp shuffle -> one atomic set per block
 __global__ void __launch_bounds__(256) crop_bbox_kernel(const float4* __restrict__ pts, int64_t n, CropParams cp, unsigned char* __restrict__ keep,
-                                                       BBoxAcc* __restrict__ acc) {
+                                                       BBoxAcc* __restrict__ acc, const Mailbox mb) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   unsigned cnt = 0;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -102,6 +106,17 @@ __global__ void __launch_bounds__(256) crop_bbox_kernel(const float4* __restrict
         atomicMax(&acc->mx[a], enc_f(mx[a]));
       }
       atomicAdd(&acc->kept, static_cast<unsigned long long>(total));
+    }
+    // the last CTA to arrive sends the finished box and count to the host mailbox (no D2H copy + stream synchronise)
+    __threadfence();
+    if (atomicAdd(&acc->done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      volatile BBoxAcc* va = acc;
+      for (int a = 0; a < 3; a++) {
+        mailbox_publish_one(mb, a, static_cast<double>(va->mn[a]));
+        mailbox_publish_one(mb, 3 + a, static_cast<double>(va->mx[a]));
+      }
+      mailbox_publish_one(mb, 6, static_cast<double>(va->kept));
     }
   }
 }
@@ -223,11 +238,20 @@ int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float 
 
   bbox_init_kernel<<<1, 32, 0, st>>>(acc);
   int blocks = std::min(grid_for(n, 256), kNumSMs * 8);
-  crop_bbox_kernel<<<blocks, 256, 0, st>>>(pts, n, cp, keep, acc);
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
+  crop_bbox_kernel<<<blocks, 256, 0, st>>>(pts, n, cp, keep, acc, mb);
   ctx->launches += 2;
-  BBoxAcc* hacc = ctx->pin.as<BBoxAcc>();
-  LGS_CUDA(cudaMemcpyAsync(hacc, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
+  LGS_CUDA(cudaGetLastError());
+  double hbox[kMailboxRecords];
+  LGS_TRY(mailbox_wait(ctx, mb, 7, hbox));
+  BBoxAcc hacc_v;
+  BBoxAcc* hacc = &hacc_v;
+  for (int a = 0; a < 3; a++) {
+    hacc->mn[a] = static_cast<unsigned>(hbox[a]);
+    hacc->mx[a] = static_cast<unsigned>(hbox[3 + a]);
+  }
+  hacc->kept = static_cast<unsigned long long>(hbox[6]);
 
   const int64_t n_kept = static_cast<int64_t>(hacc->kept);
   out->n_kept = n_kept;
@@ -283,11 +307,12 @@ int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float 
   LGS_TRY(ctx->tmp[5].reserve(static_cast<size_t>(n_kept) * 4 + 64));
   int* seg_start = ctx->tmp[5].as<int>();
   int* d_nseg = reinterpret_cast<int*>(reinterpret_cast<char*>(acc) + 48);
-  LGS_TRY(scan_select(ctx, SegmentHeads{out->keys, seg_start}, n_kept, d_nseg));
-  int* h_small = ctx->pin.as<int>() + 32;
-  LGS_CUDA(cudaMemcpyAsync(h_small, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
-  out->n_seg = h_small[0];
+  Mailbox mb2;
+  LGS_TRY(mailbox_next(ctx, &mb2));
+  LGS_TRY(scan_select(ctx, SegmentHeads{out->keys, seg_start}, n_kept, d_nseg, &mb2));  // n_kept > 0 here
+  double nseg = 0;
+  LGS_TRY(mailbox_wait(ctx, mb2, 1, &nseg));
+  out->n_seg = static_cast<int>(nseg);
   out->seg_start = seg_start;
   return LGS_OK;
 }
