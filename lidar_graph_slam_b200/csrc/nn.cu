@@ -172,11 +172,15 @@ constexpr int kFitWarps = kFitBlock / 32;
 
 // one warp per source point; lane 0 of every warp accumulates its points in index order, warps and blocks are
 // combined in a fixed order: reproducible sums
-__global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const float4* __restrict__ src, int n, const float* __restrict__ Tdev,
+struct FitTransform {
+  float m[16];  // column-major
+};
+
+__global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const float4* __restrict__ src, int n, const FitTransform Tp,
                                                               double max_range, double* __restrict__ partials, double* __restrict__ result,
-                                                              unsigned* __restrict__ counter) {
+                                                              unsigned* __restrict__ counter, const Mailbox mb) {
   __shared__ float T[16];
-  if (threadIdx.x < 16) T[threadIdx.x] = Tdev[threadIdx.x];
+  if (threadIdx.x < 16) T[threadIdx.x] = Tp.m[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double sum = 0.0, cnt = 0.0;
@@ -226,6 +230,8 @@ __global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const f
       result[0] = s;
       result[1] = c;
       *counter = 0;
+      mailbox_publish_one(mb, 0, s);  // the host reads sum and count from mapped pinned memory: no D2H copy, no synchronise
+      mailbox_publish_one(mb, 1, c);
     }
   }
 }
@@ -239,19 +245,17 @@ int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_
   double* partials = ctx->tmp[0].as<double>();
   double* result = partials + 2 * grid;
   unsigned* counter = reinterpret_cast<unsigned*>(result + 2);
-  float* Tdev = reinterpret_cast<float*>(result + 4);
-  LGS_TRY(ctx->pin_up.reserve(64));
-  memcpy(ctx->pin_up.p, T16, 64);
+  FitTransform Tp;
+  memcpy(Tp.m, T16, sizeof(Tp.m));
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
   LGS_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-  LGS_CUDA(cudaMemcpyAsync(Tdev, ctx->pin_up.p, 64, cudaMemcpyHostToDevice, st));
-  nn_fitness_kernel<<<grid, kFitBlock, 0, st>>>(index.view(), src, static_cast<int>(n_src), Tdev, max_range, partials, result, counter);
+  nn_fitness_kernel<<<grid, kFitBlock, 0, st>>>(index.view(), src, static_cast<int>(n_src), Tp, max_range, partials, result, counter, mb);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
-  LGS_TRY(ctx->pin.reserve(64));
-  LGS_CUDA(cudaMemcpyAsync(ctx->pin.p, result, 16, cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
-  const double s = ctx->pin.as<double>()[0], c = ctx->pin.as<double>()[1];
-  if (c > 0) *fitness = s / c;
+  double h[2];
+  LGS_TRY(mailbox_wait(ctx, mb, 2, h));
+  if (h[1] > 0) *fitness = h[0] / h[1];
   return LGS_OK;
 }
 
