@@ -256,6 +256,19 @@ class FastGICP : public Registration {
     check(lgs_gicp_fitness(h_, max_range, &f));
     return f;
   }
+  // FG.h:60-70: covariances as n x 9 doubles (row-major 3x3 blocks of the reference's Matrix4d)
+  void setSourceCovariances(const std::vector<double>& covs) { check(lgs_gicp_set_covariances(h_, 0, covs.data(), static_cast<int64_t>(covs.size() / 9))); }
+  void setTargetCovariances(const std::vector<double>& covs) { check(lgs_gicp_set_covariances(h_, 1, covs.data(), static_cast<int64_t>(covs.size() / 9))); }
+  std::vector<double> getSourceCovariances() {
+    std::vector<double> c(n_source_ * 9);
+    if (n_source_) check(lgs_gicp_export_covariances(h_, 0, c.data()));
+    return c;
+  }
+  std::vector<double> getTargetCovariances() {
+    std::vector<double> c(n_target_ * 9);
+    if (n_target_) check(lgs_gicp_export_covariances(h_, 1, c.data()));
+    return c;
+  }
   std::array<double, 36> getFinalHessian() {
     std::array<double, 36> H{};
     check(lgs_gicp_final_hessian(h_, H.data()));

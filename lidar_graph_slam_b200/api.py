@@ -428,6 +428,15 @@ class FastGICP(_Registration):
         check(self._L.lgs_gicp_export_covariances(self._h, int(which), c.ctypes.data_as(C.c_void_p)))
         return c.reshape(n, 3, 3)
 
+    def _set_covariances(self, which, covs):
+        c = np.ascontiguousarray(np.asarray(covs, np.float64).reshape(-1, 9))
+        check(self._L.lgs_gicp_set_covariances(self._h, which, c.ctypes.data_as(C.c_void_p), c.shape[0]))
+
+    def setSourceCovariances(self, covs): self._set_covariances(0, covs)
+    def setTargetCovariances(self, covs): self._set_covariances(1, covs)
+    def getSourceCovariances(self): return self.covariances(0)
+    def getTargetCovariances(self): return self.covariances(1)
+
     def linearize(self, T):
         Tr = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4))
         cost = C.c_double()

@@ -92,7 +92,7 @@ int GicpCloud::ensure_index(lgs_ctx* ctx) {
 }
 
 int GicpCloud::ensure_covariances(lgs_ctx* ctx, int k, int regularization) {
-  if (covs_ready && covs_k == k && covs_reg == regularization) return LGS_OK;
+  if (covs_ready && (covs_user || (covs_k == k && covs_reg == regularization))) return LGS_OK;
   LGS_REQUIRE(k >= 1 && k <= kMaxK, "k_correspondences must be in [1, 32]");
   LGS_TRY(ensure_index(ctx));
   LGS_TRY(covs.reserve(static_cast<size_t>(n > 0 ? n : 1) * 72));
@@ -106,6 +106,7 @@ int GicpCloud::ensure_covariances(lgs_ctx* ctx, int k, int regularization) {
     LGS_CUDA(cudaGetLastError());
   }
   covs_ready = true;
+  covs_user = false;
   covs_k = k;
   covs_reg = regularization;
   return LGS_OK;
@@ -488,6 +489,7 @@ int set_cloud(lgs_gicp* g, std::shared_ptr<GicpCloud>* slot, const void* pts, co
     c = *slot;
     c->nn_ready = false;
     c->covs_ready = false;
+    c->covs_user = false;
   } else {
     c = std::make_shared<GicpCloud>();
   }
@@ -650,6 +652,24 @@ int lgs_gicp_export_covariances(lgs_gicp* g, int32_t which, double* covs) {
     LGS_CUDA(cudaMemcpyAsync(covs, c->covs.p, static_cast<size_t>(c->n) * 72, cudaMemcpyDeviceToHost, g->ctx->stream));
     LGS_CUDA(cudaStreamSynchronize(g->ctx->stream));
   }
+  return LGS_OK;
+}
+
+// setSourceCovariances / setTargetCovariances (FG:93-101): the vector is taken as it is; as in computeTransformation
+// (FG:104-109) it is used only when its size equals the cloud's, otherwise the covariances are computed at align time
+int lgs_gicp_set_covariances(lgs_gicp* g, int32_t which, const double* covs, int64_t n) {
+  LGS_REQUIRE(g && (covs || n == 0), "null argument");
+  std::shared_ptr<GicpCloud> c = which == 0 ? g->source : g->target;
+  if (!c || n != c->n || n == 0) {
+    if (c) c->covs_ready = c->covs_user = false;
+    return LGS_OK;
+  }
+  LGS_TRY(use_device(g->ctx));
+  LGS_TRY(c->covs.reserve(static_cast<size_t>(n) * 72));
+  LGS_CUDA(cudaMemcpyAsync(c->covs.p, covs, static_cast<size_t>(n) * 72, cudaMemcpyHostToDevice, g->ctx->stream));
+  LGS_CUDA(cudaStreamSynchronize(g->ctx->stream));  // the caller's buffer is pageable and may go away
+  c->covs_ready = true;
+  c->covs_user = true;
   return LGS_OK;
 }
 

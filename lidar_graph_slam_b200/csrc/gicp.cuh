@@ -17,6 +17,7 @@ struct GicpCloud {
   DevBuf covs;  // n x 9 f64, row-major 3x3 block of the reference's Matrix4d
   bool covs_ready = false;
   int covs_k = 0, covs_reg = -1;
+  bool covs_user = false;  // supplied through set*Covariances (FG:93-101): used as they are
   int ensure_index(lgs_ctx* ctx);
   int ensure_covariances(lgs_ctx* ctx, int k, int regularization);
   ~GicpCloud() {

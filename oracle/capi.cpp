@@ -162,6 +162,13 @@ void orc_gicp_covariances(void* h, int which, double* covs) {
   if (c.covs.size() != c.pts.size() * 9) g->calculate_covariances(c);
   std::memcpy(covs, c.covs.data(), c.covs.size() * sizeof(double));
 }
+// setSourceCovariances / setTargetCovariances (FG:93-101): taken as they are; align recomputes them only when the
+// size differs from the cloud's (FG:104-109)
+void orc_gicp_set_covariances(void* h, int which, const double* covs, long n) {
+  FastGICP* g = static_cast<FastGICP*>(h);
+  Cloud& c = which == 0 ? *g->source : *g->target;
+  c.covs.assign(covs, covs + static_cast<size_t>(n) * 9);
+}
 // linearize at a row-major f64 transform: returns cost, fills H/b and (optionally) correspondences
 double orc_gicp_linearize(void* h, const double* T16_rowmajor, double* H36, double* b6, int* corr) {
   FastGICP* g = static_cast<FastGICP*>(h);

@@ -70,6 +70,7 @@ def lib():
         L.orc_gicp_fitness.argtypes = [vp, C.c_double]
         L.orc_gicp_final_hessian.argtypes = [vp, vp]
         L.orc_gicp_covariances.argtypes = [vp, C.c_int, vp]
+        L.orc_gicp_set_covariances.argtypes = [vp, C.c_int, vp, C.c_long]
         L.orc_gicp_linearize.restype = C.c_double
         L.orc_gicp_linearize.argtypes = [vp, vp, vp, vp, vp]
         L.orc_pgicp_create.restype = vp
@@ -317,6 +318,13 @@ class FastGICP:
         c = np.empty((n, 9))
         self._L.orc_gicp_covariances(self._h, int(which), _p(c))
         return c.reshape(n, 3, 3)
+
+    def _set_covariances(self, which, covs):
+        c = np.ascontiguousarray(np.asarray(covs, np.float64).reshape(-1, 9))
+        self._L.orc_gicp_set_covariances(self._h, which, _p(c), c.shape[0])
+
+    def setSourceCovariances(self, covs): self._set_covariances(0, covs)
+    def setTargetCovariances(self, covs): self._set_covariances(1, covs)
 
     def linearize(self, T):
         Tr = np.ascontiguousarray(np.asarray(T, np.float64))

@@ -387,6 +387,47 @@ def test_gicp_covariances_and_linearize(api, oracle, velodyne_pair):
         np.testing.assert_allclose(cg_, co_, rtol=1e-6, atol=1e-7 * np.abs(co_).max())
 
 
+def test_gicp_set_covariances(api, oracle, velodyne_pair):
+    """setSourceCovariances / setTargetCovariances (fast_gicp.hpp:60-70, FG:93-109): supplied covariances are used as they
+    are when their count matches the cloud, recomputed otherwise, and dropped by the next setInputSource."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g, o = _gicp_pair(api, oracle, t2, s2)
+    # covariances of another regularisation, computed by the oracle, handed to both
+    alt = oracle.FastGICP()
+    alt.setRegularizationMethod(oracle.REG_MIN_EIG)
+    alt.setInputSource(s2)
+    alt.setInputTarget(t2)
+    cs, ct = alt.covariances(0), alt.covariances(1)
+    for x in (g, o):
+        x.setSourceCovariances(cs)
+        x.setTargetCovariances(ct)
+    assert np.array_equal(g.getSourceCovariances(), cs) and np.array_equal(g.getTargetCovariances(), ct)
+    _compare_gicp_align(g, o)
+    plane = api.FastGICP()
+    plane.setInputTarget(t2)
+    plane.setInputSource(s2)
+    plane.align()
+    assert not np.array_equal(plane.getFinalTransformation(), g.getFinalTransformation())  # the supplied covariances mattered
+    # wrong size: ignored, computed at align time (FG:104-109); a new cloud drops them (FG:72-90)
+    g.setSourceCovariances(cs[:100])
+    g.align()
+    assert np.array_equal(g.getFinalTransformation(), _gicp_target_user_source_plane(api, t2, s2, ct))
+    g.setInputSource(s2)
+    g.setInputTarget(t2)
+    g.align()
+    assert np.array_equal(g.getFinalTransformation(), plane.getFinalTransformation())
+
+
+def _gicp_target_user_source_plane(api, t2, s2, ct):
+    x = api.FastGICP()
+    x.setInputTarget(t2)
+    x.setInputSource(s2)
+    x.setTargetCovariances(ct)
+    x.align()
+    return x.getFinalTransformation()
+
+
 def test_gicp_velodyne_align_parity(api, oracle, velodyne_pair):
     """fast_gicp gtest recipe (gicp_test.cpp:55-65,147-201) + the four set/swap orderings."""
     t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
