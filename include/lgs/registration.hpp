@@ -256,6 +256,12 @@ class FastGICP : public Registration {
     check(lgs_gicp_fitness(h_, max_range, &f));
     return f;
   }
+  void setDebugPrint(bool) {}  // lsq_registration.hpp:36
+  double evaluateCost(const Matrix4f& relative_pose) {  // LSQ:48-50
+    double c = 0;
+    check(lgs_gicp_evaluate_cost(h_, relative_pose.data(), &c));
+    return c;
+  }
   // FG.h:60-70: covariances as n x 9 doubles (row-major 3x3 blocks of the reference's Matrix4d)
   void setSourceCovariances(const std::vector<double>& covs) { check(lgs_gicp_set_covariances(h_, 0, covs.data(), static_cast<int64_t>(covs.size() / 9))); }
   void setTargetCovariances(const std::vector<double>& covs) { check(lgs_gicp_set_covariances(h_, 1, covs.data(), static_cast<int64_t>(covs.size() / 9))); }

@@ -244,6 +244,9 @@ int lgs_gicp_fitness(lgs_gicp* g, double max_range, double* fitness);
 int lgs_gicp_final_hessian(lgs_gicp* g, double* H36);                   /* LSQ:43-45 getFinalHessian */
 /* parity hooks: which = 0 source, 1 target; covs = n x 9 f64 row-major (computed on demand, FG:241-298) */
 int lgs_gicp_export_covariances(lgs_gicp* g, int32_t which, double* covs);
+/* evaluateCost (LSQ.h:58, LSQ:48-50): the GICP cost at a pose (column-major f32 4x4) over the correspondences of the
+ * last linearisation; LGS_ERR_STATE before the first align / linearize */
+int lgs_gicp_evaluate_cost(lgs_gicp* g, const float* T16, double* cost);
 /* setSourceCovariances / setTargetCovariances (FG.h:60-62, FG:93-101): n x 9 f64 row-major 3x3 blocks; used at align
  * time only if n equals the cloud's size (FG:104-109), and dropped by the next setInputSource / setInputTarget */
 int lgs_gicp_set_covariances(lgs_gicp* g, int32_t which, const double* covs, int64_t n);

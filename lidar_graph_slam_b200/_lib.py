@@ -107,6 +107,7 @@ SYMBOLS = {
     "lgs_gicp_fitness": (_i32, [_vp, _f64, C.POINTER(_f64)]),
     "lgs_gicp_final_hessian": (_i32, [_vp, _vp]),
     "lgs_gicp_export_covariances": (_i32, [_vp, _i32, _vp]),
+    "lgs_gicp_evaluate_cost": (_i32, [_vp, _vp, C.POINTER(_f64)]),
     "lgs_gicp_set_covariances": (_i32, [_vp, _i32, _vp, _i64]),
     "lgs_gicp_linearize": (_i32, [_vp, _vp, C.POINTER(_f64), _vp, _vp, _vp]),
     "lgs_gicp_omp_create": (_i32, [_vp, C.POINTER(_vp)]),

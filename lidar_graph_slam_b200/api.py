@@ -428,6 +428,15 @@ class FastGICP(_Registration):
         check(self._L.lgs_gicp_export_covariances(self._h, int(which), c.ctypes.data_as(C.c_void_p)))
         return c.reshape(n, 3, 3)
 
+    def setDebugPrint(self, flag): pass  # lsq_registration.hpp:36: console output of the LM steps; nothing to print here
+
+    def evaluateCost(self, relative_pose):
+        """LsqRegistration::evaluateCost (LSQ:48-50): cost at a pose over the correspondences of the last linearisation."""
+        keep, tp = _mat_to_c(relative_pose)
+        cost = C.c_double()
+        check(self._L.lgs_gicp_evaluate_cost(self._h, tp, C.byref(cost)))
+        return cost.value
+
     def _set_covariances(self, which, covs):
         c = np.ascontiguousarray(np.asarray(covs, np.float64).reshape(-1, 9))
         check(self._L.lgs_gicp_set_covariances(self._h, which, c.ctypes.data_as(C.c_void_p), c.shape[0]))

@@ -655,6 +655,24 @@ int lgs_gicp_export_covariances(lgs_gicp* g, int32_t which, double* covs) {
   return LGS_OK;
 }
 
+// evaluateCost (LSQ:48-50): compute_error at the given pose with the correspondences and Mahalanobis matrices of the
+// last linearisation (FG:214-237 reads them as they are)
+int lgs_gicp_evaluate_cost(lgs_gicp* g, const float* T16, double* cost) {
+  LGS_REQUIRE(g && T16 && cost, "null argument");
+  if (!g->source || !g->target || g->linearize_calls == 0) {
+    set_error("lgs_gicp_evaluate_cost: no linearisation yet (call align or lgs_gicp_linearize first)");
+    return LGS_ERR_STATE;
+  }
+  LGS_TRY(use_device(g->ctx));
+  double T[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) T[r * 4 + c] = static_cast<double>(T16[c * 4 + r]);  // Isometry3d(relative_pose.cast<double>())
+  const int keep = g->error_calls;
+  const int rc = compute_error(g, T, cost);
+  g->error_calls = keep;
+  return rc;
+}
+
 // setSourceCovariances / setTargetCovariances (FG:93-101): the vector is taken as it is; as in computeTransformation
 // (FG:104-109) it is used only when its size equals the cloud's, otherwise the covariances are computed at align time
 int lgs_gicp_set_covariances(lgs_gicp* g, int32_t which, const double* covs, int64_t n) {

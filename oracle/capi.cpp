@@ -162,6 +162,17 @@ void orc_gicp_covariances(void* h, int which, double* covs) {
   if (c.covs.size() != c.pts.size() * 9) g->calculate_covariances(c);
   std::memcpy(covs, c.covs.data(), c.covs.size() * sizeof(double));
 }
+// evaluateCost (LSQ:48-50): compute_error at Isometry3d(relative_pose.cast<double>()), column-major f32 in
+double orc_gicp_evaluate_cost(void* h, const float* T16) {
+  FastGICP* g = static_cast<FastGICP*>(h);
+  double T[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) T[r * 4 + c] = static_cast<double>(T16[c * 4 + r]);
+  const int keep = g->error_calls;
+  const double v = g->compute_error(T);
+  g->error_calls = keep;
+  return v;
+}
 // setSourceCovariances / setTargetCovariances (FG:93-101): taken as they are; align recomputes them only when the
 // size differs from the cloud's (FG:104-109)
 void orc_gicp_set_covariances(void* h, int which, const double* covs, long n) {

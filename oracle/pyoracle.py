@@ -70,6 +70,8 @@ def lib():
         L.orc_gicp_fitness.argtypes = [vp, C.c_double]
         L.orc_gicp_final_hessian.argtypes = [vp, vp]
         L.orc_gicp_covariances.argtypes = [vp, C.c_int, vp]
+        L.orc_gicp_evaluate_cost.restype = C.c_double
+        L.orc_gicp_evaluate_cost.argtypes = [vp, vp]
         L.orc_gicp_set_covariances.argtypes = [vp, C.c_int, vp, C.c_long]
         L.orc_gicp_linearize.restype = C.c_double
         L.orc_gicp_linearize.argtypes = [vp, vp, vp, vp, vp]
@@ -318,6 +320,10 @@ class FastGICP:
         c = np.empty((n, 9))
         self._L.orc_gicp_covariances(self._h, int(which), _p(c))
         return c.reshape(n, 3, 3)
+
+    def evaluateCost(self, relative_pose):
+        Tc = np.asarray(relative_pose, np.float32).ravel(order="F").copy()
+        return self._L.orc_gicp_evaluate_cost(self._h, _p(Tc))
 
     def _set_covariances(self, which, covs):
         c = np.ascontiguousarray(np.asarray(covs, np.float64).reshape(-1, 9))

@@ -404,6 +404,14 @@ def test_gicp_set_covariances(api, oracle, velodyne_pair):
         x.setTargetCovariances(ct)
     assert np.array_equal(g.getSourceCovariances(), cs) and np.array_equal(g.getTargetCovariances(), ct)
     _compare_gicp_align(g, o)
+    # evaluateCost (LSQ:48-50) at the solution and next to it, over the correspondences of the last linearisation
+    for dx in (0.0, 0.05):
+        T = g.getFinalTransformation().copy()
+        T[0, 3] += dx
+        assert g.evaluateCost(T) == pytest.approx(o.evaluateCost(T), rel=1e-10)
+    assert g.evaluateCost(T) > g.evaluateCost(g.getFinalTransformation())
+    with pytest.raises(RuntimeError):
+        api.FastGICP().evaluateCost(np.eye(4))
     plane = api.FastGICP()
     plane.setInputTarget(t2)
     plane.setInputSource(s2)
