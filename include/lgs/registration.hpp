@@ -202,6 +202,11 @@ class NormalDistributionsTransform : public Registration {
     check(lgs_ndt_fitness(h_, max_range, &f));
     return f;
   }
+  static Matrix4f convertTransform(const std::array<double, 6>& x) {  // NDT.h:214-238
+    Matrix4f T = Identity4f();
+    lgs_ndt_convert_transform(x.data(), T.data());
+    return T;
+  }
   double getTransformationProbability() const { return result_.trans_probability; }
   int getFinalNumIteration() const { return result_.iterations; }
   double calculateScore(const Matrix4f& T) {

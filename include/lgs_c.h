@@ -209,6 +209,8 @@ int lgs_ndt_derivatives(lgs_ndt* ndt, const float* T16, const double* p6, int32_
  * call, then enables (1) / disables (0) per-launch timing of the evaluation kernels.  out8 = {launches, ms} for
  * computeDerivatives with Hessian, gradient-only, and the f64 computeHessian kernel, then the number of accepted
  * (point, voxel) terms of the last evaluation and the source size.  out8 may be NULL. */
+/* static convertTransform(x, trans) (NDT.h:214-238): (x, y, z, roll, pitch, yaw) -> column-major f32 4x4.  Host only. */
+int lgs_ndt_convert_transform(const double* x6, float* T16);
 int lgs_ndt_profile(lgs_ndt* ndt, int32_t enable, double* out8);
 
 /* ------------------------------------------------------------------------------------------- */

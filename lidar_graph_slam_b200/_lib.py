@@ -86,6 +86,7 @@ SYMBOLS = {
     "lgs_ndt_grid_info_get": (_i32, [_vp, C.POINTER(NdtGridInfo)]),
     "lgs_ndt_export_voxels": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lgs_ndt_derivatives": (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_f64), _vp, _vp]),
+    "lgs_ndt_convert_transform": (_i32, [_vp, _vp]),
     "lgs_ndt_profile": (_i32, [_vp, _i32, _vp]),
     "lgs_gicp_create": (_i32, [_vp, C.POINTER(_vp)]),
     "lgs_gicp_destroy": (None, [_vp]),

@@ -346,6 +346,14 @@ class NormalDistributionsTransform(_Registration):
     def setNeighborhoodSearchMethod(self, m): check(self._L.lgs_ndt_set_search_method(self._h, int(m)))
     def setNumThreads(self, n): pass  # OpenMP knob of the reference (NDT.h:113-115); meaningless on the GPU
 
+    @staticmethod
+    def convertTransform(x):
+        """static convertTransform (NDT.h:214-238): (x, y, z, roll, pitch, yaw) -> 4x4 float32."""
+        x = np.ascontiguousarray(x, np.float64)
+        T = np.empty(16, np.float32)
+        check(_lib.load().lgs_ndt_convert_transform(x.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p)))
+        return T.reshape(4, 4, order="F").copy()
+
     def getTransformationProbability(self): return self.result.trans_probability
     def getFinalNumIteration(self): return int(self.result.iterations)
 

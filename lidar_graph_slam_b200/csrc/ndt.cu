@@ -1175,6 +1175,14 @@ int lgs_ndt_debug_trace(lgs_ndt* n, double* out, int32_t n_cta) {
 }
 #endif
 
+// static convertTransform (NDT.h:214-238): Translation(x, y, z) * AngleAxis(roll, X) * AngleAxis(pitch, Y) * AngleAxis(yaw, Z)
+// in f32, as the optimiser builds its poses.  Pure host arithmetic: needs no device.
+int lgs_ndt_convert_transform(const double* x6, float* T16) {
+  LGS_REQUIRE(x6 && T16, "null argument");
+  pose_to_matrix(x6, T16);
+  return LGS_OK;
+}
+
 int lgs_ndt_derivatives(lgs_ndt* n, const float* T16, const double* p6, int32_t mode, double* score, double* g6, double* H36) {
   LGS_REQUIRE(n && T16 && p6 && H36, "null argument");
   LGS_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");

@@ -351,6 +351,16 @@ def test_exact_sums_product_equals_oracle(tmp_path):
     assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout[-2000:]
 
 
+def test_ndt_convert_transform_host_function(oracle):
+    """static convertTransform (NDT.h:214-238) is host arithmetic in the product too: bit-identical to the oracle's, no GPU needed."""
+    from lidar_graph_slam_b200 import api
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        x = np.concatenate([rng.normal(scale=30.0, size=3), rng.uniform(-np.pi, np.pi, size=3)])
+        assert np.array_equal(api.NormalDistributionsTransform.convertTransform(x), oracle.ndt_convert_transform(x))
+    assert np.array_equal(api.NormalDistributionsTransform.convertTransform(np.zeros(6)), np.eye(4, dtype=np.float32))
+
+
 def test_c_abi_exports_every_declared_symbol():
     """liblgs_b200.so loads on a CPU-only box and exports exactly what include/lgs_c.h declares."""
     from lidar_graph_slam_b200 import _lib
