@@ -210,8 +210,8 @@ __device__ __forceinline__ void gicp_point_terms(const LinParams& P, const float
 // the target, kept when its squared distance is below the threshold.  The Mahalanobis half (FG:139-150) is fused
 // into gicp_linearize_kernel.
 constexpr int kCorrBlock = 256;
-__global__ void __launch_bounds__(kCorrBlock) gicp_correspondence_kernel(NNView tv, const float4* __restrict__ src, int n, LinParams P,
-                                                                        int* __restrict__ corr) {
+__global__ void __launch_bounds__(kCorrBlock) gicp_correspondence_kernel(NNView tv, const float4* __restrict__ src, const float4* __restrict__ tgt, int n,
+                                                                        LinParams P, int* __restrict__ corr, int* __restrict__ nn_prev, int use_seed) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = blockIdx.x * (kCorrBlock / 32) + warp; i < n; i += gridDim.x * (kCorrBlock / 32)) {
     const float4 a = __ldg(src + i);
@@ -221,8 +221,15 @@ __global__ void __launch_bounds__(kCorrBlock) gicp_correspondence_kernel(NNView 
     const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.Tf[8], a.x), __fmul_rn(P.Tf[9], a.y)), __fmul_rn(P.Tf[10], a.z)), P.Tf[11]);
     float d2;
     int id;
-    nn_search1_warp(tv, qx, qy, qz, lane, d2, id);
-    if (lane == 0) corr[i] = (static_cast<double>(d2) < P.corr_thr2) ? id : -1;  // FG:136
+    // seed: the neighbour found at the previous linearisation (the pose moved little since), see nn_search1_warp_seeded
+    const int seed = use_seed ? nn_prev[i] : -1;
+    float seed_d = 0.f;
+    if (seed >= 0) seed_d = nn_dist2(qx, qy, qz, __ldg(tgt + seed));
+    nn_search1_warp_seeded(tv, qx, qy, qz, lane, seed_d, seed, d2, id);
+    if (lane == 0) {
+      corr[i] = (static_cast<double>(d2) < P.corr_thr2) ? id : -1;  // FG:136
+      nn_prev[i] = id;
+    }
   }
 }
 
@@ -352,6 +359,8 @@ int ensure_ready(lgs_gicp* g) {
   LGS_TRY(g->target->ensure_index(g->ctx));
   const size_t n = static_cast<size_t>(std::max<int64_t>(g->source->n, 1));
   LGS_TRY(g->corr.reserve(n * 4));
+  LGS_TRY(g->nn_prev.reserve(n * 4));
+  g->have_seed = false;  // a new align / hook call: the clouds may have changed since the seeds were written
   LGS_TRY(g->mahal.reserve(n * 72));
   const int grid = lin_grid(g->source->n);
   LGS_TRY(g->partials.reserve(static_cast<size_t>(grid) * 44 * 8));
@@ -387,7 +396,9 @@ int linearize(lgs_gicp* g, const double* T, double* cost, double* H, double* b) 
   const int cgrid = std::max(1, std::min(grid_for(n, kCorrBlock / 32), kNumSMs * 8));
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
-  gicp_correspondence_kernel<<<cgrid, kCorrBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), n, P, g->corr.as<int>());
+  gicp_correspondence_kernel<<<cgrid, kCorrBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P, g->corr.as<int>(),
+                                                          g->nn_prev.as<int>(), g->have_seed ? 1 : 0);
+  g->have_seed = true;
   gicp_linearize_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P,
                                                           g->source->covs.as<double>(), g->target->covs.as<double>(), g->corr.as<int>(),
                                                           g->mahal.as<double>(), (H && b) ? 1 : 0, g->partials.as<double>(), result, counter, mb);
@@ -563,7 +574,7 @@ void lgs_gicp_destroy(lgs_gicp* g) {
   cudaStreamSynchronize(g->ctx->stream);
   g->source.reset();
   g->target.reset();
-  for (DevBuf* b : {&g->corr, &g->mahal, &g->partials, &g->result, &g->out_cloud}) b->release();
+  for (DevBuf* b : {&g->corr, &g->nn_prev, &g->mahal, &g->partials, &g->result, &g->out_cloud}) b->release();
   delete g;
 }
 

@@ -41,6 +41,8 @@ struct lgs_gicp {
   double lm_init_lambda_factor = 1e-9, lm_lambda = -1.0;
   std::shared_ptr<lgs::GicpCloud> source, target;
   lgs::DevBuf corr, mahal, partials, result, out_cloud;
+  lgs::DevBuf nn_prev;     // nearest target point of every source point at the previous linearisation (search seed)
+  bool have_seed = false;  // nn_prev is valid for the current source / target pair
   double final_hessian[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
   float final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   int linearize_calls = 0, error_calls = 0;

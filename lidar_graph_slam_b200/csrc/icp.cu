@@ -28,11 +28,12 @@ constexpr int kIcpSums = 17;
 struct IcpParams {
   float T[16];       // column-major transform applied to every point before the search
   int apply;         // 0: T is the identity, the cloud is not rewritten
+  int use_seed;      // nn_prev holds the neighbours of the previous iteration
   double max_dist2;
 };
 
-__device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int n, const IcpParams& P,
-                                              double* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox& mb) {
+__device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int* __restrict__ nn_prev, int n,
+                                              const IcpParams& P, double* __restrict__ partials, unsigned* __restrict__ counter, const Mailbox& mb) {
   __shared__ double sm[kIcpBlock / 32][kIcpSums];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -46,7 +47,12 @@ __device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __
     }
     float d2;
     int id;
-    nn_search1_warp(tv, p.x, p.y, p.z, lane, d2, id);
+    // seeded with the previous iteration's neighbour (the cloud moved by one small transformation since)
+    const int seed = P.use_seed ? nn_prev[i] : -1;
+    float seed_d = 0.f;
+    if (seed >= 0) seed_d = nn_dist2(p.x, p.y, p.z, __ldg(tgt + seed));
+    nn_search1_warp_seeded(tv, p.x, p.y, p.z, lane, seed_d, seed, d2, id);
+    if (lane == 0) nn_prev[i] = id;
     if (id < 0 || static_cast<double>(d2) > P.max_dist2) continue;  // warp-uniform
     const float4 q = __ldg(tgt + id);  // id is the ORIGINAL index of the matched target point
     const double pv[3] = {static_cast<double>(p.x), static_cast<double>(p.y), static_cast<double>(p.z)};
@@ -94,10 +100,11 @@ __device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __
   }
 }
 
-__global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(const __grid_constant__ NNView tv, const float4* __restrict__ tgt, float4* __restrict__ cloud, int n,
-                                                            const __grid_constant__ IcpParams P, double* __restrict__ partials,
-                                                            unsigned* __restrict__ counter, const __grid_constant__ Mailbox mb) {
-  icp_step_body(tv, tgt, cloud, n, P, partials, counter, mb);
+__global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(const __grid_constant__ NNView tv, const float4* __restrict__ tgt, float4* __restrict__ cloud,
+                                                            int* __restrict__ nn_prev, int n, const __grid_constant__ IcpParams P,
+                                                            double* __restrict__ partials, unsigned* __restrict__ counter,
+                                                            const __grid_constant__ Mailbox mb) {
+  icp_step_body(tv, tgt, cloud, nn_prev, n, P, partials, counter, mb);
 }
 
 // Persistent form: the grid stays resident for the iterations of one align and receives {transformation_, mailbox token}
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(kIcpBlock) icp_step_kernel(const __grid_consta
 struct IcpPose {
   float T[16];
   int apply;  // < 0: end of the run
-  int pad;
+  int use_seed;
   unsigned long long token;
 };
 constexpr int kIcpWords = static_cast<int>(sizeof(IcpPose) / 8);
@@ -116,7 +123,7 @@ using IcpCmdDev = CmdDev<kIcpWords>;
 constexpr int kIcpResident = 4;  // CTAs per SM of the persistent grid (all co-resident)
 
 __global__ void __launch_bounds__(kIcpBlock, kIcpResident) icp_persistent_kernel(const __grid_constant__ NNView tv, const float4* __restrict__ tgt,
-                                                                                float4* __restrict__ cloud, int n, double max_dist2,
+                                                                                float4* __restrict__ cloud, int* __restrict__ nn_prev, int n, double max_dist2,
                                                                                 double* __restrict__ partials, unsigned* __restrict__ counter,
                                                                                 MailboxRecord* mailbox, const IcpCmdHost* __restrict__ cmd_host,
                                                                                 IcpCmdDev* __restrict__ cmd_dev, unsigned long long first_seq) {
@@ -131,13 +138,14 @@ __global__ void __launch_bounds__(kIcpBlock, kIcpResident) icp_persistent_kernel
     if (threadIdx.x < 16) P.T[threadIdx.x] = pose.T[threadIdx.x];
     if (threadIdx.x == 0) {
       P.apply = pose.apply;
+      P.use_seed = pose.use_seed;
       P.max_dist2 = max_dist2;
     }
     __syncthreads();
     Mailbox mb;
     mb.r = mailbox;
     mb.token = pose.token;
-    icp_step_body(tv, tgt, cloud, n, P, partials, counter, mb);
+    icp_step_body(tv, tgt, cloud, nn_prev, n, P, partials, counter, mb);
     __syncthreads();
   }
 }
@@ -162,7 +170,8 @@ struct lgs_icp {
   double fitness_eps = -std::numeric_limits<double>::max();
   double corr_dist_threshold = 1.3407807929942596e154;  // sqrt(DBL_MAX)
   int min_correspondences = 3;
-  DevBuf source, target, target_copy, cloud, partials, state, out_cloud;
+  DevBuf source, target, target_copy, cloud, nn_prev, partials, state, out_cloud;
+  bool have_seed = false;  // nn_prev belongs to the working cloud of the running align
   int64_t n_source = 0, n_target = 0;
   NNIndex nn;
   bool nn_ready = false;
@@ -261,6 +270,7 @@ int ensure_ready(lgs_icp* g) {
     g->nn_ready = true;
   }
   LGS_TRY(g->cloud.reserve(static_cast<size_t>(g->n_source) * 16));
+  LGS_TRY(g->nn_prev.reserve(static_cast<size_t>(g->n_source) * 4));
   LGS_TRY(g->partials.reserve(static_cast<size_t>(step_grid(g->n_source)) * kIcpSums * 8));
   if (!g->state.p) {
     LGS_TRY(g->state.reserve(64));
@@ -300,6 +310,8 @@ int step(lgs_icp* g, const float* T, double* sums) {
   P.apply = T ? 1 : 0;
   if (T) memcpy(P.T, T, sizeof(P.T)); else identity16f(P.T);
   P.max_dist2 = g->corr_dist_threshold * g->corr_dist_threshold;
+  P.use_seed = g->have_seed ? 1 : 0;
+  g->have_seed = true;
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
   const int grid = step_grid(g->n_source);
@@ -311,7 +323,7 @@ int step(lgs_icp* g, const float* T, double* sums) {
     if (persist_try_acquire(ctx->device)) {
       void* dv = nullptr;
       LGS_CUDA(cudaHostGetDevicePointer(&dv, g->cmd_host, 0));
-      icp_persistent_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), n, P.max_dist2,
+      icp_persistent_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), g->nn_prev.as<int>(), n, P.max_dist2,
                                                                g->partials.as<double>(), g->state.as<unsigned>(), mb.r, static_cast<const IcpCmdHost*>(dv),
                                                                g->cmd_dev.as<IcpCmdDev>(), g->cmd_seq + 1);
       ctx->launches++;
@@ -329,7 +341,7 @@ int step(lgs_icp* g, const float* T, double* sums) {
     IcpPose pose;
     memcpy(pose.T, P.T, sizeof(pose.T));
     pose.apply = P.apply;
-    pose.pad = 0;
+    pose.use_seed = P.use_seed;
     pose.token = mb.token;
     persist_send<kIcpWords>(g->cmd_host, ++g->cmd_seq, &pose);
     const int rc = mailbox_wait(ctx, mb, kIcpSums, sums);
@@ -344,7 +356,7 @@ int step(lgs_icp* g, const float* T, double* sums) {
     }
     return rc;
   }
-  icp_step_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), n, P, g->partials.as<double>(),
+  icp_step_kernel<<<grid, kIcpBlock, 0, ctx->stream>>>(g->nn.view(), g->target.as<float4>(), g->cloud.as<float4>(), g->nn_prev.as<int>(), n, P, g->partials.as<double>(),
                                                       g->state.as<unsigned>(), mb);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
@@ -380,7 +392,7 @@ void lgs_icp_destroy(lgs_icp* g) {
   cudaStreamSynchronize(g->ctx->stream);
   if (g->cmd_host) cudaFreeHost(g->cmd_host);
   g->cmd_dev.release();
-  for (DevBuf* b : {&g->source, &g->target, &g->target_copy, &g->cloud, &g->partials, &g->state, &g->out_cloud}) b->release();
+  for (DevBuf* b : {&g->source, &g->target, &g->target_copy, &g->cloud, &g->nn_prev, &g->partials, &g->state, &g->out_cloud}) b->release();
   g->nn.release();
   delete g;
 }
@@ -439,6 +451,7 @@ static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* re
   bool is_identity = true;
   for (int i = 0; i < 16; i++)
     if (guess[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) is_identity = false;
+  g->have_seed = false;  // the seeds belong to one align (one working cloud, one target)
   // input_transformed = guess * input (or a copy)
   LGS_CUDA(cudaMemcpyAsync(g->cloud.p, g->source.p, static_cast<size_t>(g->n_source) * 16, cudaMemcpyDeviceToDevice, st));
   identity16f(T);
@@ -503,6 +516,7 @@ int lgs_icp_step(lgs_icp* g, const float* guess16, double* sums17, float* T16, i
   LGS_TRY(use_device(g->ctx));
   LGS_TRY(ensure_ready(g));
   LGS_CUDA(cudaMemcpyAsync(g->cloud.p, g->source.p, static_cast<size_t>(g->n_source) * 16, cudaMemcpyDeviceToDevice, g->ctx->stream));
+  g->have_seed = false;
   LGS_TRY(step(g, guess16, sums17));
   *ok = static_cast<int>(sums17[0]) >= g->min_correspondences ? 1 : 0;
   identity16f(T16);

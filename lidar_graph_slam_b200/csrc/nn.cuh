@@ -154,6 +154,20 @@ __device__ __forceinline__ void nn_search1_warp(const NNView& v, float qx, float
     nn1_descend<5>(v, 0, v.cnt[5], qx, qy, qz, lane, best_d, best_i);
 }
 
+// The same search started from a known indexed point (seed_i, at squared distance seed_d from the query; seed_i < 0: no
+// seed).  Any indexed point is a valid upper bound and the walk still visits every box that could hold a closer point
+// or an equally close one with a smaller index, so the result is the same exact nearest neighbour - found after fewer
+// node visits.  Iterative registration uses the previous iteration's neighbour as the seed.
+__device__ __forceinline__ void nn_search1_warp_seeded(const NNView& v, float qx, float qy, float qz, int lane, float seed_d, int seed_i, float& best_d,
+                                                       int& best_i) {
+  best_d = seed_i >= 0 ? seed_d : __int_as_float(0x7f800000);
+  best_i = seed_i >= 0 ? seed_i : 0x7fffffff;
+  if (v.n_levels == 3)
+    nn1_descend<2>(v, 0, v.cnt[2], qx, qy, qz, lane, best_d, best_i);
+  else if (v.n_levels == 6)
+    nn1_descend<5>(v, 0, v.cnt[5], qx, qy, qz, lane, best_d, best_i);
+}
+
 // ---- k-NN -------------------------------------------------------------------------------------------------------
 // The warp holds a list of 32 candidates sorted ascending by (d2, idx), entry j in lane j; worst / worst_i
 // (warp-uniform) mirror entry k - 1.  Empty entries are (+inf, INT_MAX).
