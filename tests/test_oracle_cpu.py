@@ -289,6 +289,36 @@ def test_icp_oracle_umeyama_and_convergence(oracle, velodyne_pair, golden):
     assert np.array_equal(far.final_transformation, np.eye(4, dtype=np.float32))
 
 
+def test_pcl_style_registrations_are_thread_count_invariant(oracle, velodyne_pair):
+    """The reference's pclomp GICP sums per OpenMP thread (gicp_omp_impl.hpp:251,274), so its low bits move with the thread
+    count; the restatement's exact sums (and ICP's serial ones) make the whole align a function of the inputs only."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    guess = np.eye(4, dtype=np.float32)
+    guess[:3, 3] = [0.1, -0.05, 0.0]
+    for cls in (oracle.GeneralizedIterativeClosestPoint, oracle.IterativeClosestPoint):
+        res = []
+        for threads in (1, 3):
+            g = cls()
+            g.setNumThreads(threads)
+            g.setMaximumIterations(30)
+            g.setInputTarget(t2)
+            g.setInputSource(s2)
+            out = g.align(guess)
+            res.append((g.final_transformation.copy(), g.nr_iterations, g.converged, out.copy()))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1:3] == res[1][1:3] and np.array_equal(res[0][3], res[1][3])
+        # align() twice on the same object (covariances kept, GO:381-392) gives the same answer
+        again = g.align(guess)
+        assert np.array_equal(g.final_transformation, res[1][0]) and np.array_equal(again, res[1][3])
+    # the backward direction lands on the inverse of relative.txt (fast_gicp gtest, gicp_test.cpp:167-175, for the BFGS variant)
+    b = oracle.GeneralizedIterativeClosestPoint()
+    b.setInputTarget(s2)
+    b.setInputSource(t2)
+    b.align()
+    t_err, r_err = pose_error(velodyne_pair["relative"], np.linalg.inv(b.final_transformation.astype(np.float64)))
+    assert b.converged and t_err < 0.05 and np.degrees(r_err) < 1.0
+
+
 def test_knn_against_scipy(oracle, velodyne_pair):
     from scipy.spatial import cKDTree
     pts = oracle.voxel_grid(velodyne_pair["target"], 0.3)["points"]
