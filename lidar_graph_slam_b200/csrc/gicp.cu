@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kCorrBlock) gicp_correspondence_kernel(NNView 
     float d2;
     int id;
     // seed: the neighbour found at the previous linearisation (the pose moved little since), see nn_search1_warp_seeded
-    const int seed = use_seed ? nn_prev[i] : -1;
+    int seed = use_seed ? nn_prev[i] : -1;
+    if (seed >= tv.n) seed = -1;  // the 'nothing found' sentinel of an empty index
     float seed_d = 0.f;
     if (seed >= 0) seed_d = nn_dist2(qx, qy, qz, __ldg(tgt + seed));
     nn_search1_warp_seeded(tv, qx, qy, qz, lane, seed_d, seed, d2, id);

@@ -48,7 +48,8 @@ __device__ __forceinline__ void icp_step_body(const NNView& tv, const float4* __
     float d2;
     int id;
     // seeded with the previous iteration's neighbour (the cloud moved by one small transformation since)
-    const int seed = P.use_seed ? nn_prev[i] : -1;
+    int seed = P.use_seed ? nn_prev[i] : -1;
+    if (seed >= tv.n) seed = -1;  // the 'nothing found' sentinel of an empty index
     float seed_d = 0.f;
     if (seed >= 0) seed_d = nn_dist2(p.x, p.y, p.z, __ldg(tgt + seed));
     nn_search1_warp_seeded(tv, p.x, p.y, p.z, lane, seed_d, seed, d2, id);

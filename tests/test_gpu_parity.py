@@ -945,6 +945,42 @@ def test_loop_closure_cfg4_full_size_properties(api):
         assert list(r.T) == list(recs[i].T) and r.fitness == recs[i].fitness and r.iterations == recs[i].iterations
 
 
+def test_registrations_survive_degenerate_clouds(api, velodyne_pair):
+    """Empty or tiny clouds never take the process or the GPU down: the calls return (an error or a not-converged
+    result, as the reference's objects would report), and the same objects work normally afterwards."""
+    s2 = velodyne_pair["source"][:5000]
+    t2 = velodyne_pair["target"][:5000]
+    empty = np.zeros((0, 4), np.float32)
+    g = api.FastGICP()
+    g.setInputTarget(empty)
+    g.setInputSource(s2)
+    g.align()                       # no target points: no correspondences at any LM iteration (seeded search included)
+    g.align()
+    g.setInputTarget(t2)
+    g.setInputSource(empty)
+    g.align()
+    assert g.result.iterations == 0
+    for cls in (api.IterativeClosestPoint, api.GeneralizedIterativeClosestPoint):
+        x = cls()
+        x.setInputTarget(empty)
+        x.setInputSource(s2)
+        with pytest.raises(RuntimeError):
+            x.align()
+        x.setInputTarget(t2)
+        x.align()
+        assert x.result.iterations >= 1
+    n = api.NormalDistributionsTransform()
+    n.setInputTarget(t2)
+    n.setInputSource(empty)
+    n.align()
+    n.setInputSource(s2)
+    n.align()
+    assert n.result.iterations >= 1
+    g.setInputSource(s2)
+    g.align()
+    assert g.hasConverged()
+
+
 def test_device_resident_inputs(api, oracle, velodyne_pair):
     """_dev entry points: clouds already in HBM (torch tensors) give the same results as host uploads."""
     import torch
