@@ -203,69 +203,78 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def loop_closure_bench(rank, world, device, pairs_per_rank):
-    """configs[4] in miniature at N GPUs: GICP verification of (scan, submap) candidates, sharded by size, one NCCL
-    gather of the result records.  Returns pairs/s over all ranks (max-over-ranks time)."""
+def loop_closure_bench(rank, world, device, n_total, n_host_pairs):
+    """configs[4]: GICP verification of `n_total` (scan, 41-key-frame sub-map) candidates - 4096 by default - through the
+    collective C-ABI call lgs_batch_align_keyframes_dist: the candidate list is the same on every rank, the C++ host deals the
+    pairs by size, each pair's last kernel stores its 96-byte record in the NCCL send buffer, one ncclAllGather returns all
+    records to every rank.  STRONG scaling: n_total is fixed as N grows.  Returns pairs/s over all ranks (max-over-ranks time)."""
     import torch
     import torch.distributed as dist
     from lidar_graph_slam_b200 import api, synth
-    from lidar_graph_slam_b200.distributed import gather_records, partition_pairs, records_to_array
-    n_total = pairs_per_rank * world
-    scans, submaps, _ = synth.loop_pairs(n_pairs=n_total, n_keyframes=41, n_azimuth=900, n_unique=2)
-    sizes = [len(a) + len(b) for a, b in zip(scans, submaps)]
-    mine = partition_pairs(sizes, rank, world)
-    my_scans, my_subs = [scans[i] for i in mine], [submaps[i] for i in mine]
-    # concurrent pairs per GPU, each a host thread on its own stream: 4 when the box has the cores for it (1211 / 1133 / 970 /
-    # 724 pairs/s at 8 / 4 / 2 / 1 workers on one B200, tools/dev_loop_workers.sh); the workers spin on result mailboxes,
-    # so never more than the host cores per rank
+    n_az = _env_int("LGS_BENCH_LOOP_AZIMUTH", 900)
+    d = synth.loop_keyframes(n_pairs=n_total, n_keyframes=41, n_azimuth=n_az, n_unique=2)
+    ctx = api.Context(device)
+    kf = api.KeyFrameArray(ctx)
+    for c, P in zip(d["clouds"], d["poses"]):
+        kf.push(c, P)
+    comm = api.Comm.from_torch_distributed(device)
+    # concurrent pairs per GPU, each a host thread on its own stream; never more than the host cores per rank
     n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", max(1, min(4, host_threads() // max(world, 1))))
-    api.batch_align(my_scans[:2 * n_workers], my_subs[:2 * n_workers], n_workers=n_workers, device=device)  # warm-up: every worker allocates its device state once
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    recs = api.batch_align(my_scans, my_subs, method=api.METHOD_GICP, device=device, n_workers=n_workers, pair_id0=0)
-    local = torch.from_numpy(records_to_array(recs)).cuda(device)
-    gathered = gather_records(local, n_total, torch.tensor(mine, dtype=torch.int64), rank, world)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tmax = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % device)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    conv = int(gathered[:, 19].sum().item())
-    # the same candidates with every cloud already resident in the device key-frame array (lgs_batch_align_keyframes):
-    # sub-maps are assembled and voxel-filtered on the GPU, only the records cross PCIe
-    kfres = None
-    try:
-        d = synth.loop_keyframes(n_pairs=n_total, n_keyframes=41, n_azimuth=900, n_unique=2)
-        ctx = api.Context(device)
-        kf = api.KeyFrameArray(ctx)
-        for c, P in zip(d["clouds"], d["poses"]):
-            kf.push(c, P)
-        mine_k = list(range(rank, n_total, world))
-        sid = [d["scan_ids"][i] for i in mine_k]
-        cid = [d["center_ids"][i] for i in mine_k]
-        kf.batch_align(sid[:2 * n_workers], cid[:2 * n_workers], search_key_frame_num=20, n_workers=n_workers)
+    kw = dict(search_key_frame_num=20, method=api.METHOD_GICP, n_workers=n_workers)
+    kf.batch_align_dist(comm, d["scan_ids"][:4 * n_workers * world], d["center_ids"][:4 * n_workers * world], **kw)  # warm-up: every worker's device state
+
+    def timed_call(fn):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        recs_k = kf.batch_align(sid, cid, search_key_frame_num=20, method=api.METHOD_GICP, n_workers=n_workers)
-        local_k = torch.from_numpy(records_to_array(recs_k)).cuda(device)
-        gathered_k = gather_records(local_k, n_total, torch.tensor(mine_k, dtype=torch.int64), rank, world)
+        out = fn()
         torch.cuda.synchronize()
-        dtk = time.perf_counter() - t0
-        tk = torch.tensor([dtk], dtype=torch.float64, device="cuda:%d" % device)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % device)
         if world > 1:
-            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        kfres = {"pairs_per_sec": n_total / tk.item(), "converged": int(gathered_k[:, 19].sum().item()),
-                 "note": "key frames resident in HBM (lgs_keyframes), sub-map assembly + VoxelGrid 0.5 m + GICP + fitness on the device"}
-    except Exception as e:
-        kfres = {"error": repr(e)}
-    return {"pairs_per_sec": n_total / tmax.item(), "n_pairs": n_total, "converged": conv, "method": "FastGICP k=20, max_corr 2.0, submap VoxelGrid 0.5 m",
-            "from_keyframe_array": kfres,
-            "gather": "all_gather of %d x 26 f32 records (%s)" % (n_total, "nccl" if world > 1 else "single rank"), "workers_per_gpu": n_workers,
-            "mean_scan_pts": float(np.mean([len(s) for s in scans])), "mean_submap_pts": float(np.mean([len(s) for s in submaps]))}
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, t.item()
+
+    (recs, info), dt = timed_call(lambda: kf.batch_align_dist(comm, d["scan_ids"], d["center_ids"], **kw))
+    conv = sum(1 for r in recs if r.converged)
+    accepted = sum(1 for r in recs if r.converged and r.fitness <= 0.3)  # GBS:328 with score_threshold 0.3
+    # algorithmic bytes of a pair (SURVEY.md section 8d "Loop pair"): sub-map assembly (32 B per point) + VoxelGrid 0.5 m
+    # (16 N + 4 N + 4 N + 16 V) + k-NN covariances of both clouds (16 + 24 B per point) + every linearisation / error pass
+    # (N_s (16 + 24 + 16 + 24)) + fitness (32 N_s)
+    n_kf = 2 * 41
+    sub_pts = float(np.mean([sum(len(d["clouds"][j]) for j in range(c - 20, c + 21) if 0 <= j < n_kf) for c in d["center_ids"][:64]]))
+    scan_pts = float(np.mean([len(d["clouds"][s]) for s in d["scan_ids"][:64]]))
+    one, _ = kf.assemble([j for j in range(d["center_ids"][0] - 20, d["center_ids"][0] + 21) if 0 <= j < n_kf], leaf=0.5).shape
+    passes = float(np.mean([r.evaluations + r.line_search_trials for r in recs]))
+    bytes_pair = 32 * sub_pts + 24 * sub_pts + 16 * one + 40 * (one + scan_pts) + passes * scan_pts * 80 + 32 * scan_pts
+    peak, _ = measured_peak_hbm()
+    pps = n_total / dt
+    out = {"pairs_per_sec": pps, "n_pairs": n_total, "scaling": "strong", "seconds": dt, "converged": conv, "accepted_by_fitness_gate": accepted,
+           "method": "FastGICP k=20, max_corr 2.0, eps 0.01, submap VoxelGrid 0.5 m (graph_based_slam.param.yaml)",
+           "api": "lgs_batch_align_keyframes_dist (C-ABI; partition, verification and the ncclAllGather of the records all inside liblgs_b200.so)",
+           "comm_nranks": info["world"], "nccl_version": comm.nccl_version, "pairs_rank0": info["n_local"], "verify_ms_rank0": info["verify_ms"],
+           "gather_ms_rank0": info["gather_ms"], "gather_bytes": info["gather_bytes"], "workers_per_gpu": n_workers,
+           "mean_scan_pts": scan_pts, "mean_submap_pts": sub_pts, "submap_pts_after_voxelgrid": int(one), "passes_per_pair": passes,
+           "algorithmic_bytes_per_pair": bytes_pair, "achieved_gbs": bytes_pair * pps / 1e9, "frac_of_hbm_peak_all_gpus": bytes_pair * pps / 1e9 / (peak * world),
+           "n_azimuth": n_az}
+    # the same collective with the clouds of every pair coming from HOST arrays (each rank uploads only its own pairs: 17 MB of
+    # sub-map per pair over PCIe) on a bounded sample
+    if n_host_pairs > 0:
+        try:
+            scans, submaps, _ = synth.loop_pairs(n_pairs=n_host_pairs, n_keyframes=41, n_azimuth=n_az, n_unique=2)
+            sizes = [(len(a), len(b)) for a, b in zip(scans, submaps)]
+            mine = set(api.partition_pairs([a + b for a, b in sizes], rank, world))
+            hs = [s if i in mine else None for i, s in enumerate(scans)]
+            hm = [s if i in mine else None for i, s in enumerate(submaps)]
+            api.batch_align_dist(comm, hs[:2 * n_workers * world], hm[:2 * n_workers * world], sizes=sizes[:2 * n_workers * world], n_workers=n_workers)
+            (hrecs, hinfo), hdt = timed_call(lambda: api.batch_align_dist(comm, hs, hm, sizes=sizes, n_workers=n_workers))
+            out["from_host_arrays"] = {"pairs_per_sec": n_host_pairs / hdt, "n_pairs": n_host_pairs, "converged": sum(1 for r in hrecs if r.converged),
+                                       "api": "lgs_batch_align_dist", "h2d_bytes_per_pair": 16 * (sub_pts + scan_pts)}
+        except Exception as e:
+            out["from_host_arrays"] = {"error": repr(e)}
+    comm.close()
+    return out
 
 
 def gicp_odometry_bench(device, stream, ctx, n_sweeps=8, reps=3):
@@ -319,7 +328,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 32), help="loop-closure pairs per rank (0 disables)")
+    ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 4096),
+                    help="loop-closure candidates in TOTAL (BASELINE configs[4]: 4096; strong scaling over --gpus; 0 disables)")
+    ap.add_argument("--loop-host-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_HOST_PAIRS", 128), help="sample of pairs verified from host arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
@@ -435,7 +446,7 @@ def main():
     loop = None
     if args.loop_pairs > 0:
         try:
-            loop = loop_closure_bench(rank, world, local_rank, args.loop_pairs)
+            loop = loop_closure_bench(rank, world, local_rank, args.loop_pairs, args.loop_host_pairs)
         except Exception as e:  # the headline line must still be printed
             loop = {"error": repr(e)}
 

@@ -394,6 +394,50 @@ int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, const lgs_ba
                               const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
                               const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev);
 
+/* ------------------------------------------------------------------------------------------- */
+/* the same batch over the GPUs of a box: one process per GPU, one NCCL gather of the records    */
+/*   SURVEY.md section 8b "batch_align_dist(ncclComm, rank, world, ...)" / section 8e.  The      */
+/*   reference verifies one candidate per optimization_callback on one core (GBS:245-340); a     */
+/*   pose graph with thousands of candidates (BASELINE configs[4]) is embarrassingly parallel:   */
+/*   pairs are dealt to the ranks by size, every rank verifies its own, and the fixed-size        */
+/*   records are exchanged with a single ncclAllGather over NVLink.                               */
+typedef struct lgs_comm lgs_comm;
+#define LGS_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+
+/* rank 0 calls lgs_comm_get_unique_id and hands the 128 bytes to the other ranks by any means it has (MPI, a file,
+ * torch.distributed); every rank then calls lgs_comm_init_rank (ncclCommInitRank on `device`).  A host that already
+ * owns an ncclComm_t passes it to lgs_comm_adopt instead (the handle is used, never destroyed). */
+int lgs_comm_get_unique_id(uint8_t* id128);
+int lgs_comm_init_rank(const uint8_t* id128, int32_t rank, int32_t world, int32_t device, lgs_comm** out);
+int lgs_comm_adopt(void* nccl_comm, int32_t device, lgs_comm** out);
+void lgs_comm_destroy(lgs_comm* comm);
+int lgs_comm_info(lgs_comm* comm, int32_t* rank, int32_t* world, int32_t* nccl_version);
+
+/* The partition rule, exported so that callers and tests can predict it: pairs sorted by descending size (index breaks
+ * ties) and dealt round-robin; out_ids receives this rank's pair indices in ascending order.  Pure host arithmetic. */
+int lgs_batch_partition(const int64_t* sizes, int64_t n_total, int32_t rank, int32_t world, int32_t* out_ids, int64_t capacity, int64_t* n_mine);
+
+typedef struct lgs_batch_dist_info {
+  int32_t rank, world;
+  int64_t n_local;      /* pairs this rank verified */
+  int64_t n_received;   /* records that came back from the gather (= n_pairs on success) */
+  int64_t gather_bytes; /* bytes received by this rank in the ncclAllGather */
+  double verify_ms;     /* host wall time of this rank's own pairs */
+  double gather_ms;     /* ncclAllGather + D2H of the gathered records + placement */
+} lgs_batch_dist_info;
+
+/* Collective: every rank of `comm` calls it with the SAME list of n_pairs candidates (the pose graph is replicated, its
+ * key-frame array resident on every GPU) and receives ALL n_pairs records in records_all[pair index], bit-identical on
+ * every rank and for every world size.  Each pair's last kernel stores its record in the NCCL send buffer. */
+int lgs_batch_align_keyframes_dist(lgs_keyframes* kf, lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs,
+                                   const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
+                                   const float* guesses16, lgs_align_result* records_all, lgs_batch_dist_info* info);
+/* Host-array form: n_scan / n_submap are needed for all pairs on every rank (they drive the partition); scans[i] /
+ * submaps[i] are read only on the rank that owns pair i and may be NULL elsewhere (each rank uploads only its own). */
+int lgs_batch_align_dist(lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
+                         const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
+                         const float* guesses16, lgs_align_result* records_all, lgs_batch_dist_info* info);
+
 /* The per-worker device state of lgs_batch_align (stream, registration objects, staging buffers) is kept in a
  * process-wide pool between calls, the way the reference keeps one registration_ object per node for its lifetime
  * (graph_based_slam.hpp:108).  This frees it (call with no batch in flight, e.g. at node shutdown). */

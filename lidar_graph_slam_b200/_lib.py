@@ -49,6 +49,11 @@ class BatchParams(C.Structure):
                 ("n_workers", C.c_int32), ("max_optimizer_iterations", C.c_int32), ("euclidean_fitness_epsilon", C.c_double)]
 
 
+class BatchDistInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_local", C.c_int64), ("n_received", C.c_int64), ("gather_bytes", C.c_int64),
+                ("verify_ms", C.c_double), ("gather_ms", C.c_double)]
+
+
 # every symbol include/lgs_c.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 SYMBOLS = {
@@ -155,6 +160,14 @@ SYMBOLS = {
     "lgs_batch_align_keyframes": (_i32, [_vp, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lgs_batch_release": (None, []),
+    "lgs_comm_get_unique_id": (_i32, [_vp]),
+    "lgs_comm_init_rank": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "lgs_comm_adopt": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "lgs_comm_destroy": (None, [_vp]),
+    "lgs_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "lgs_batch_partition": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, C.POINTER(_i64)]),
+    "lgs_batch_align_keyframes_dist": (_i32, [_vp, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _i32, _vp, _vp, C.POINTER(BatchDistInfo)]),
+    "lgs_batch_align_dist": (_i32, [_vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(BatchDistInfo)]),
 }
 
 _lib = None

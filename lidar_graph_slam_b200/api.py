@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AlignResult, BatchParams, NdtGridInfo, Pc2Layout, SorInfo, VoxelGridInfo, check
+from ._lib import AlignResult, BatchDistInfo, BatchParams, NdtGridInfo, Pc2Layout, SorInfo, VoxelGridInfo, check
 
 NDT_KDTREE, NDT_DIRECT26, NDT_DIRECT7, NDT_DIRECT1 = 0, 1, 2, 3
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = 0, 1, 2, 3, 4
@@ -574,6 +574,27 @@ class KeyFrameArray:
                                                 vp(g) if g is not None else None, int(pair_id0), recs, C.c_void_p(records_dev) if records_dev else None))
         return [recs[i] for i in range(n)]
 
+    def batch_align_dist(self, comm, scan_ids, center_ids, search_key_frame_num=20, method=METHOD_GICP, guesses=None, max_iterations=100,
+                         transformation_epsilon=0.01, max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0, ndt_step_size=0.1,
+                         submap_leaf=0.5, fitness_max_range=-1.0, n_workers=0, max_optimizer_iterations=0, euclidean_fitness_epsilon=0.0):
+        """lgs_batch_align_keyframes_dist (collective over `comm`): the candidate list is the same on every rank, each rank
+        verifies its share from its own resident key-frame array, one ncclAllGather returns all records everywhere."""
+        sid = np.ascontiguousarray(scan_ids, np.int32)
+        cid = np.ascontiguousarray(center_ids, np.int32)
+        n = int(sid.size)
+        assert cid.size == n
+        g = None
+        if guesses is not None:
+            g = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).reshape(4, 4).ravel(order="F") for T in guesses]))
+        bp = _batch_params(method, max_iterations, transformation_epsilon, max_correspondence_distance, k_correspondences, ndt_resolution,
+                           ndt_step_size, submap_leaf, fitness_max_range, n_workers, max_optimizer_iterations, euclidean_fitness_epsilon)
+        recs = (AlignResult * max(n, 1))()
+        info = BatchDistInfo()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self._L.lgs_batch_align_keyframes_dist(self._h, comm._h, C.byref(bp), n, vp(sid), vp(cid), int(search_key_frame_num),
+                                                     vp(g) if g is not None else None, recs, C.byref(info)))
+        return [recs[i] for i in range(n)], _dist_info(info)
+
     def assemble(self, ids, leaf=0.0):
         """Returns a CUDA float32 tensor (N, 4): a copy of the library's sub-map buffer."""
         import torch
@@ -673,6 +694,131 @@ def batch_align(scans, submaps, method=METHOD_GICP, guesses=None, device=0, stre
                             g.ctypes.data_as(C.c_void_p) if g is not None else None, int(pair_id0), recs,
                             C.c_void_p(records_dev) if records_dev else None))
     return [recs[i] for i in range(n)]
+
+
+def _batch_params(method, max_iterations, transformation_epsilon, max_correspondence_distance, k_correspondences, ndt_resolution, ndt_step_size,
+                  submap_leaf, fitness_max_range, n_workers, max_optimizer_iterations, euclidean_fitness_epsilon):
+    return BatchParams(method=method, max_iterations=max_iterations, transformation_epsilon=transformation_epsilon,
+                       max_correspondence_distance=max_correspondence_distance, k_correspondences=k_correspondences,
+                       ndt_resolution=ndt_resolution, ndt_step_size=ndt_step_size, submap_leaf=submap_leaf,
+                       fitness_max_range=fitness_max_range, n_workers=n_workers, max_optimizer_iterations=max_optimizer_iterations,
+                       euclidean_fitness_epsilon=euclidean_fitness_epsilon)
+
+
+def partition_pairs(sizes, rank, world):
+    """lgs_batch_partition: the pair indices rank `rank` of `world` verifies (descending size, dealt round-robin)."""
+    L = _lib.load()
+    sz = np.ascontiguousarray(sizes, np.int64)
+    out = np.empty(max(sz.size, 1), np.int32)
+    n = C.c_int64()
+    check(L.lgs_batch_partition(sz.ctypes.data_as(C.c_void_p), int(sz.size), int(rank), int(world), out.ctypes.data_as(C.c_void_p), int(out.size), C.byref(n)))
+    return out[: n.value].tolist()
+
+
+def _prefer_bundled_nccl():
+    """liblgs_b200.so binds NCCL at run time (dlopen).  In a Python process that also imports PyTorch the copy PyTorch ships
+    (site-packages/nvidia/nccl) must be the one that gets loaded: a different libnccl.so.2 loaded first would satisfy
+    PyTorch's own dependency by soname and miss symbols it needs.  Points LGS_NCCL_LIB at the bundled file if there is one."""
+    import os
+    if os.environ.get("LGS_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["LGS_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+class Comm:
+    """NCCL communicator of the distributed loop-closure batch (lgs_comm): one process per GPU.  Rank 0 draws the 128-byte
+    unique id (Comm.unique_id()) and the caller carries it to the other ranks (Comm.from_torch_distributed does that with a
+    torch.distributed broadcast); the gather of the records is then a single ncclAllGather issued by the C++ host."""
+
+    def __init__(self, unique_id, rank, world, device):
+        _prefer_bundled_nccl()
+        self._L = _lib.load()
+        idb = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert idb.size == 128
+        h = C.c_void_p()
+        check(self._L.lgs_comm_init_rank(idb.ctypes.data_as(C.c_void_p), int(rank), int(world), int(device), C.byref(h)))
+        self._h = h
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+
+    @staticmethod
+    def unique_id():
+        _prefer_bundled_nccl()
+        idb = np.zeros(128, np.uint8)
+        check(_lib.load().lgs_comm_get_unique_id(idb.ctypes.data_as(C.c_void_p)))
+        return idb.tobytes()
+
+    @classmethod
+    def from_torch_distributed(cls, device):
+        """One communicator per rank of the default torch.distributed process group (the id travels by broadcast)."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return cls(cls.unique_id(), 0, 1, device)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = "cuda:%d" % device if dist.get_backend() == "nccl" else "cpu"
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(bytes(t.cpu().numpy().tobytes()), rank, world, device)
+
+    @property
+    def nccl_version(self):
+        v = C.c_int32()
+        check(self._L.lgs_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lgs_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _dist_info(info):
+    return dict(rank=info.rank, world=info.world, n_local=info.n_local, n_received=info.n_received, gather_bytes=info.gather_bytes,
+                verify_ms=info.verify_ms, gather_ms=info.gather_ms)
+
+
+def batch_align_dist(comm, scans, submaps, method=METHOD_GICP, guesses=None, max_iterations=100, transformation_epsilon=0.01,
+                     max_correspondence_distance=2.0, k_correspondences=20, ndt_resolution=1.0, ndt_step_size=0.1, submap_leaf=0.5, fitness_max_range=-1.0,
+                     n_workers=0, max_optimizer_iterations=0, euclidean_fitness_epsilon=0.0, sizes=None):
+    """lgs_batch_align_dist (collective): every rank passes the same pair list; entries of scans / submaps this rank does not
+    own may be None when `sizes` = [(n_scan, n_submap), ...] is given.  Returns (all records, info dict)."""
+    L = _lib.load()
+    n = len(scans)
+    assert len(submaps) == n
+    sc = [None if s is None else np.ascontiguousarray(s, np.float32) for s in scans]
+    sm = [None if s is None else np.ascontiguousarray(s, np.float32) for s in submaps]
+    sp = (C.c_void_p * max(n, 1))(*[None if s is None else s.ctypes.data for s in sc])
+    mp = (C.c_void_p * max(n, 1))(*[None if s is None else s.ctypes.data for s in sm])
+    if sizes is None:
+        sizes = [(a.shape[0], b.shape[0]) for a, b in zip(sc, sm)]
+    ns = (C.c_int64 * max(n, 1))(*[int(a) for a, _ in sizes])
+    nm = (C.c_int64 * max(n, 1))(*[int(b) for _, b in sizes])
+    g = None
+    if guesses is not None:
+        g = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).reshape(4, 4).ravel(order="F") for T in guesses]))
+    bp = _batch_params(method, max_iterations, transformation_epsilon, max_correspondence_distance, k_correspondences, ndt_resolution, ndt_step_size,
+                       submap_leaf, fitness_max_range, n_workers, max_optimizer_iterations, euclidean_fitness_epsilon)
+    recs = (AlignResult * max(n, 1))()
+    info = BatchDistInfo()
+    check(L.lgs_batch_align_dist(comm._h, C.byref(bp), n, sp, ns, mp, nm, 16, g.ctypes.data_as(C.c_void_p) if g is not None else None, recs, C.byref(info)))
+    return [recs[i] for i in range(n)], _dist_info(info)
 
 
 def batch_release():

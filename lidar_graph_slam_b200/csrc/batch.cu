@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "dist.cuh"
 #include "gicp.cuh"
 #include "keyframes.cuh"
 #include "voxel_common.cuh"
@@ -38,6 +39,10 @@ struct BatchShared {
   const int32_t* scan_ids = nullptr;
   const int32_t* center_ids = nullptr;
   int32_t search_key_frame_num = 0;
+  // record sinks: pair i's record goes to records[i] (host) and, when rec_dev is set, is also stored at rec_dev[i] by the
+  // pair's last kernel (its getFitnessScore reduction): rec_dev is the NCCL send buffer of lgs_batch_align*_dist
+  lgs_align_result* rec_dev = nullptr;
+  const int32_t* pair_ids = nullptr;  // global ids of the local pairs (distributed batch); otherwise pair_id0 + i
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
   std::mutex err_mu;
@@ -102,6 +107,15 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     scan_dev = scan_buf->as<float>();
   }
   const float* guess = S->guesses ? S->guesses + 16 * i : nullptr;
+  const int32_t pair_id = S->pair_ids ? S->pair_ids[i] : S->pair_id0 + static_cast<int32_t>(i);
+  // arms the one-shot record sink of this context: the fitness kernel that follows completes and stores the record
+  auto arm_record = [&]() {
+    rec.pair_id = pair_id;
+    if (S->rec_dev) {
+      ctx->rec_out_proto = rec;
+      ctx->rec_out_dev = S->rec_dev + i;
+    }
+  };
   const double max_range = bp.fitness_max_range > 0 ? bp.fitness_max_range : std::numeric_limits<double>::max();
   if (bp.method == LGS_METHOD_GICP) {
     LGS_TRY(lgs_gicp_set_target_dev(gicp, tgt_dev, n_tgt));
@@ -113,6 +127,7 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     clk.lap(3);
     LGS_TRY(lgs_gicp_align(gicp, guess, &rec, nullptr));
     clk.lap(4);
+    arm_record();
     LGS_TRY(lgs_gicp_fitness(gicp, max_range, &rec.fitness));
     clk.lap(5);
   } else if (bp.method == LGS_METHOD_ICP) {
@@ -125,6 +140,7 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     clk.lap(3);
     LGS_TRY(lgs_icp_align(icp, guess, &rec, nullptr));
     clk.lap(4);
+    arm_record();
     LGS_TRY(lgs_icp_fitness(icp, max_range, &rec.fitness));
     clk.lap(5);
   } else if (bp.method == LGS_METHOD_GICP_OMP) {
@@ -137,6 +153,7 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     clk.lap(3);
     LGS_TRY(lgs_gicp_omp_align(gomp, guess, &rec, nullptr));
     clk.lap(4);
+    arm_record();
     LGS_TRY(lgs_gicp_omp_fitness(gomp, max_range, &rec.fitness));
     clk.lap(5);
   } else {
@@ -149,13 +166,14 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     clk.lap(3);
     LGS_TRY(lgs_ndt_align(ndt, guess, &rec, nullptr));
     clk.lap(4);
+    arm_record();
     LGS_TRY(lgs_ndt_fitness(ndt, max_range, &rec.fitness));
     clk.lap(5);
   }
   if (clk.on)
     fprintf(stderr, "[lgs batch] pair %lld: upload %.2f  voxelgrid %.2f  set_target %.2f  set_source %.2f  align %.2f  fitness %.2f ms (target %lld pts)\n",
             static_cast<long long>(i), clk.ms[0], clk.ms[1], clk.ms[2], clk.ms[3], clk.ms[4], clk.ms[5], static_cast<long long>(n_tgt));
-  rec.pair_id = S->pair_id0 + static_cast<int32_t>(i);
+  rec.pair_id = pair_id;
   return LGS_OK;
 }
 
@@ -280,7 +298,7 @@ void worker(BatchShared* S) {
 
 }  // namespace
 
-static int run_batch(BatchShared& S, void* cuda_stream, void* records_dev);
+static int run_batch(BatchShared& S);
 
 extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
                                const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
@@ -301,7 +319,9 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
   S.guesses = guesses16;
   S.pair_id0 = pair_id0;
   S.records = records;
-  return run_batch(S, cuda_stream, records_dev);
+  S.rec_dev = static_cast<lgs_align_result*>(records_dev);
+  (void)cuda_stream;  // every worker synchronises its own stream before the call returns: records_dev is complete
+  return run_batch(S);
 }
 
 // The same verification with both clouds of every pair taken from the device-resident key-frame array: pair i aligns key
@@ -334,10 +354,12 @@ extern "C" int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, c
   S.scan_ids = scan_ids;
   S.center_ids = center_ids;
   S.search_key_frame_num = search_key_frame_num;
-  return run_batch(S, cuda_stream, records_dev);
+  S.rec_dev = static_cast<lgs_align_result*>(records_dev);
+  (void)cuda_stream;
+  return run_batch(S);
 }
 
-static int run_batch(BatchShared& S, void* cuda_stream, void* records_dev) {
+static int run_batch(BatchShared& S) {
   const lgs_batch_params* params = S.bp;
   const int64_t n_pairs = S.n_pairs;
   const int device = S.device;
@@ -357,13 +379,131 @@ static int run_batch(BatchShared& S, void* cuda_stream, void* records_dev) {
     set_error("lgs_batch_align: %s", S.err.c_str());
     return S.failed.load();
   }
-  if (records_dev && n_pairs) {
-    LGS_CUDA(cudaSetDevice(device));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    LGS_CUDA(cudaMemcpyAsync(records_dev, records, static_cast<size_t>(n_pairs) * sizeof(lgs_align_result), cudaMemcpyHostToDevice, st));
-    LGS_CUDA(cudaStreamSynchronize(st));
+  return LGS_OK;
+}
+
+// ---- the batch over the GPUs of a box -----------------------------------------------------------
+namespace {
+
+// partition -> local verification with the send buffer as record sink -> one ncclAllGather -> records_all[pair id]
+template <typename FillLocal>
+int run_dist(lgs_comm* comm, int device, const int64_t* sizes, int64_t n_pairs, lgs_align_result* records_all, lgs_batch_dist_info* info, BatchShared& S,
+             FillLocal fill_local) {
+  if (device != comm->device) {
+    set_error("the communicator lives on device %d, the batch on device %d", comm->device, device);
+    return LGS_ERR_INVALID;
+  }
+  LGS_CUDA(cudaSetDevice(device));
+  std::vector<int32_t> mine;
+  partition_pairs(sizes, n_pairs, comm->rank, comm->world, &mine);
+  const int64_t cap = std::max<int64_t>(1, (n_pairs + comm->world - 1) / comm->world);
+  LGS_TRY(comm->send.reserve(static_cast<size_t>(cap) * sizeof(lgs_align_result)));
+  cudaStream_t st = nullptr;  // the gather runs on the legacy default stream: it orders after the memset below and,
+                              // because every worker synchronises its own stream before returning, after the records
+  LGS_CUDA(cudaMemsetAsync(comm->send.p, 0xFF, static_cast<size_t>(cap) * sizeof(lgs_align_result), st));  // pair_id = -1: unused slot
+  LGS_CUDA(cudaStreamSynchronize(st));
+  std::vector<lgs_align_result> local(mine.size());
+  S.n_pairs = static_cast<int64_t>(mine.size());
+  S.records = local.data();
+  S.rec_dev = comm->send.as<lgs_align_result>();
+  S.pair_ids = mine.data();
+  S.pair_id0 = 0;
+  S.device = device;
+  fill_local(mine);
+  const auto t0 = std::chrono::steady_clock::now();
+  LGS_TRY(run_batch(S));
+  const auto t1 = std::chrono::steady_clock::now();
+  int64_t got = 0;
+  LGS_TRY(comm_all_gather_records(comm, st, cap, n_pairs, records_all, &got));
+  const auto t2 = std::chrono::steady_clock::now();
+  if (info) {
+    info->rank = comm->rank;
+    info->world = comm->world;
+    info->n_local = static_cast<int64_t>(mine.size());
+    info->n_received = got;
+    info->gather_bytes = cap * comm->world * static_cast<int64_t>(sizeof(lgs_align_result));
+    info->verify_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    info->gather_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  }
+  if (got != n_pairs) {
+    set_error("the gather returned %lld of %lld records", static_cast<long long>(got), static_cast<long long>(n_pairs));
+    return LGS_ERR_STATE;
   }
   return LGS_OK;
+}
+
+}  // namespace
+
+extern "C" int lgs_batch_align_keyframes_dist(lgs_keyframes* kf, lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs,
+                                              const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
+                                              const float* guesses16, lgs_align_result* records_all, lgs_batch_dist_info* info) {
+  LGS_REQUIRE(kf && comm && params && (records_all || n_pairs == 0), "null argument");
+  LGS_REQUIRE(n_pairs >= 0 && n_pairs < (int64_t(1) << 31) && search_key_frame_num >= 0, "count out of range");
+  LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
+  LGS_REQUIRE(n_pairs == 0 || (scan_ids && center_ids), "null pair arrays");
+  const int64_t count = keyframes_count(kf);
+  std::vector<int64_t> sizes(static_cast<size_t>(n_pairs));
+  for (int64_t i = 0; i < n_pairs; i++) {
+    LGS_REQUIRE(scan_ids[i] >= 0 && scan_ids[i] < count && center_ids[i] >= 0 && center_ids[i] < count, "key frame id out of range");
+    int64_t sz = keyframes_points(kf, scan_ids[i]);
+    for (int64_t id = std::max<int64_t>(0, static_cast<int64_t>(center_ids[i]) - search_key_frame_num);
+         id <= std::min<int64_t>(count - 1, static_cast<int64_t>(center_ids[i]) + search_key_frame_num); id++)
+      sz += keyframes_points(kf, id);
+    sizes[static_cast<size_t>(i)] = sz;
+  }
+  LGS_TRY(keyframes_wait_resident(kf));
+  BatchShared S;
+  S.bp = params;
+  S.scans = nullptr;
+  S.n_scan = nullptr;
+  S.submaps = nullptr;
+  S.n_submap = nullptr;
+  S.stride = 16;
+  S.kf = kf;
+  S.search_key_frame_num = search_key_frame_num;
+  std::vector<int32_t> sid, cid;
+  std::vector<float> gl;
+  return run_dist(comm, keyframes_device(kf), sizes.data(), n_pairs, records_all, info, S, [&](const std::vector<int32_t>& mine) {
+    for (int32_t i : mine) {
+      sid.push_back(scan_ids[i]);
+      cid.push_back(center_ids[i]);
+      if (guesses16) gl.insert(gl.end(), guesses16 + 16 * static_cast<size_t>(i), guesses16 + 16 * static_cast<size_t>(i) + 16);
+    }
+    S.scan_ids = sid.data();
+    S.center_ids = cid.data();
+    S.guesses = guesses16 ? gl.data() : nullptr;
+  });
+}
+
+extern "C" int lgs_batch_align_dist(lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans, const int64_t* n_scan,
+                                    const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes, const float* guesses16,
+                                    lgs_align_result* records_all, lgs_batch_dist_info* info) {
+  LGS_REQUIRE(comm && params && (records_all || n_pairs == 0), "null argument");
+  LGS_REQUIRE(n_pairs >= 0 && n_pairs < (int64_t(1) << 31), "count out of range");
+  LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
+  LGS_REQUIRE(n_pairs == 0 || (scans && n_scan && submaps && n_submap), "null pair arrays");
+  std::vector<int64_t> sizes(static_cast<size_t>(n_pairs));
+  for (int64_t i = 0; i < n_pairs; i++) sizes[static_cast<size_t>(i)] = n_scan[i] + n_submap[i];
+  BatchShared S;
+  S.bp = params;
+  S.stride = stride_bytes;
+  std::vector<const void*> ls, lm;
+  std::vector<int64_t> lns, lnm;
+  std::vector<float> gl;
+  return run_dist(comm, comm->device, sizes.data(), n_pairs, records_all, info, S, [&](const std::vector<int32_t>& mine) {
+    for (int32_t i : mine) {
+      ls.push_back(scans[i]);
+      lm.push_back(submaps[i]);
+      lns.push_back(n_scan[i]);
+      lnm.push_back(n_submap[i]);
+      if (guesses16) gl.insert(gl.end(), guesses16 + 16 * static_cast<size_t>(i), guesses16 + 16 * static_cast<size_t>(i) + 16);
+    }
+    S.scans = ls.data();
+    S.n_scan = lns.data();
+    S.submaps = lm.data();
+    S.n_submap = lnm.data();
+    S.guesses = guesses16 ? gl.data() : nullptr;
+  });
 }
 
 extern "C" void lgs_batch_release(void) {

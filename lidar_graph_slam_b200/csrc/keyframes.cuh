@@ -13,6 +13,7 @@ int keyframes_assemble_into(const lgs_keyframes* kf, lgs_ctx* ctx, const int32_t
 // everything pushed so far is resident (the pushes are asynchronous on the array's own stream)
 int keyframes_wait_resident(const lgs_keyframes* kf);
 int64_t keyframes_count(const lgs_keyframes* kf);
+int64_t keyframes_points(const lgs_keyframes* kf, int64_t id);  // points of key frame id
 int keyframes_device(const lgs_keyframes* kf);
 
 }  // namespace lgs

@@ -175,10 +175,18 @@ constexpr int kFitWarps = kFitBlock / 32;
 struct FitTransform {
   float m[16];  // column-major
 };
+struct FitRecord {  // loop-closure batch: the pair's record, completed with the fitness and stored by the last block
+  lgs_align_result* dst;
+  lgs_align_result proto;
+};
+
+__global__ void record_write_kernel(const FitRecord rec) {
+  if (threadIdx.x == 0) *rec.dst = rec.proto;
+}
 
 __global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const float4* __restrict__ src, int n, const FitTransform Tp,
                                                               double max_range, double* __restrict__ partials, double* __restrict__ result,
-                                                              unsigned* __restrict__ counter, const Mailbox mb) {
+                                                              unsigned* __restrict__ counter, const Mailbox mb, const FitRecord rec) {
   __shared__ float T[16];
   if (threadIdx.x < 16) T[threadIdx.x] = Tp.m[threadIdx.x];
   __syncthreads();
@@ -232,14 +240,31 @@ __global__ void __launch_bounds__(kFitBlock) nn_fitness_kernel(NNView v, const f
       *counter = 0;
       mailbox_publish_one(mb, 0, s);  // the host reads sum and count from mapped pinned memory: no D2H copy, no synchronise
       mailbox_publish_one(mb, 1, c);
+      if (rec.dst) {  // same f64 division as the host's (nn_fitness below): the two copies of the record are bit-identical
+        lgs_align_result r = rec.proto;
+        r.fitness = c > 0 ? s / c : 1.7976931348623157e308;
+        *rec.dst = r;
+      }
     }
   }
 }
 
 int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_src, const float* T16, double max_range, double* fitness) {
   *fitness = std::numeric_limits<double>::max();
-  if (n_src == 0 || index.n == 0) return LGS_OK;
   cudaStream_t st = ctx->stream;
+  FitRecord rec;
+  rec.dst = ctx->rec_out_dev;
+  rec.proto = ctx->rec_out_proto;
+  ctx->rec_out_dev = nullptr;  // one-shot
+  if (n_src == 0 || index.n == 0) {
+    if (rec.dst) {
+      rec.proto.fitness = *fitness;
+      record_write_kernel<<<1, 32, 0, st>>>(rec);
+      ctx->launches++;
+      LGS_CUDA(cudaGetLastError());
+    }
+    return LGS_OK;
+  }
   const int grid = std::max(1, std::min(grid_for(n_src, kFitWarps), kNumSMs * 8));
   LGS_TRY(ctx->tmp[0].reserve(static_cast<size_t>(grid) * 16 + 256));
   double* partials = ctx->tmp[0].as<double>();
@@ -250,7 +275,7 @@ int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
   LGS_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-  nn_fitness_kernel<<<grid, kFitBlock, 0, st>>>(index.view(), src, static_cast<int>(n_src), Tp, max_range, partials, result, counter, mb);
+  nn_fitness_kernel<<<grid, kFitBlock, 0, st>>>(index.view(), src, static_cast<int>(n_src), Tp, max_range, partials, result, counter, mb, rec);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   double h[2];

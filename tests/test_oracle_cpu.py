@@ -449,6 +449,54 @@ def test_pair_partitioning_balanced():
         assert max(loads) - min(loads) <= max(sizes)
 
 
+def test_c_partition_equals_python_partition():
+    """lgs_batch_partition (the rule lgs_batch_align*_dist applies inside the C++ host) is pure host arithmetic: it runs
+    without a GPU and deals the pairs exactly like distributed.partition_pairs."""
+    from lidar_graph_slam_b200 import api
+    from lidar_graph_slam_b200.distributed import partition_pairs
+    rs = np.random.RandomState(3)
+    for n in (0, 1, 7, 103, 4096):
+        sizes = rs.randint(1, 60, size=n)  # many ties: the index must break them
+        for world in (1, 2, 3, 8):
+            parts = [api.partition_pairs(sizes, r, world) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            for r in range(world):
+                assert parts[r] == partition_pairs(sizes.tolist(), r, world)
+
+
+def _gloo_id_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from lidar_graph_slam_b200 import api
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(api.Comm.unique_id()), dtype=torch.uint8))  # ncclGetUniqueId needs no GPU
+    dist.broadcast(t, 0)
+    sizes = [10 + (i * 37) % 91 for i in range(29)]
+    q.put((rank, bytes(t.numpy().tobytes()), api.partition_pairs(sizes, rank, world)))
+    dist.destroy_process_group()
+
+
+def test_comm_bootstrap_world2_gloo():
+    """Host side of the N>1 path on CPU: rank 0 draws the NCCL unique id through the C-ABI, the id reaches rank 1 over a
+    torch.distributed (gloo) broadcast as Comm.from_torch_distributed does it, and the two ranks' C-side partitions tile
+    the candidate list.  (ncclCommInitRank itself needs GPUs: tests/test_gpu_dist.py.)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_id_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert got[0][1] == got[1][1] and len(got[0][1]) == 128 and any(got[0][1])
+    assert sorted(got[0][2] + got[1][2]) == list(range(29))
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
