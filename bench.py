@@ -13,8 +13,10 @@ under "loop_closure".
   value  aligns/s, sweeps already resident in HBM (set_source_dev + align), per-step CUDA events, L2 flushed
          between steps outside the event pairs
   e2e    aligns/s through the reference-facing call sequence with HOST buffers: setInputSource(pinned host sweep)
-         -> align -> getFinalTransformation, H2D of the sweep and D2H of the result inside the timed region
-  roofline  the dominant kernel (ndt_derivatives_kernel<true>): algorithmic bytes / CUDA-event duration
+         -> align(aligned cloud, guess) -> getFinalTransformation; H2D of the sweep and D2H of the aligned cloud and of
+         the result inside the timed region
+  roofline  the dominant kernel (ndt_align_kernel: one launch per align): algorithmic bytes of all its evaluations /
+         its CUDA-event duration, timed live in the timed region
   cpu_baseline  the oracle (CPU restatement of the reference's OpenMP path) on this box's host cores, bounded sample
 
 --impl reference times the reference's CPU path (the oracle port: the reference cannot be compiled here) on the
@@ -325,7 +327,7 @@ def gicp_odometry_bench(device, stream, ctx, n_sweeps=8, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=240)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 4096),
@@ -383,9 +385,13 @@ def main():
         ndt.setInputSource(sweeps_dev[i % len(sweeps_dev)])
         ndt.align(guesses[i % len(guesses)])
 
+    aligned_pinned = torch.empty((max(len(x) for x in sweeps), 4), dtype=torch.float32).pin_memory()
+
     def step_host(i):
+        # the reference's call sequence (LSM:162-172): setInputSource(host cloud) -> align(aligned_cloud, guess) ->
+        # getFinalTransformation; the aligned cloud comes back to the host like the output argument of pcl's align
         ndt.setInputSource(sweeps_pinned[i % len(sweeps_pinned)].numpy())
-        ndt.align(guesses[i % len(guesses)])
+        ndt.align(guesses[i % len(guesses)], want_output=True, out=aligned_pinned.numpy())
         return ndt.getFinalTransformation()
 
     def timed(fn, steps, warm):
@@ -399,7 +405,8 @@ def main():
         l0 = ctx.launch_count
         evals = 0
         for i in range(steps):
-            flush.zero_()  # L2 flush, outside the event pair
+            flush.zero_()  # L2 flush, outside the event pair ...
+            torch.cuda.current_stream().synchronize()  # ... and complete before the step's host-side set-up starts
             starts[i].record(stream)
             fn(i)
             stops[i].record(stream)
@@ -407,34 +414,42 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-        return ms, ctx.launch_count - l0, evals
+        per = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
+        return per, ctx.launch_count - l0, evals
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, evals_dev = timed(step_dev, K, W)
-    ms_host, _, evals_host = timed(step_host, K, W)
+    # the dominant kernel is timed live in the timed region: CUDA events on the launching stream around every
+    # ndt_align_kernel launch (one launch = one whole align: all its evaluations and the optimiser between them)
+    ndt.profile(2)
+    per_dev, launches, evals_dev = timed(step_dev, K, W)
+    prof = ndt.profile(0)
+    per_host, _, evals_host = timed(step_host, K, W)
     clocks = sampler.stop() if rank == 0 else None
+    ms_dev, ms_host = float(per_dev.sum()), float(per_host.sum())
 
     # accuracy sanity of the timed workload (not a parity test: those live in tests/)
     step_dev(0)
     E = np.linalg.inv(poses[0]) @ ndt.getFinalTransformation().astype(np.float64)
     t_err = float(np.linalg.norm(E[:3, 3]))
 
-    # per-kernel timing pass for the roofline (CUDA events around every evaluation launch, same stream)
-    ndt.profile(True)
-    for i in range(min(K, 20)):
-        step_dev(i)
-    prof = ndt.profile(False)
+    # roofline of the dominant kernel.  Algorithmic bytes of one evaluation: point float4 + 7 (key, slot)
+    # probes per point + one 40-byte voxel record per accepted (point, voxel) term; a launch runs all evaluations of an align
     n_src = prof["n_source"]
-    terms = prof["terms_last_eval"]
-    hbar = terms / max(n_src, 1)
-    alg_bytes = n_src * (16 + 7 * 8) + 40.0 * terms  # point float4 + 7 (key,slot) probes + h voxel records of 40 B
-    kern_ms = prof["hess_ms"] / max(prof["hess_launches"], 1)
+    n_launch = max(prof["align_launches"], 1)
+    alg_bytes = (prof["evaluations"] * n_src * (16 + 7 * 8) + 40.0 * prof["terms"]) / n_launch
+    kern_ms = prof["align_ms"] / n_launch
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    hbar = prof["terms"] / max(prof["evaluations"] * n_src, 1)
     peak, peak_src = measured_peak_hbm()
     traffic, traffic_src = ncu_traffic()
+
+    # the evaluation body alone, one launch per evaluation (the host steps the optimiser): what a single evaluation costs
+    ndt.profile(1)
+    for i in range(min(K, 12)):
+        step_dev(i)
+    prof1 = ndt.profile(0)
 
     # max over ranks
     t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device="cuda:%d" % local_rank)
@@ -472,18 +487,25 @@ def main():
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pairs); within an align the 1.9 MB sweep and the voxel table are re-read from L2 by design",
                        "parallelism": "1 sequence per GPU (replicas, no collective)" if world > 1 else "single GPU",
                        "evaluations_per_align": evals_dev / K, "launches_per_align": launches / K,
-                       "evaluator": ("persistent grid: one resident ndt_persistent_kernel serves a run of evaluations, commands and results cross PCIe "
-                                     "through mapped pinned memory (LGS_NDT_PERSISTENT=0 launches one kernel per evaluation); the roofline pass below "
-                                     "times the same evaluation body launched once per evaluation, CUDA events around each launch"),
-                       "target_build_ms": target_build_ms, "pose_error_m": t_err},
+                       "evaluator": ("device-resident align: ONE cooperative launch of ndt_align_kernel per align - the grid evaluates, CTA 0 runs "
+                                     "the Newton / More-Thuente state machine between evaluations, nothing crosses PCIe until the result record "
+                                     "(LGS_NDT_DEVICE_ALIGN=0: the host steps the same machine with one launch per evaluation)"),
+                       "target_build_ms": target_build_ms, "pose_error_m": t_err,
+                       "ms_per_step_spread": {"min": float(per_dev.min()), "median": float(np.median(per_dev)), "max": float(per_dev.max()),
+                                              "p90": float(np.percentile(per_dev, 90))},
+                       "e2e_ms_per_step_spread": {"min": float(per_host.min()), "median": float(np.median(per_host)), "max": float(per_host.max())}},
             "e2e": {"value": total_steps / (ms_host_max * 1e-3), "unit": "aligns/s", "h2d_bytes_per_step": int(n_src) * 16 + 64,
-                    "d2h_bytes_per_step": int(round(evals_host / K * 44 * 8))},
+                    "d2h_bytes_per_step": int(n_src) * 16 + 32 * 16,
+                    "call": "setInputSource(pinned host sweep) -> align(aligned cloud to pinned host memory, guess) -> getFinalTransformation (LSM:162-172)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "ndt_derivatives_kernel<true>", "kernel_ms": kern_ms, "launches_timed": prof["hess_launches"],
+                         "kernel": "ndt_align_kernel<true> (one launch = one align: %.2f derivative evaluations + the optimiser between them)" % (prof["evaluations"] / n_launch),
+                         "kernel_ms": kern_ms, "launches_timed": prof["align_launches"], "timed": "live, CUDA events on the launching stream around every launch of the timed region",
                          "algorithmic_bytes": alg_bytes, "h_bar": hbar, "peak_source": peak_src,
-                         "other_kernels_ms": {"ndt_derivatives_kernel<false>": prof["grad_ms"] / max(prof["grad_launches"], 1),
-                                              "ndt_hessian_f64_kernel": prof["h64_ms"] / max(prof["h64_launches"], 1)}},
+                         "single_evaluation_kernels_ms": {"ndt_derivatives_kernel<0> (score + g + H)": prof1["hess_ms"] / max(prof1["hess_launches"], 1),
+                                                          "ndt_derivatives_kernel<1> (score + g)": prof1["grad_ms"] / max(prof1["grad_launches"], 1),
+                                                          "ndt_derivatives_kernel<2> (f64 Hessian)": prof1["h64_ms"] / max(prof1["h64_launches"], 1),
+                                                          "note": "the same evaluation body launched once per evaluation (host-stepped optimiser), separate pass"}},
             "cpu_baseline": cpu, "clocks": clocks, "loop_closure": loop, "gicp_odometry": gicp_odo,
         }
         print(json.dumps(line), flush=True)

@@ -212,6 +212,12 @@ int lgs_ndt_derivatives(lgs_ndt* ndt, const float* T16, const double* p6, int32_
 /* static convertTransform(x, trans) (NDT.h:214-238): (x, y, z, roll, pitch, yaw) -> column-major f32 4x4.  Host only. */
 int lgs_ndt_convert_transform(const double* x6, float* T16);
 int lgs_ndt_profile(lgs_ndt* ndt, int32_t enable, double* out8);
+/* measurement hook: where the last device-resident align (one ndt_align_kernel launch) spent its time, as SM cycles of
+ * CTA 0 summed over the align's evaluations: out16 = {evaluating, waiting for the other CTAs, adding the per-CTA rows,
+ * optimiser step, publishing the next command, whole kernel, 0, 0; then the optimiser step in detail: More-Thuente /
+ * exit rules (thread 0), 6x6 elimination (warp 0), Newton post-processing (thread 0), sines / cosines, transform +
+ * angular tables, 0, 0, 0} */
+int lgs_ndt_align_breakdown(lgs_ndt* ndt, double* out16);
 
 /* ------------------------------------------------------------------------------------------- */
 /* GICP: fast_gicp::FastGICP over LsqRegistration (FG.h:48-70, LSQ.h:48-60)                       */

@@ -93,6 +93,7 @@ SYMBOLS = {
     "lgs_ndt_derivatives": (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_f64), _vp, _vp]),
     "lgs_ndt_convert_transform": (_i32, [_vp, _vp]),
     "lgs_ndt_profile": (_i32, [_vp, _i32, _vp]),
+    "lgs_ndt_align_breakdown": (_i32, [_vp, _vp]),
     "lgs_gicp_create": (_i32, [_vp, C.POINTER(_vp)]),
     "lgs_gicp_destroy": (None, [_vp]),
     "lgs_gicp_set_correspondence_randomness": (_i32, [_vp, _i32]),

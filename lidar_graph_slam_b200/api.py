@@ -291,11 +291,15 @@ class _Registration:
     def setInputSource(self, cloud):
         self._ns = self._set_cloud("source", cloud)
 
-    def align(self, guess=None, want_output=False):
-        """Runs the registration.  Returns the aligned source cloud when want_output, else None."""
+    def align(self, guess=None, want_output=False, out=None):
+        """Runs the registration (pcl::Registration::align(output, guess)).  Returns the aligned source cloud when want_output
+        (written into `out`, a C-contiguous float32 (>= n_source, 4) host array, when the caller supplies one), else None."""
         keep, gp = _mat_to_c(guess)
         res = AlignResult()
-        out = np.empty((max(self._ns, 1), 4), np.float32) if want_output else None
+        if want_output and out is None:
+            out = np.empty((max(self._ns, 1), 4), np.float32)
+        if want_output:
+            assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.shape[0] >= self._ns and out.shape[1] == 4
         check(self._fn("align")(self._h, gp, C.byref(res), out.ctypes.data_as(C.c_void_p) if want_output else None))
         self.result = res
         self.final_transformation = _result_T(res)
@@ -364,11 +368,24 @@ class NormalDistributionsTransform(_Registration):
         return s.value
 
     def profile(self, enable):
-        """Measurement hook: returns the per-kernel CUDA-event timings gathered so far and (re)arms / disarms timing."""
+        """Measurement hook: returns the CUDA-event timings gathered so far and (re)arms / disarms timing.  enable = 1 (True):
+        one launch per evaluation (the host steps the optimiser), each launch timed; enable = 2: the device-resident align
+        (one ndt_align_kernel launch per align) timed as a whole.  The returned dict describes the mode that WAS armed."""
+        was = getattr(self, "_profiling", 0)
         out = np.zeros(8)
-        check(self._L.lgs_ndt_profile(self._h, 1 if enable else 0, out.ctypes.data_as(C.c_void_p)))
+        check(self._L.lgs_ndt_profile(self._h, int(enable), out.ctypes.data_as(C.c_void_p)))
+        self._profiling = int(enable)
+        if was == 2:
+            return dict(align_launches=int(out[0]), align_ms=out[1], evaluations=out[2], terms=out[3], terms_last_eval=out[6], n_source=int(out[7]))
         return dict(hess_launches=int(out[0]), hess_ms=out[1], grad_launches=int(out[2]), grad_ms=out[3], h64_launches=int(out[4]),
                     h64_ms=out[5], terms_last_eval=out[6], n_source=int(out[7]))
+
+    def align_breakdown(self):
+        """SM cycles CTA 0 spent per phase of the last device-resident align (lgs_ndt_align_breakdown)."""
+        out = np.zeros(16)
+        check(self._L.lgs_ndt_align_breakdown(self._h, out.ctypes.data_as(C.c_void_p)))
+        return dict(evaluate=out[0], wait_grid=out[1], add_rows=out[2], optimiser=out[3], publish=out[4], total=out[5],
+                    opt_decide=out[8], opt_solve=out[9], opt_after_solve=out[10], opt_trig=out[11], opt_pose_tables=out[12], raw=out.tolist())
 
     # parity hooks -------------------------------------------------------------------------------
     def grid_info(self):

@@ -362,8 +362,6 @@ extern "C" int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, c
 static int run_batch(BatchShared& S) {
   const lgs_batch_params* params = S.bp;
   const int64_t n_pairs = S.n_pairs;
-  const int device = S.device;
-  lgs_align_result* records = S.records;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
     set_error("no CUDA device available; this library has no CPU fallback");

@@ -231,6 +231,7 @@ __device__ __forceinline__ void block_reduce_and_finish(double (&acc)[K], double
 }  // namespace lgs
 
 #include "persist.cuh"
+#include "ndt_opt.cuh"
 #include "ndt_deriv.cuh"
 
 namespace lgs {
@@ -314,17 +315,15 @@ struct lgs_ndt {
   EvalParams P;
   int evals = 0, trials = 0, hess_recomputes = 0;
   double last_terms = 0;
-  // persistent evaluator (ndt_deriv.cuh): a run of evaluations served by one resident grid, inside lgs_ndt_align only
-  bool allow_session = false, session_active = false, session_broken = false;
-  int session_device = -1;
-  lgs::NdtCommandHost* cmd_host = nullptr;  // mapped pinned memory
-  lgs::DevBuf cmd_dev;
-  unsigned long long cmd_seq = 0;
-  int session_evals = 0, session_launches = 0;
-  double trace_roundtrip_us[3] = {0, 0, 0};
+  // device-resident align (ndt_align_kernel): the hand-over block of the resident grid, and how the last align ran
+  lgs::DevBuf align_dev;
+  int align_launches = 0;      // ndt_align_kernel launches of the last align (1, or 0 when the host stepped the optimiser)
+  double align_trace[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // CTA 0's cycle breakdown of the last device-resident align
+  double terms_total = 0;      // accepted (point, voxel) terms over all evaluations of the last device-resident align
   // optional per-kernel timing (bench.py roofline): CUDA event pairs around each evaluation launch
-  bool profiling = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];
+  int profiling = 0;  // 1: per-evaluation launches timed (host-stepped optimiser), 2: ndt_align_kernel launches timed
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[4];  // modes 0, 1, 2 and whole aligns
+  double prof_align_evals = 0, prof_align_terms = 0;
 };
 
 namespace {
@@ -335,44 +334,11 @@ void identity16(float* T) {
   for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
 }
 
-// Eigen::AngleAxis<float>(angle, Unit{X,Y,Z}).toRotationMatrix(): note (1-c)*1 + c on the axis diagonal
-void angle_axis_unit(float angle, int axis, float* R) {
-  float ax[3] = {0, 0, 0};
-  ax[axis] = 1.0f;
-  const float s = std::sin(angle), c = std::cos(angle);
-  const float sa[3] = {s * ax[0], s * ax[1], s * ax[2]};
-  const float ca[3] = {(1.0f - c) * ax[0], (1.0f - c) * ax[1], (1.0f - c) * ax[2]};
-  float tmp = ca[0] * ax[1];
-  R[1] = tmp - sa[2];
-  R[3] = tmp + sa[2];
-  tmp = ca[0] * ax[2];
-  R[2] = tmp + sa[1];
-  R[6] = tmp - sa[1];
-  tmp = ca[1] * ax[2];
-  R[5] = tmp - sa[0];
-  R[7] = tmp + sa[0];
-  for (int a = 0; a < 3; a++) R[a * 4] = ca[a] * ax[a] + c;
-}
-
-void mul3f(const float* a, const float* b, float* c) {
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) c[i * 3 + j] = (a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j];
-}
-
-// NDT.h:214-231: Translation * AngleAxis(X) * AngleAxis(Y) * AngleAxis(Z) in f32, column-major out
+// NDT.h:214-231 (ndt_opt.cuh holds the arithmetic, shared with the device-resident optimiser)
 void pose_to_matrix(const double x[6], float* T) {
-  float Rx[9], Ry[9], Rz[9], Rxy[9], R[9];
-  angle_axis_unit(static_cast<float>(x[3]), 0, Rx);
-  angle_axis_unit(static_cast<float>(x[4]), 1, Ry);
-  angle_axis_unit(static_cast<float>(x[5]), 2, Rz);
-  mul3f(Rx, Ry, Rxy);
-  mul3f(Rxy, Rz, R);
-  identity16(T);
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) T[c * 4 + r] = R[r * 3 + c];
-  T[12] = static_cast<float>(x[0]);
-  T[13] = static_cast<float>(x[1]);
-  T[14] = static_cast<float>(x[2]);
+  ndtopt::Trig t;
+  ndtopt::trig_of_pose(x, &t);
+  ndtopt::pose_to_matrix(x, t, T);
 }
 
 // p = [translation, eulerAngles(0,1,2)] of an Affine3f (NDT:103-111): rotation() is the polar factor
@@ -418,45 +384,11 @@ void compute_gauss(lgs_ndt* n) {  // NDT:86-93
   n->gauss_d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - n->gauss_d3) / n->gauss_d1);
 }
 
-// computeAngleDerivatives (NDT:288-394)
+// computeAngleDerivatives (NDT:288-394; arithmetic in ndt_opt.cuh)
 void angle_derivatives(const double p[6], EvalParams* P) {
-  double cx, cy, cz, sx, sy, sz;
-  if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
-  if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
-  if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
-  const double J[8][3] = {{(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
-                          {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
-                          {(-sy * cz), sy * sz, cy},
-                          {sx * cy * cz, (-sx * cy * sz), sx * sy},
-                          {(-cx * cy * cz), cx * cy * sz, (-cx * sy)},
-                          {(-cy * sz), (-cy * cz), 0},
-                          {(cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0},
-                          {(sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0}};
-  const double H[15][3] = {{(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy},
-                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy)},
-                           {(cx * cy * cz), (-cx * cy * sz), (cx * sy)},
-                           {(sx * cy * cz), (-sx * cy * sz), (sx * sy)},
-                           {(-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0},
-                           {(cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0},
-                           {(-cy * cz), (cy * sz), (sy)},
-                           {(-sx * sy * cz), (sx * sy * sz), (sx * cy)},
-                           {(cx * sy * cz), (-cx * sy * sz), (-cx * cy)},
-                           {(sy * sz), (sy * cz), 0},
-                           {(-sx * cy * sz), (-sx * cy * cz), 0},
-                           {(cx * cy * sz), (cx * cy * cz), 0},
-                           {(-cy * cz), (cy * sz), 0},
-                           {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},
-                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};
-  for (int r = 0; r < 8; r++)
-    for (int c = 0; c < 3; c++) {
-      P->j_ang_d[r][c] = J[r][c];
-      P->j_ang[r][c] = static_cast<float>(J[r][c]);
-    }
-  for (int r = 0; r < 15; r++)
-    for (int c = 0; c < 3; c++) {
-      P->h_ang_d[r][c] = H[r][c];
-      P->h_ang[r][c] = static_cast<float>(H[r][c]);
-    }
+  ndtopt::Trig t;
+  ndtopt::trig_of_pose(p, &t);
+  ndtopt::angle_tables(t, P->j_ang_d, P->h_ang_d, P->j_ang, P->h_ang);
 }
 
 void fill_offsets(int method, EvalParams* P) {
@@ -522,7 +454,7 @@ int build_grid(lgs_ndt* n) {
   const float leaf[3] = {n->resolution, n->resolution, n->resolution};
   SortedVoxels sv;
   LGS_TRY(build_sorted_voxels(ctx, n->target.as<float4>(), n->n_target, leaf, -1.0, nullptr, nullptr, nullptr, &sv));
-  if (n->n_target == 0 || sv.status == LGS_VG_REFUSED_OVERFLOW) {  // VGC:79-84: grid cleared, every lookup misses
+  if (n->n_target == 0 || sv.n_kept == 0 || sv.status == LGS_VG_REFUSED_OVERFLOW) {  // VGC:79-84: grid cleared, every lookup misses (also: no finite point)
     n->refused = true;
     n->grid_ready = true;
     return LGS_OK;
@@ -570,67 +502,16 @@ int build_grid(lgs_ndt* n) {
   return LGS_OK;
 }
 
-// ---- persistent evaluator sessions (channel and the one-session-per-device rule: persist.cuh) ---------------------
-void send_command(lgs_ndt* n, const NdtPose& pose) { persist_send<kCmdWords>(n->cmd_host, ++n->cmd_seq, &pose); }
-
-void end_session(lgs_ndt* n) {
-  if (!n->session_active) return;
-  NdtPose quit;
-  memset(&quit, 0, sizeof(quit));
-  quit.mode = -1;
-  send_command(n, quit);
-  n->session_active = false;
-  persist_release(n->session_device);
-}
-
-// everything a session needs that may allocate or synchronise happens here, before the grid becomes resident
-int prepare_session(lgs_ndt* n) {
-  if (!n->cmd_host) {
-    void* p = nullptr;
-    LGS_CUDA(cudaHostAlloc(&p, sizeof(NdtCommandHost), cudaHostAllocMapped | cudaHostAllocPortable));
-    memset(p, 0, sizeof(NdtCommandHost));
-    n->cmd_host = static_cast<NdtCommandHost*>(p);
-  }
-  if (!n->cmd_dev.p) {
-    LGS_TRY(n->cmd_dev.reserve(sizeof(NdtCommandDev)));
-    LGS_CUDA(cudaMemsetAsync(n->cmd_dev.p, 0, sizeof(NdtCommandDev), n->ctx->stream));
-  }
-  return LGS_OK;
-}
-
-// one computeDerivatives / computeHessian evaluation.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian
-int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* score, double* g, double* H) {
-  lgs_ctx* ctx = n->ctx;
-  cudaStream_t st = ctx->stream;
-  EvalParams& P = n->P;
-  memcpy(P.T, T, sizeof(float) * 16);
-  if (mode != 2 || p) angle_derivatives(p, &P);
-  P.gauss_d1 = n->gauss_d1;
-  P.gauss_d2 = n->gauss_d2;
-  P.gauss_d2f = static_cast<float>(n->gauss_d2);
-  fill_offsets(n->search, &P);
-  const int K = mode == 0 ? 29 : (mode == 1 ? 8 : 22);
-  if (score) *score = 0;
-  if (g) std::fill(g, g + 6, 0.0);
-  if (H) std::fill(H, H + 36, 0.0);
-  if (mode == 2) n->hess_recomputes++; else n->evals++;
-  if (n->n_source == 0 || n->refused || n->n_valid == 0) return LGS_OK;
-  const int grid = eval_grid(n->n_source);
-  LGS_TRY(n->partials.reserve(static_cast<size_t>(std::max(grid, kNumSMs)) * kNumAcc * sizeof(double)));
-  if (!n->result.p) {
-    LGS_TRY(n->result.reserve(kNumAcc * sizeof(double) + 64));
-    LGS_CUDA(cudaMemsetAsync(n->result.p, 0, kNumAcc * sizeof(double) + 64, st));
-  }
-  double* result = n->result.as<double>();
-  unsigned* counter = reinterpret_cast<unsigned*>(result + kNumAcc);
-  CellTable ct = make_cell_table(n);
-  const float4* src = n->source.as<float4>();
-  const int ns = static_cast<int>(n->n_source);
-  Mailbox mb;
-  LGS_TRY(mailbox_next(ctx, &mb));
-  static bool smem_opt_in_dev[64] = {};  // > 48 KB of shared memory per CTA needs the opt-in attribute (once per device: function attributes live in the device's context)
-  bool& smem_opt_in = smem_opt_in_dev[ctx->device & 63];
-  if (!smem_opt_in) {
+// one-time (per device) opt-in for > 48 KB of dynamic shared memory + the co-residency check of the align grid
+struct DeviceCaps {
+  bool ready = false;
+  int num_sms = 0;
+  int align_ctas_per_sm[2] = {0, 0};  // ndt_align_kernel<D7 = false / true>
+};
+int device_caps(lgs_ctx* ctx, const DeviceCaps** out) {
+  static DeviceCaps caps[64];
+  DeviceCaps& c = caps[ctx->device & 63];
+  if (!c.ready) {
     const int smem = static_cast<int>(sizeof(DerivSmem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -638,95 +519,78 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     LGS_CUDA(cudaFuncSetAttribute(ndt_derivatives_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LGS_CUDA(cudaFuncSetAttribute(ndt_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_opt_in = true;
+    LGS_CUDA(cudaFuncSetAttribute(ndt_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaFuncSetAttribute(ndt_align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LGS_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    int coop = 0;
+    LGS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (coop) {
+      LGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.align_ctas_per_sm[0], ndt_align_kernel<false>, kDerivThreads, sizeof(DerivSmem)));
+      LGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.align_ctas_per_sm[1], ndt_align_kernel<true>, kDerivThreads, sizeof(DerivSmem)));
+    }
+    c.ready = true;
   }
-  // ---- persistent evaluator: every evaluation of an align, full-size grids only
-  const bool want_session = n->allow_session && !n->profiling && !n->session_broken && persist_env_enabled() && ns >= 32 * kNumSMs;
-  if (!want_session) end_session(n);
-  if (want_session && !n->session_active) {
-    LGS_TRY(prepare_session(n));
-    if (persist_try_acquire(ctx->device)) {
-      void* dv = nullptr;
-      LGS_CUDA(cudaHostGetDevicePointer(&dv, n->cmd_host, 0));
-      const u64 one2 = 0x3f8000003f800000ull;
-      const unsigned long long first = n->cmd_seq + 1;
-      if (n->search == LGS_NDT_DIRECT7)
-        ndt_persistent_kernel<true><<<kNumSMs, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->ex_mean.as<double>(),
-                                                                                      n->ex_icov.as<double>(), n->partials.as<double>(), result, counter, one2,
-                                                                                      mb.r, static_cast<const NdtCommandHost*>(dv), n->cmd_dev.as<NdtCommandDev>(),
-                                                                                      first);
-      else
-        ndt_persistent_kernel<false><<<kNumSMs, kDerivThreads, sizeof(DerivSmem), st>>>(src, ns, P, ct, n->recs.as<VoxelRec>(), n->ex_mean.as<double>(),
-                                                                                       n->ex_icov.as<double>(), n->partials.as<double>(), result, counter, one2,
-                                                                                       mb.r, static_cast<const NdtCommandHost*>(dv), n->cmd_dev.as<NdtCommandDev>(),
-                                                                                       first);
-      ctx->launches++;
-      n->session_launches++;
-      cudaError_t le = cudaGetLastError();
-      if (le != cudaSuccess) {
-        persist_release(ctx->device);
-        set_error("ndt_persistent_kernel launch failed: %s", cudaGetErrorString(le));
-        return LGS_ERR_CUDA;
-      }
-      n->session_active = true;
-      n->session_device = ctx->device;
-    }
+  *out = &c;
+  return LGS_OK;
+}
+
+bool device_align_env_enabled() {  // LGS_NDT_DEVICE_ALIGN=0: the host steps the optimiser, one launch per evaluation
+  static const bool on = [] {
+    const char* e = getenv("LGS_NDT_DEVICE_ALIGN");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+void fill_eval_constants(lgs_ndt* n) {
+  EvalParams& P = n->P;
+  P.gauss_d1 = n->gauss_d1;
+  P.gauss_d2 = n->gauss_d2;
+  P.gauss_d2f = static_cast<float>(n->gauss_d2);
+  fill_offsets(n->search, &P);
+}
+
+int ensure_reduction_buffers(lgs_ndt* n, int grid) {
+  cudaStream_t st = n->ctx->stream;
+  LGS_TRY(n->partials.reserve(static_cast<size_t>(std::max(grid, kNumSMs)) * kNumAcc * sizeof(double)));
+  if (!n->result.p) {
+    LGS_TRY(n->result.reserve(kNumAcc * sizeof(double) + 64));
+    LGS_CUDA(cudaMemsetAsync(n->result.p, 0, kNumAcc * sizeof(double) + 64, st));
   }
-  if (n->session_active) {
-    NdtPose pose;
-    memcpy(pose.T, P.T, sizeof(pose.T));
-    memcpy(pose.j_ang, P.j_ang, sizeof(pose.j_ang));
-    memcpy(pose.h_ang, P.h_ang, sizeof(pose.h_ang));
-    pose.mode = mode;
-    pose.pad = 0;
-    pose.token = mb.token;
-    memcpy(pose.j_ang_d, P.j_ang_d, sizeof(pose.j_ang_d));
-    memcpy(pose.h_ang_d, P.h_ang_d, sizeof(pose.h_ang_d));
-    static const bool trace = getenv("LGS_NDT_TRACE") != nullptr;  // development aid: device round trip per evaluation
-    const auto t_send = std::chrono::steady_clock::now();
-    send_command(n, pose);
-    n->session_evals++;
-    double h[kMailboxRecords];
-    const int rc = mailbox_wait(ctx, mb, K, h);
-    if (trace) n->trace_roundtrip_us[mode] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_send).count();
-    if (rc != LGS_OK) {
-      // The grid ended without answering (its command time-out: the host was held up for longer than that, e.g. by a tool
-      // that blocks in the launch call).  If the stream is healthy, evaluate this pose with a plain launch and keep doing
-      // so for the rest of this object's life; a real CUDA error is reported as it is.
-      end_session(n);
-      if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return rc;
-      n->session_broken = true;
-      // a grid that lost some of its CTAs to the time-out may have left the arrival counter mid-count
-      if (cudaMemsetAsync(counter, 0, sizeof(unsigned), st) != cudaSuccess) return rc;
-      n->evals -= mode == 2 ? 0 : 1;
-      n->hess_recomputes -= mode == 2 ? 1 : 0;
-      return evaluate(n, T, p, mode, score, g, H);
-    }
-    if (mode == 2) {
-      for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[tri(i, j)];
-      return LGS_OK;
-    }
-    *score = h[0];
-    memcpy(g, h + 1, 6 * sizeof(double));
-    if (mode == 0) {
-      for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[7 + tri(i, j)];
-    }
-    n->last_terms = h[mode == 0 ? 28 : 7];
-    return LGS_OK;
-  }
+  return LGS_OK;
+}
+
+// one computeDerivatives / computeHessian evaluation as one kernel launch, with the transform and the angular tables
+// already in n->P.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian.  sums: the kernel's packed result (29 / 8 /
+// 22 doubles, zeros when there is nothing to evaluate).
+int evaluate_launch(lgs_ndt* n, int mode, double* sums) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  fill_eval_constants(n);
+  const int K = mode == 0 ? 29 : (mode == 1 ? 8 : 22);
+  std::fill(sums, sums + 32, 0.0);
+  if (mode == 2) n->hess_recomputes++; else n->evals++;
+  if (n->n_source == 0 || n->refused || n->n_valid == 0) return LGS_OK;
+  const DeviceCaps* caps = nullptr;
+  LGS_TRY(device_caps(ctx, &caps));
+  const int ns = static_cast<int>(n->n_source);
+  // one CTA per SM (fewer when the cloud has fewer rounds of 32 points than SMs)
+  const int dgrid = std::max(1, std::min(kNumSMs, (ns + 31) / 32));
+  LGS_TRY(ensure_reduction_buffers(n, dgrid));
+  double* result = n->result.as<double>();
+  unsigned* counter = reinterpret_cast<unsigned*>(result + kNumAcc);
+  const CellTable ct = make_cell_table(n);
+  const float4* src = n->source.as<float4>();
+  const EvalParams& P = n->P;
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (n->profiling) {
+  if (n->profiling == 1) {
     LGS_CUDA(cudaEventCreate(&ev0));
     LGS_CUDA(cudaEventCreate(&ev1));
     LGS_CUDA(cudaEventRecord(ev0, st));
   }
   {
-    // one CTA per SM (fewer when the cloud has fewer rounds of 32 points than SMs)
-    const int dgrid = std::max(1, std::min(kNumSMs, (ns + 31) / 32));
     const u64 one2 = 0x3f8000003f800000ull;  // (1.0f, 1.0f): see ndt_deriv.cuh
     const bool d7 = n->search == LGS_NDT_DIRECT7;
     VoxelRec* rc = n->recs.as<VoxelRec>();
@@ -741,140 +605,150 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
     else LGS_LAUNCH(2, false);
 #undef LGS_LAUNCH
   }
-  if (n->profiling) {
+  if (n->profiling == 1) {
     LGS_CUDA(cudaEventRecord(ev1, st));
     n->prof_events[mode].emplace_back(ev0, ev1);
   }
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   // the last CTA publishes the K sums to the host mailbox; no D2H copy, no stream synchronisation
-  double h[kMailboxRecords];
-  LGS_TRY(mailbox_wait(ctx, mb, K, h));
+  LGS_TRY(mailbox_wait(ctx, mb, K, sums));
+  n->last_terms = sums[K - 1];
+  return LGS_OK;
+}
+
+// the parity-hook form: transform T, tables of pose p
+int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* score, double* g, double* H) {
+  memcpy(n->P.T, T, sizeof(float) * 16);
+  if (p) angle_derivatives(p, &n->P);
+  double sums[32];
+  LGS_TRY(evaluate_launch(n, mode, sums));
   if (mode == 2) {
     for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[tri(i, j)];
-  } else {
-    *score = h[0];
-    memcpy(g, h + 1, 6 * sizeof(double));
-    if (mode == 0) {
+      for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = sums[tri(i, j)];
+    return LGS_OK;
+  }
+  if (score) *score = sums[0];
+  if (g) memcpy(g, sums + 1, 6 * sizeof(double));
+  if (H) {
+    std::fill(H, H + 36, 0.0);
+    if (mode == 0)
       for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = h[7 + tri(i, j)];
-    }
-    n->last_terms = h[mode == 0 ? 28 : 7];
+        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = sums[7 + tri(i, j)];
   }
   return LGS_OK;
 }
 
-inline double dot6(const double* a, const double* b) {
-  double s = 0;
-  for (int i = 0; i < 6; i++) s += a[i] * b[i];
-  return s;
+void command_to_params(const ndtopt::Command& c, EvalParams* P) {
+  memcpy(P->T, c.T, sizeof(P->T));
+  memcpy(P->j_ang, c.j_ang, sizeof(P->j_ang));
+  memcpy(P->h_ang, c.h_ang, sizeof(P->h_ang));
+  memcpy(P->j_ang_d, c.j_ang_d, sizeof(P->j_ang_d));
+  memcpy(P->h_ang_d, c.h_ang_d, sizeof(P->h_ang_d));
 }
 
-// updateIntervalMT (NDT:647-685)
-bool update_interval(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t) {
-  if (f_t > f_l) {
-    a_u = a_t; f_u = f_t; g_u = g_t;
-    return false;
+struct AlignOutcome {
+  float T[16];
+  int iterations, converged, evals, trials, hess;
+  double trans_probability;
+};
+
+// the optimiser stepped by the host: one kernel launch per evaluation (small or empty inputs, profiling of the
+// per-evaluation kernels, LGS_NDT_DEVICE_ALIGN=0)
+int align_host_stepped(lgs_ndt* n, const double p0[6], const float T0[16], AlignOutcome* out) {
+  ndtopt::Machine m;
+  ndtopt::Command c;
+  m.begin(p0, T0, n->step_size, n->trans_eps, n->max_iter, static_cast<double>(n->n_source), &c);
+  n->evals = n->hess_recomputes = 0;
+  while (true) {
+    command_to_params(c, &n->P);
+    double sums[32];
+    LGS_TRY(evaluate_launch(n, c.mode, sums));
+    if (!m.advance(sums, &c)) break;
   }
-  if (g_t * (a_l - a_t) > 0) {
-    a_l = a_t; f_l = f_t; g_l = g_t;
-    return false;
-  }
-  if (g_t * (a_l - a_t) < 0) {
-    a_u = a_l; f_u = f_l; g_u = g_l;
-    a_l = a_t; f_l = f_t; g_l = g_t;
-    return false;
-  }
-  return true;
+  memcpy(out->T, m.final_T, sizeof(out->T));
+  out->iterations = m.nr_iterations;
+  out->converged = m.converged;
+  out->evals = m.evals;
+  out->trials = m.trials;
+  out->hess = m.hess_recomputes;
+  out->trans_probability = m.trans_probability;
+  return LGS_OK;
 }
 
-// trialValueSelectionMT (NDT:688-768)
-double trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
-  auto cubic = [](double a0, double f0, double g0, double a1, double f1, double g1) {
-    double z = 3 * (f1 - f0) / (a1 - a0) - g1 - g0;
-    double w = std::sqrt(z * z - g1 * g0);
-    return a0 + (a1 - a0) * (w - g0 - z) / (g1 - g0 + 2 * w);
-  };
-  if (f_t > f_l) {
-    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
-    double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
-    return std::fabs(a_c - a_l) < std::fabs(a_q - a_l) ? a_c : 0.5 * (a_q + a_c);
+// the whole align as one cooperative launch of ndt_align_kernel; *used = false when the device cannot hold the grid
+int align_on_device(lgs_ndt* n, const double p0[6], const float T0[16], AlignOutcome* out, bool* used) {
+  *used = false;
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  const DeviceCaps* caps = nullptr;
+  LGS_TRY(device_caps(ctx, &caps));
+  const bool d7 = n->search == LGS_NDT_DIRECT7;
+  const int ns = static_cast<int>(n->n_source);
+  // evaluating CTAs (one per round of 32 points at most) + the optimiser CTA, one CTA per SM
+  const int grid = std::max(1, std::min(std::min(kNumSMs, caps->num_sms) - 1, (ns + 31) / 32)) + 1;
+  if (caps->num_sms < 2 || caps->align_ctas_per_sm[d7 ? 1 : 0] * caps->num_sms < grid) return LGS_OK;  // the grid must be co-resident
+  LGS_TRY(ensure_reduction_buffers(n, grid));
+  if (!n->align_dev.p) LGS_TRY(n->align_dev.reserve(sizeof(NdtAlignDev)));
+  fill_eval_constants(n);
+  // the first command (NDT:119): the guess and the tables of its pose; the machine on the device builds the same one
+  memcpy(n->P.T, T0, sizeof(float) * 16);
+  angle_derivatives(p0, &n->P);
+  NdtAlignArgs args;
+  memcpy(args.p0, p0, sizeof(args.p0));
+  memcpy(args.T0, T0, sizeof(args.T0));
+  args.step_size = n->step_size;
+  args.trans_eps = n->trans_eps;
+  args.n_in = static_cast<double>(n->n_source);
+  args.max_iter = n->max_iter;
+  args.pad = 0;
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
+  LGS_CUDA(cudaMemsetAsync(n->align_dev.p, 0, 48, st));  // seq, the arrival counter, the trace words
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (n->profiling == 2) {
+    LGS_CUDA(cudaEventCreate(&ev0));
+    LGS_CUDA(cudaEventCreate(&ev1));
+    LGS_CUDA(cudaEventRecord(ev0, st));
   }
-  if (g_t * g_l < 0) {
-    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
-    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
-    return std::fabs(a_c - a_t) >= std::fabs(a_s - a_t) ? a_c : a_s;
+  const float4* src = n->source.as<float4>();
+  CellTable ct = make_cell_table(n);
+  const VoxelRec* rc = n->recs.as<VoxelRec>();
+  const double *vm = n->ex_mean.as<double>(), *vc = n->ex_icov.as<double>();
+  double* pt = n->partials.as<double>();
+  NdtAlignDev* dev = n->align_dev.as<NdtAlignDev>();
+  u64 one2 = 0x3f8000003f800000ull;
+  int ns_arg = ns;
+  void* kargs[] = {&src, &ns_arg, &n->P, &ct, &rc, &vm, &vc, &pt, &dev, &args, &one2, &mb};
+  const void* fn = d7 ? reinterpret_cast<const void*>(ndt_align_kernel<true>) : reinterpret_cast<const void*>(ndt_align_kernel<false>);
+  cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kDerivThreads), kargs, sizeof(DerivSmem), st);
+  if (le != cudaSuccess) {
+    set_error("ndt_align_kernel cooperative launch failed: %s", cudaGetErrorString(le));
+    return LGS_ERR_CUDA;
   }
-  if (std::fabs(g_t) <= std::fabs(g_l)) {
-    double a_c = cubic(a_l, f_l, g_l, a_t, f_t, g_t);
-    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
-    double a_next = std::fabs(a_c - a_t) < std::fabs(a_s - a_t) ? a_c : a_s;
-    return a_t > a_l ? std::min(a_t + 0.66 * (a_u - a_t), a_next) : std::max(a_t + 0.66 * (a_u - a_t), a_next);
+  if (n->profiling == 2) {
+    LGS_CUDA(cudaEventRecord(ev1, st));
+    n->prof_events[3].emplace_back(ev0, ev1);
   }
-  return cubic(a_u, f_u, g_u, a_t, f_t, g_t);
-}
-
-// computeStepLengthMT (NDT:771-931)
-int step_length_mt(lgs_ndt* n, const double x[6], double dir[6], double step_init, double step_max, double step_min, double& score, double g[6],
-                   double H[36], double* step_out) {
-  const double phi_0 = -score;
-  double d_phi_0 = -dot6(g, dir);
-  if (d_phi_0 >= 0) {
-    if (d_phi_0 == 0) {
-      *step_out = 0;
-      return LGS_OK;
-    }
-    d_phi_0 *= -1;
-    for (int i = 0; i < 6; i++) dir[i] *= -1;
+  ctx->launches++;
+  n->align_launches = 1;
+  double h[kMailboxRecords];
+  LGS_TRY(mailbox_wait(ctx, mb, kAlignResultRecords, h));
+  for (int i = 0; i < 16; i++) out->T[i] = static_cast<float>(h[i]);
+  out->trans_probability = h[23];
+  out->iterations = static_cast<int>(h[24]);
+  out->converged = static_cast<int>(h[25]);
+  out->evals = static_cast<int>(h[26]);
+  out->trials = static_cast<int>(h[27]);
+  out->hess = static_cast<int>(h[28]);
+  n->last_terms = h[29];
+  n->terms_total = h[30];
+  for (int i = 0; i < 16; i++) n->align_trace[i] = h[32 + i];
+  if (n->profiling == 2) {
+    n->prof_align_evals += h[26] + h[28];
+    n->prof_align_terms += h[30];
   }
-  const int max_step_iterations = 10;
-  int step_iterations = 0;
-  const double mu = 1.e-4, nu = 0.9;
-  double a_l = 0, a_u = 0;
-  double f_l = phi_0 - phi_0 - mu * d_phi_0 * a_l;  // auxiliaryFunction_PsiMT (NDT.h:430-436)
-  double g_l = d_phi_0 - mu * d_phi_0;              // auxiliaryFunction_dPsiMT (NDT.h:438-447)
-  double f_u = phi_0 - phi_0 - mu * d_phi_0 * a_u;
-  double g_u = d_phi_0 - mu * d_phi_0;
-  bool interval_converged = (step_max - step_min) < 0, open_interval = true;
-  double a_t = std::max(std::min(step_init, step_max), step_min);
-  double x_t[6];
-  for (int i = 0; i < 6; i++) x_t[i] = x[i] + dir[i] * a_t;
-  pose_to_matrix(x_t, n->final_T);
-  LGS_TRY(evaluate(n, n->final_T, x_t, 0, &score, g, H));
-  double phi_t = -score;
-  double d_phi_t = -dot6(g, dir);
-  double psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
-  double d_psi_t = d_phi_t - mu * d_phi_0;
-  while (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
-    n->trials++;
-    if (open_interval)
-      a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
-    else
-      a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
-    a_t = std::max(std::min(a_t, step_max), step_min);
-    for (int i = 0; i < 6; i++) x_t[i] = x[i] + dir[i] * a_t;
-    pose_to_matrix(x_t, n->final_T);
-    LGS_TRY(evaluate(n, n->final_T, x_t, 1, &score, g, H));  // compute_hessian = false: H is zeroed
-    phi_t = -score;
-    d_phi_t = -dot6(g, dir);
-    psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
-    d_psi_t = d_phi_t - mu * d_phi_0;
-    if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
-      open_interval = false;
-      f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
-      g_l = g_l + mu * d_phi_0;
-      f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
-      g_u = g_u + mu * d_phi_0;
-    }
-    if (open_interval)
-      interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
-    else
-      interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
-    step_iterations++;
-  }
-  if (step_iterations) LGS_TRY(evaluate(n, n->final_T, nullptr, 2, nullptr, nullptr, H));  // NDT:927-928 (angle tables of x_t are current)
-  *step_out = a_t;
+  *used = true;
   return LGS_OK;
 }
 
@@ -895,11 +769,9 @@ int lgs_ndt_create(lgs_ctx* ctx, lgs_ndt** out) {
 
 void lgs_ndt_destroy(lgs_ndt* n) {
   if (!n) return;
-  end_session(n);
   cudaSetDevice(n->ctx->device);
   cudaStreamSynchronize(n->ctx->stream);
-  if (n->cmd_host) cudaFreeHost(n->cmd_host);
-  n->cmd_dev.release();
+  n->align_dev.release();
   for (DevBuf* b : {&n->target, &n->source, &n->out_cloud, &n->table, &n->hkeys, &n->recs, &n->ex_idx, &n->ex_n, &n->ex_mean, &n->ex_cov, &n->ex_icov,
                     &n->small, &n->partials, &n->result})
     b->release();
@@ -968,24 +840,8 @@ int lgs_ndt_set_source_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
 }
 
 // pcl::Registration::align shell + computeTransformation (NDT:80-171)
-static int ndt_align_body(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud);
-
 int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
   LGS_REQUIRE(n && res, "null argument");
-  n->allow_session = true;
-  const auto t0 = std::chrono::steady_clock::now();
-  n->trace_roundtrip_us[0] = n->trace_roundtrip_us[1] = n->trace_roundtrip_us[2] = 0;
-  const int rc = ndt_align_body(n, guess16, res, out_cloud);
-  end_session(n);  // every exit path releases the resident grid
-  n->allow_session = false;
-  if (getenv("LGS_NDT_TRACE"))
-    fprintf(stderr, "[lgs ndt] align %.1f us: %d evaluations (%d trials, %d f64 Hessians), device round trips mode0 %.1f us, mode1 %.1f us, mode2 %.1f us in total\n",
-            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), res->evaluations, res->line_search_trials,
-            res->hessian_recomputes, n->trace_roundtrip_us[0], n->trace_roundtrip_us[1], n->trace_roundtrip_us[2]);
-  return rc;
-}
-
-static int ndt_align_body(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
   memset(res, 0, sizeof(*res));
   if (!n->have_target || !n->have_source) {
     set_error("lgs_ndt_align: setInputTarget and setInputSource must be called first");
@@ -993,54 +849,35 @@ static int ndt_align_body(lgs_ndt* n, const float* guess16, lgs_align_result* re
   }
   LGS_TRY(use_device(n->ctx));
   if (!n->grid_ready) LGS_TRY(build_grid(n));
+  const auto t0 = std::chrono::steady_clock::now();
   n->evals = n->trials = n->hess_recomputes = 0;
-  int nr_iterations = 0;
-  bool converged = false;
+  n->align_launches = 0;
   compute_gauss(n);
   float guess[16];
   identity16(guess);
-  if (guess16) memcpy(guess, guess16, sizeof(guess));
-  identity16(n->final_T);
-  bool is_identity = true;
-  for (int i = 0; i < 16; i++)
-    if (guess[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) is_identity = false;
-  if (!is_identity) memcpy(n->final_T, guess, sizeof(guess));  // NDT:95-101; the evaluation transforms by final_T on the fly
-
-  double p[6], delta_p[6], g[6], H[36], score = 0;
-  matrix_to_pose(n->final_T, p);  // NDT:103-111
-  LGS_TRY(evaluate(n, n->final_T, p, 0, &score, g, H));  // NDT:119
-  const double n_in = static_cast<double>(n->n_source);
-  double trans_probability = 0;
-  bool early_exit = false;
-  while (!converged) {
-    double neg_g[6];
-    for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
-    m::svd_solve<6>(H, neg_g, delta_p);  // NDT:127-129
-    double delta_p_norm = std::sqrt(dot6(delta_p, delta_p));
-    if (delta_p_norm == 0 || delta_p_norm != delta_p_norm) {  // NDT:134-139
-      trans_probability = score / n_in;
-      converged = delta_p_norm == delta_p_norm;
-      early_exit = true;
-      break;
-    }
-    for (int i = 0; i < 6; i++) delta_p[i] /= delta_p_norm;
-    double step = 0;
-    LGS_TRY(step_length_mt(n, p, delta_p, delta_p_norm, n->step_size, n->trans_eps / 2, score, g, H, &step));
-    delta_p_norm = step;
-    for (int i = 0; i < 6; i++) delta_p[i] *= delta_p_norm;
-    for (int i = 0; i < 6; i++) p[i] = p[i] + delta_p[i];
-    if (nr_iterations > n->max_iter || (nr_iterations && (std::fabs(delta_p_norm) < n->trans_eps))) converged = true;  // NDT:158-162
-    nr_iterations++;
-  }
-  if (!early_exit) trans_probability = score / n_in;  // NDT:170
-  end_session(n);  // the optimiser is done: what follows (output cloud, fitness) are ordinary launches
-  memcpy(res->T, n->final_T, sizeof(float) * 16);
-  res->trans_probability = trans_probability;
-  res->iterations = nr_iterations;
-  res->converged = converged ? 1 : 0;
-  res->evaluations = n->evals;
-  res->line_search_trials = n->trials;
-  res->hessian_recomputes = n->hess_recomputes;
+  if (guess16) memcpy(guess, guess16, sizeof(guess));  // NDT:95-101; the evaluation transforms by the guess on the fly
+  double p0[6];
+  matrix_to_pose(guess, p0);  // NDT:103-111
+  AlignOutcome out;
+  bool on_device = false;
+  const bool nothing_to_evaluate = n->n_source == 0 || n->refused || n->n_valid == 0;
+  if (!nothing_to_evaluate && n->profiling != 1 && device_align_env_enabled()) LGS_TRY(align_on_device(n, p0, guess, &out, &on_device));
+  if (!on_device) LGS_TRY(align_host_stepped(n, p0, guess, &out));
+  memcpy(n->final_T, out.T, sizeof(float) * 16);
+  memcpy(res->T, out.T, sizeof(float) * 16);
+  res->trans_probability = out.trans_probability;
+  res->iterations = out.iterations;
+  res->converged = out.converged;
+  res->evaluations = out.evals;
+  res->line_search_trials = out.trials;
+  res->hessian_recomputes = out.hess;
+  n->evals = out.evals;
+  n->trials = out.trials;
+  n->hess_recomputes = out.hess;
+  if (getenv("LGS_NDT_TRACE"))
+    fprintf(stderr, "[lgs ndt] align %.1f us (%s): %d evaluations (%d trials, %d f64 Hessians), %d iterations\n",
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), on_device ? "one resident launch" : "host-stepped",
+            res->evaluations, res->line_search_trials, res->hessian_recomputes, res->iterations);
   if (out_cloud && n->n_source) {
     cudaStream_t st = n->ctx->stream;
     LGS_TRY(n->out_cloud.reserve(static_cast<size_t>(n->n_source) * 16));
@@ -1139,30 +976,49 @@ int lgs_ndt_export_voxels(lgs_ndt* n, int32_t* idx, int32_t* nr_points, double* 
 
 int lgs_ndt_profile(lgs_ndt* n, int32_t enable, double* out8) {
   LGS_REQUIRE(n, "null argument");
+  LGS_REQUIRE(enable >= 0 && enable <= 2, "enable must be 0, 1 or 2");
   LGS_TRY(use_device(n->ctx));
   LGS_CUDA(cudaStreamSynchronize(n->ctx->stream));
+  auto total_ms = [](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+    double ms = 0;
+    for (auto& pr : v) {
+      float t = 0;
+      cudaEventElapsedTime(&t, pr.first, pr.second);
+      ms += t;
+    }
+    return ms;
+  };
   if (out8) {
-    for (int m = 0; m < 3; m++) {
-      double ms = 0;
-      for (auto& pr : n->prof_events[m]) {
-        float t = 0;
-        cudaEventElapsedTime(&t, pr.first, pr.second);
-        ms += t;
+    if (n->profiling == 2) {  // whole aligns: launches, ms, evaluations and accepted terms summed over them
+      out8[0] = static_cast<double>(n->prof_events[3].size());
+      out8[1] = total_ms(n->prof_events[3]);
+      out8[2] = n->prof_align_evals;
+      out8[3] = n->prof_align_terms;
+      out8[4] = out8[5] = 0;
+    } else {
+      for (int m = 0; m < 3; m++) {
+        out8[2 * m] = static_cast<double>(n->prof_events[m].size());
+        out8[2 * m + 1] = total_ms(n->prof_events[m]);
       }
-      out8[2 * m] = static_cast<double>(n->prof_events[m].size());
-      out8[2 * m + 1] = ms;
     }
     out8[6] = n->last_terms;
     out8[7] = static_cast<double>(n->n_source);
   }
-  for (int m = 0; m < 3; m++) {
+  for (int m = 0; m < 4; m++) {
     for (auto& pr : n->prof_events[m]) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
     n->prof_events[m].clear();
   }
-  n->profiling = enable != 0;
+  n->prof_align_evals = n->prof_align_terms = 0;
+  n->profiling = enable;
+  return LGS_OK;
+}
+
+int lgs_ndt_align_breakdown(lgs_ndt* n, double* out16) {
+  LGS_REQUIRE(n && out16, "null argument");
+  memcpy(out16, n->align_trace, sizeof(n->align_trace));
   return LGS_OK;
 }
 

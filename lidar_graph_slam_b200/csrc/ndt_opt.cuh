@@ -12,6 +12,8 @@
 // All state is f64 and every expression keeps the reference's operation order (no FMA contraction: -fmad=false), so both
 // drivers walk the same path.
 #pragma once
+#include <cstring>
+
 #include "math.cuh"
 
 namespace lgs {
@@ -19,35 +21,109 @@ namespace ndtopt {
 
 // ---- trigonometry ------------------------------------------------------------------------------------------------
 // The reference takes sinf / cosf of the f32 angles (Eigen::AngleAxisf, NDT.h:222-224) and sin / cos of the f64 angles
-// (NDT:293-326).  Here the f32 values are the f64 functions of the widened f32 angle rounded to f32, i.e. the correctly
-// rounded sinf / cosf: one definition that the host's libm and the device's libdevice both deliver (their f64 sin / cos
-// differ by an ulp now and then, which the rounding to f32 absorbs), so that the two drivers build the same transform.
-// A libm whose sinf is not correctly rounded (glibc's is within 0.56 ulp) may differ from this in the last bit.
+// (NDT:293-326) from the C library.  A one-ulp difference in a sine moves every transformed point, so the device-resident
+// optimiser must produce the libm's bits, not merely a good sine.  sinf_libm / cosf_libm restate glibc's single-precision
+// routines (sysdeps/ieee754/flt-32/s_sincosf.h, the ARM optimized-routines algorithm, glibc 2.28+; pinned here against
+// glibc 2.39 on x86-64 with FMA: quadrant reduction x - n * pi/2 with n = round(x * 2/pi) taken from a 2^24-scaled
+// conversion, then a degree-7 / degree-8 polynomial in f64 with the constants below, multiply-adds fused as the library's
+// FMA build fuses them) and agree with it bit for bit for every |x| < 120 (2.2e9 values, tests/sincos_check.cpp runs a
+// sample of that sweep).  The f64 sine / cosine of the angular tables are the platform's own (libm on the host,
+// libdevice on the GPU, which may differ by an ulp): they reach the f32 terms only through a cast that absorbs it.
+struct SinCosTab {
+  double c0, c1, s1, c2, s2, c3, s3, c4;
+};
+LGS_HD double fma_rn(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+LGS_HD float sincosf_poly(double x, double x2, bool negated, int n) {
+  const SinCosTab t0 = {0x1p0, -0x1.ffffffd0c621cp-2, -0x1.555545995a603p-3, 0x1.55553e1068f19p-5, 0x1.1107605230bc4p-7, -0x1.6c087e89a359dp-10,
+                        -0x1.994eb3774cf24p-13, 0x1.99343027bf8c3p-16};
+  const SinCosTab t1 = {-0x1p0, 0x1.ffffffd0c621cp-2, -0x1.555545995a603p-3, -0x1.55553e1068f19p-5, 0x1.1107605230bc4p-7, 0x1.6c087e89a359dp-10,
+                        -0x1.994eb3774cf24p-13, -0x1.99343027bf8c3p-16};
+  const SinCosTab& p = negated ? t1 : t0;
+  if ((n & 1) == 0) {
+    const double x3 = x * x2;
+    const double s1 = fma_rn(x2, p.s3, p.s2);
+    const double x7 = x3 * x2;
+    const double s = fma_rn(x3, p.s1, x);
+    return static_cast<float>(fma_rn(x7, s1, s));
+  }
+  const double x4 = x2 * x2;
+  const double c2 = fma_rn(x2, p.c4, p.c3);
+  const double c1 = fma_rn(x2, p.c1, p.c0);
+  const double x6 = x4 * x2;
+  const double c = fma_rn(x4, p.c2, c1);
+  return static_cast<float>(fma_rn(x6, c2, c));
+}
+LGS_HD unsigned abstop12(float x) {
+#if defined(__CUDA_ARCH__)
+  return (__float_as_uint(x) >> 20) & 0x7ffu;
+#else
+  unsigned u;
+  memcpy(&u, &x, 4);
+  return (u >> 20) & 0x7ffu;
+#endif
+}
+// which = 0: sinf(y), 1: cosf(y)
+LGS_HD float sincosf_libm(float y, int which) {
+  double x = y;
+  if (abstop12(y) < abstop12(0x1.921FB6p-1f)) {
+    if (abstop12(y) < abstop12(0x1p-12f)) return which ? 1.0f : y;
+    return sincosf_poly(x, x * x, false, which);
+  }
+  if (abstop12(y) < abstop12(120.0f)) {
+    const double r = x * 0x1.45F306DC9C883p+23;
+    const int n = (static_cast<int>(r) + 0x800000) >> 24;
+    x = fma_rn(-static_cast<double>(n), 0x1.921FB54442D18p0, x);
+    const int q = n + which;
+    const double sign = ((q & 3) == 1 || (q & 3) == 2) ? -1.0 : 1.0;
+    return sincosf_poly(x * sign, x * x, (q & 2) != 0, n ^ which);
+  }
+  // |y| >= 120 rad never occurs for roll / pitch / yaw (the library switches to a Payne-Hanek style reduction there): f64 function, rounded
+  return static_cast<float>(which ? cos(x) : sin(x));
+}
+LGS_HD float sinf_libm(float y) { return sincosf_libm(y, 0); }
+LGS_HD float cosf_libm(float y) { return sincosf_libm(y, 1); }
+
 struct Trig {
-  float sf[3], cf[3];   // sin / cos of (float) roll, pitch, yaw, rounded to f32
-  double sd[3], cd[3];  // sin / cos of the f64 angles with the small-angle snap of NDT:293-326
+  float sf[3], cf[3];  // sinf / cosf of (float) roll, pitch, yaw
+  double f[8];         // 1, 0, then cos / sin of the f64 roll, pitch, yaw (cx, sx, cy, sy, cz, sz) with the small-angle snap
+                       // of NDT:293-326: the factors of the angular tables, addressed by angle_entry
 };
 
-LGS_HD void trig_of_pose(const double x[6], Trig* t) {
-  for (int a = 0; a < 3; a++) {
-    const double af = static_cast<double>(static_cast<float>(x[3 + a]));
-    t->sf[a] = static_cast<float>(sin(af));
-    t->cf[a] = static_cast<float>(cos(af));
-    if (fabs(x[3 + a]) < 10e-5) {  // NDT:293-326
-      t->cd[a] = 1.0;
-      t->sd[a] = 0.0;
-    } else {
-      t->cd[a] = cos(x[3 + a]);
-      t->sd[a] = sin(x[3 + a]);
+// the twelve values of a pose, one at a time (k = 0..2: sinf, 3..5: cosf, 6..8: sin, 9..11: cos of roll / pitch / yaw) so
+// that the device can spread them over threads; trig_of_pose is the same arithmetic in a loop
+LGS_HD void trig_value(const double x[6], int k, Trig* t) {
+  const int a = k % 3;
+  if (k < 3) {
+    t->sf[a] = sinf_libm(static_cast<float>(x[3 + a]));
+  } else if (k < 6) {
+    t->cf[a] = cosf_libm(static_cast<float>(x[3 + a]));
+  } else {
+    const bool snap = fabs(x[3 + a]) < 10e-5;  // NDT:293-326
+    if (k < 9)
+      t->f[3 + 2 * a] = snap ? 0.0 : sin(x[3 + a]);
+    else
+      t->f[2 + 2 * a] = snap ? 1.0 : cos(x[3 + a]);
+    if (k == 6) {
+      t->f[0] = 1.0;
+      t->f[1] = 0.0;
     }
   }
+}
+LGS_HD void trig_of_pose(const double x[6], Trig* t) {
+  for (int k = 0; k < 12; k++) trig_value(x, k, t);
 }
 
 // Eigen::AngleAxis<float>(angle, Unit{X,Y,Z}).toRotationMatrix() from the angle's sine and cosine: note (1-c)*1 + c on
 // the axis diagonal
-LGS_HD void angle_axis_unit(float s, float c, int axis, float* R) {
-  float ax[3] = {0, 0, 0};
-  ax[axis] = 1.0f;
+template <int AXIS>
+LGS_HD void angle_axis_unit(float s, float c, float* R) {
+  const float ax[3] = {AXIS == 0 ? 1.0f : 0.0f, AXIS == 1 ? 1.0f : 0.0f, AXIS == 2 ? 1.0f : 0.0f};
   const float sa[3] = {s * ax[0], s * ax[1], s * ax[2]};
   const float ca[3] = {(1.0f - c) * ax[0], (1.0f - c) * ax[1], (1.0f - c) * ax[2]};
   float tmp = ca[0] * ax[1];
@@ -62,17 +138,18 @@ LGS_HD void angle_axis_unit(float s, float c, int axis, float* R) {
   for (int a = 0; a < 3; a++) R[a * 4] = ca[a] * ax[a] + c;
 }
 
+LGS_HD float mul3f_entry(const float* a, const float* b, int i, int j) { return (a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j]; }
 LGS_HD void mul3f(const float* a, const float* b, float* c) {
   for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) c[i * 3 + j] = (a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j];
+    for (int j = 0; j < 3; j++) c[i * 3 + j] = mul3f_entry(a, b, i, j);
 }
 
 // NDT.h:214-231: Translation * AngleAxis(X) * AngleAxis(Y) * AngleAxis(Z) in f32, column-major out
 LGS_HD void pose_to_matrix(const double x[6], const Trig& t, float* T) {
   float Rx[9], Ry[9], Rz[9], Rxy[9], R[9];
-  angle_axis_unit(t.sf[0], t.cf[0], 0, Rx);
-  angle_axis_unit(t.sf[1], t.cf[1], 1, Ry);
-  angle_axis_unit(t.sf[2], t.cf[2], 2, Rz);
+  angle_axis_unit<0>(t.sf[0], t.cf[0], Rx);
+  angle_axis_unit<1>(t.sf[1], t.cf[1], Ry);
+  angle_axis_unit<2>(t.sf[2], t.cf[2], Rz);
   mul3f(Rx, Ry, Rxy);
   mul3f(Rxy, Rz, R);
   for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
@@ -83,9 +160,60 @@ LGS_HD void pose_to_matrix(const double x[6], const Trig& t, float* T) {
   T[14] = static_cast<float>(x[2]);
 }
 
-// computeAngleDerivatives (NDT:329-392): rows a..h of j_ang and a2..f3 of h_ang, f64 and their f32 casts
+// computeAngleDerivatives (NDT:329-392): rows a..h of j_ang (entries 0..23) and a2..f3 of h_ang (entries 24..68), f64 and
+// their f32 casts.  Every entry of the reference is s1 * f1 * f2 * f3 [+ s2 * f4 * f5 * f6] with the factors taken from
+// {1, 0, cx, sx, cy, sy, cz, sz}, products evaluated left to right; the encoding below (generated from the expressions of
+// angle_tables_explicit, 3 bits per factor, 1 sign bit per term, 1 bit "has a second term") lets one thread evaluate one
+// entry without a 69-way branch.  Multiplying by 1.0 and negating are exact, so each entry has the bits of its expression.
+#define LGS_ANGLE_CODES                                                                                                       \
+  0x16aa3b, 0x1faa33, 0x000222, 0x16ac3a, 0x1fac32, 0x000223, 0x000235, 0x00003d, 0x000004, 0x0001a3, 0x0003e3, 0x00002b,     \
+      0x0003a2, 0x0001e2, 0x00022a, 0x00023c, 0x000234, 0x000001, 0x1fac32, 0x1eae3a, 0x000001, 0x17a833, 0x18edaa, 0x000001, \
+      0x1eae3a, 0x17ae32, 0x000023, 0x16aa3b, 0x18cfea, 0x000222, 0x0001a2, 0x0003e2, 0x00002a, 0x0001a3, 0x0003e3, 0x00002b, \
+      0x1faa33, 0x1ea83b, 0x000001, 0x1fac32, 0x18ebab, 0x000001, 0x000234, 0x00003c, 0x000005, 0x0003ab, 0x0001eb, 0x000023, \
+      0x0001aa, 0x0003ea, 0x000222, 0x00003d, 0x000035, 0x000001, 0x0003e3, 0x0003a3, 0x000001, 0x0001e2, 0x0001a2, 0x000001, \
+      0x000234, 0x00003c, 0x000001, 0x1eae3a, 0x17ae32, 0x000001, 0x16aa3b, 0x18cfea, 0x000001
+#if defined(__CUDACC__)
+__constant__ unsigned kAngleCodeDev[69] = {LGS_ANGLE_CODES};
+#endif
+// the encoding table; on the device a driver copies it next to the state it works on (Machine::codes, shared memory):
+// 69 threads reading 69 different words of __constant__ memory would be serialised by the constant cache
+LGS_HD void angle_codes(unsigned* out) {
+#if defined(__CUDA_ARCH__)
+  for (int e = 0; e < 69; e++) out[e] = kAngleCodeDev[e];
+#else
+  static const unsigned code[69] = {LGS_ANGLE_CODES};
+  for (int e = 0; e < 69; e++) out[e] = code[e];
+#endif
+}
+LGS_HD double angle_entry(const Trig& t, unsigned c) {
+  const double* f = t.f;
+  double t1 = (f[c & 7] * f[(c >> 3) & 7]) * f[(c >> 6) & 7];
+  if (c & (1u << 9)) t1 = -t1;
+  if (!(c & (1u << 20))) return t1;
+  double t2 = (f[(c >> 10) & 7] * f[(c >> 13) & 7]) * f[(c >> 16) & 7];
+  if (c & (1u << 19)) t2 = -t2;
+  return t1 + t2;
+}
+LGS_HD void angle_table_store(const Trig& t, const unsigned* codes, int e, double (*Jd)[3], double (*Hd)[3], float (*Jf)[3], float (*Hf)[3]) {
+  const double v = angle_entry(t, codes[e]);
+  if (e < 24) {
+    (&Jd[0][0])[e] = v;
+    (&Jf[0][0])[e] = static_cast<float>(v);
+  } else {
+    (&Hd[0][0])[e - 24] = v;
+    (&Hf[0][0])[e - 24] = static_cast<float>(v);
+  }
+}
 LGS_HD void angle_tables(const Trig& t, double (*Jd)[3], double (*Hd)[3], float (*Jf)[3], float (*Hf)[3]) {
-  const double cx = t.cd[0], cy = t.cd[1], cz = t.cd[2], sx = t.sd[0], sy = t.sd[1], sz = t.sd[2];
+  unsigned codes[69];
+  angle_codes(codes);
+  for (int e = 0; e < 69; e++) angle_table_store(t, codes, e, Jd, Hd, Jf, Hf);
+}
+
+// The same tables written out as in the reference (NDT:329-392).  Only tests/ndt_opt_check.cpp calls this: it pins the
+// table-driven form above to these expressions bit for bit (signed zeros included).
+LGS_HD void angle_tables_explicit(const Trig& t, double (*Jd)[3], double (*Hd)[3], float (*Jf)[3], float (*Hf)[3]) {
+  const double cx = t.f[2], sx = t.f[3], cy = t.f[4], sy = t.f[5], cz = t.f[6], sz = t.f[7];
   const double J[8][3] = {{(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
                           {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
                           {(-sy * cz), sy * sz, cy},
@@ -180,61 +308,85 @@ LGS_HD double trial_value(double a_l, double f_l, double g_l, double a_u, double
 
 // ---- Newton step ------------------------------------------------------------------------------------------------------
 // delta = -H^-1 g (NDT:127-129).  The reference goes through Eigen's two-sided JacobiSVD: ~80 dependent plane rotations,
-// each a chain of f64 divisions and square roots - 5 us on a CPU core, but 30-40 us on one GPU thread, more than the
-// derivative evaluation it sits between.  The solution only enters the align through p -> (f32 transform, f32 tables), so
-// the machine solves the well-conditioned case - every regular registration - by Gaussian elimination with partial
-// pivoting (equal to the SVD solution to ~cond(H) * 1e-16 relative, orders below the f32 quantisation of the transform)
-// and keeps the JacobiSVD, with Eigen's rank threshold, for the ill-conditioned / singular case (pivot ratio below 1e-8,
-// non-finite entries), where the minimum-norm semantics of the SVD matter.  Both drivers use this same rule.
-LGS_HD bool lu_solve6(const double* A, const double* b, double* x) {
-  double M[6][7];
-  for (int r = 0; r < 6; r++) {
-    for (int c = 0; c < 6; c++) M[r][c] = A[r * 6 + c];
-    M[r][6] = b[r];
+// each a chain of f64 divisions and square roots - 5 us on a CPU core, 30-40 us on a GPU thread, more than the derivative
+// evaluation it sits between; Gaussian elimination still chains six reciprocals (measured: 5.8k SM cycles).  The solution
+// only enters the align through p -> (f32 transform, f32 tables), so the machine solves the regular case by block
+// elimination on the symmetric H = [A B; B^T D] (A: translations, D: rotations): A^-1 and the inverse of the Schur
+// complement S = D - B^T A^-1 B in closed form (adjugate / determinant) - two reciprocals in the whole dependency chain.
+// It agrees with the SVD solution to ~cond * 1e-16 relative, orders below the f32 quantisation of the transform.  Whenever
+// a determinant is small against the products it is summed from (cancellation = ill-conditioning), or anything is not
+// finite, the machine falls back to the JacobiSVD with Eigen's rank threshold, whose minimum-norm semantics then matter.
+// Both drivers use this rule.  Ht: upper triangle of H, row by row (21 values); b: right-hand side; x: solution.
+LGS_HD int tri6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
+
+// adjugate and determinant of a symmetric 3x3 (a00 a01 a02 a11 a12 a22); false when the determinant cancels
+LGS_HD bool sym3_adjugate(const double* a, double* adj, double* det) {
+  const double a00 = a[0], a01 = a[1], a02 = a[2], a11 = a[3], a12 = a[4], a22 = a[5];
+  adj[0] = a11 * a22 - a12 * a12;
+  adj[1] = a02 * a12 - a01 * a22;
+  adj[2] = a01 * a12 - a02 * a11;
+  adj[3] = a00 * a22 - a02 * a02;
+  adj[4] = a01 * a02 - a00 * a12;
+  adj[5] = a00 * a11 - a01 * a01;
+  const double t0 = a00 * adj[0], t1 = a01 * adj[1], t2 = a02 * adj[2];
+  *det = (t0 + t1) + t2;
+  const double mag = (fabs(t0) + fabs(t1)) + fabs(t2);
+  return fabs(*det) > 1e-10 * mag && mag < 1.7976931348623157e308;  // NaN fails the first comparison
+}
+LGS_HD void sym3_mul_vec(const double* m, const double* v, double* out) {  // m packed as above
+  out[0] = (m[0] * v[0] + m[1] * v[1]) + m[2] * v[2];
+  out[1] = (m[1] * v[0] + m[3] * v[1]) + m[4] * v[2];
+  out[2] = (m[2] * v[0] + m[4] * v[1]) + m[5] * v[2];
+}
+LGS_HD bool schur_solve6(const double* Ht, const double* b, double* x) {
+  const double A[6] = {Ht[tri6(0, 0)], Ht[tri6(0, 1)], Ht[tri6(0, 2)], Ht[tri6(1, 1)], Ht[tri6(1, 2)], Ht[tri6(2, 2)]};
+  double adjA[6], detA;
+  if (!sym3_adjugate(A, adjA, &detA)) return false;
+  const double rA = 1.0 / detA;
+  double Ai[6];
+  for (int k = 0; k < 6; k++) Ai[k] = adjA[k] * rA;
+  // W = A^-1 B (3x3, column c of B = H[0..2][3 + c]); u = A^-1 b1
+  double W[3][3], u[3];
+  for (int c = 0; c < 3; c++) {
+    const double col[3] = {Ht[tri6(0, 3 + c)], Ht[tri6(1, 3 + c)], Ht[tri6(2, 3 + c)]};
+    double w[3];
+    sym3_mul_vec(Ai, col, w);
+    W[0][c] = w[0];
+    W[1][c] = w[1];
+    W[2][c] = w[2];
   }
-  double pmax = 0, pmin = 0;
-  for (int k = 0; k < 6; k++) {
-    int piv = k;
-    double big = fabs(M[k][k]);
-    for (int r = k + 1; r < 6; r++) {
-      const double v = fabs(M[r][k]);
-      if (v > big) {
-        big = v;
-        piv = r;
-      }
-    }
-    if (!(big > 0) || big != big || big > 1.7976931348623157e308) return false;
-    if (piv != k)
-      for (int c = k; c < 7; c++) {
-        const double t = M[k][c];
-        M[k][c] = M[piv][c];
-        M[piv][c] = t;
-      }
-    if (k == 0) {
-      pmax = pmin = big;
-    } else {
-      pmax = big > pmax ? big : pmax;
-      pmin = big < pmin ? big : pmin;
-    }
-    const double inv = 1.0 / M[k][k];
-    for (int r = k + 1; r < 6; r++) {
-      const double f = M[r][k] * inv;
-      for (int c = k + 1; c < 7; c++) M[r][c] = M[r][c] - f * M[k][c];
-    }
+  sym3_mul_vec(Ai, b, u);
+  // S = D - B^T W (symmetric: the upper triangle is formed), r = b2 - B^T u
+  double S[6], r[3];
+  int k = 0;
+  for (int i = 0; i < 3; i++) {
+    const double bi[3] = {Ht[tri6(0, 3 + i)], Ht[tri6(1, 3 + i)], Ht[tri6(2, 3 + i)]};  // column i of B = row i of B^T
+    for (int j = i; j < 3; j++) S[k++] = Ht[tri6(3 + i, 3 + j)] - ((bi[0] * W[0][j] + bi[1] * W[1][j]) + bi[2] * W[2][j]);
+    r[i] = b[3 + i] - ((bi[0] * u[0] + bi[1] * u[1]) + bi[2] * u[2]);
   }
-  if (!(pmin > 1e-8 * pmax)) return false;
-  for (int r = 5; r >= 0; r--) {
-    double acc = M[r][6];
-    for (int c = r + 1; c < 6; c++) acc = acc - M[r][c] * x[c];
-    x[r] = acc / M[r][r];
-  }
-  for (int r = 0; r < 6; r++)
-    if (x[r] != x[r]) return false;
+  double adjS[6], detS;
+  if (!sym3_adjugate(S, adjS, &detS)) return false;
+  const double rS = 1.0 / detS;
+  double y[3];
+  sym3_mul_vec(adjS, r, y);
+  for (int i = 0; i < 3; i++) x[3 + i] = y[i] * rS;
+  for (int i = 0; i < 3; i++) x[i] = u[i] - ((W[i][0] * x[3] + W[i][1] * x[4]) + W[i][2] * x[5]);
+  for (int i = 0; i < 6; i++)
+    if (!(fabs(x[i]) < 1.7976931348623157e308)) return false;
   return true;
 }
 
-LGS_HD void newton_solve(const double* H, const double* neg_g, double* delta) {
-  if (!lu_solve6(H, neg_g, delta)) m::svd_solve<6>(H, neg_g, delta);
+// JacobiSVD with Eigen's rank threshold, as the reference; out of line on the device (rare, large stack frame)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void svd_fallback(const double* Ht, const double* b, double* x) {
+  double H[36];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) H[i * 6 + j] = Ht[tri6(i, j)];
+  m::svd_solve<6>(H, b, x);
 }
 
 // ---- the machine ------------------------------------------------------------------------------------------------------
@@ -247,12 +399,14 @@ struct Command {       // the evaluation to run next
   double h_ang_d[15][3];
 };
 
+enum Action { kDone = 0, kSolve = 1, kPose = 2, kHessian = 3 };
+
 struct Machine {
   // parameters
   double step_size, trans_eps, n_in;
   int max_iter;
   // optimiser state (NDT:103-171)
-  double p[6], score, g[6], H[36];
+  double p[6], score, g[6], Ht[21];  // Ht: upper triangle of H, row by row
   int nr_iterations, converged, early_exit;
   double trans_probability;
   int evals, trials, hess_recomputes;
@@ -263,16 +417,12 @@ struct Machine {
   double phi_t, d_phi_t, psi_t, d_psi_t;
   int interval_converged, open_interval, step_iterations;
   int pending;  // what the evaluation in flight is: 0 initial (NDT:119), 1 first of a line search, 2 trial, 3 computeHessian
-
-  // pose + transform + tables of the evaluation at x
-  LGS_HD void pose_command(const double x[6], int mode, Command* c) {
-    Trig t;
-    trig_of_pose(x, &t);
-    pose_to_matrix(x, t, final_T);
-    for (int i = 0; i < 16; i++) c->T[i] = final_T[i];
-    angle_tables(t, c->j_ang_d, c->h_ang_d, c->j_ang, c->h_ang);
-    c->mode = mode;
-  }
+  double delta_p[6];  // solution of the Newton system
+  // work areas of the steps a driver may run in parallel
+  int pose_mode;  // kPose: evaluation mode of the pose x_t
+  Trig trig;
+  float Rx[9], Ry[9], Rz[9], Rxy[9], R[9];
+  unsigned codes[69];  // angle_codes, next to the state (see there)
 
   // NDT:103-119: the first evaluation, at the pose of the guess (T0 = the guess itself, p0 its translation + Euler angles)
   LGS_HD void begin(const double p0[6], const float T0[16], double step_size_, double trans_eps_, int max_iter_, double n_in_, Command* c) {
@@ -284,152 +434,207 @@ struct Machine {
     for (int i = 0; i < 16; i++) final_T[i] = T0[i];
     score = 0;
     for (int i = 0; i < 6; i++) g[i] = 0;
-    for (int i = 0; i < 36; i++) H[i] = 0;
+    for (int i = 0; i < 21; i++) Ht[i] = 0;
     nr_iterations = converged = early_exit = 0;
     trans_probability = 0;
-    evals = trials = hess_recomputes = 0;
-    pending = 0;
-    Trig t;
-    trig_of_pose(p0, &t);
-    for (int i = 0; i < 16; i++) c->T[i] = T0[i];
-    angle_tables(t, c->j_ang_d, c->h_ang_d, c->j_ang, c->h_ang);
-    c->mode = 0;
     evals = 1;
+    trials = hess_recomputes = 0;
+    pending = 0;
+    trig_of_pose(p0, &trig);
+    for (int i = 0; i < 16; i++) c->T[i] = T0[i];
+    angle_codes(codes);
+    for (int e = 0; e < 69; e++) angle_table_store(trig, codes, e, c->j_ang_d, c->h_ang_d, c->j_ang, c->h_ang);
+    c->mode = 0;
   }
 
   LGS_HD void take_sums(const double* s, int mode) {
-    // mode 0: score, g[6], upper triangle of H (21); mode 1: score, g[6] (H zeroed, NDT:201); mode 2: upper triangle of H
+    // mode 0: score, g[6], upper triangle of H (21); mode 1: score, g[6]; mode 2: upper triangle of H.  (The reference
+    // zeroes H in a gradient-only evaluation, NDT:201; computeHessian always overwrites it before its next use, NDT:927.)
     if (mode == 2) {
-      int k = 0;
-      for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = s[k++];
+      for (int k = 0; k < 21; k++) Ht[k] = s[k];
       return;
     }
     score = s[0];
     for (int i = 0; i < 6; i++) g[i] = s[1 + i];
-    if (mode == 0) {
-      int k = 7;
-      for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = s[k++];
-    } else {
-      for (int i = 0; i < 36; i++) H[i] = 0;
-    }
+    if (mode == 0)
+      for (int k = 0; k < 21; k++) Ht[k] = s[7 + k];
   }
 
-  // Feeds the sums of the pending evaluation; returns true and fills *c when another evaluation is needed, false when
-  // the align is over (results in nr_iterations / converged / trans_probability / final_T / p).  *c must be the object
-  // the previous call (or begin) filled: computeHessian re-uses its transform and tables.
-  LGS_HD bool advance(const double* sums, Command* c) {
+  // NDT:127-129
+  LGS_HD void solve() {
+    double neg_g[6];
+    for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
+    if (schur_solve6(Ht, neg_g, delta_p)) return;
+    svd_fallback(Ht, neg_g, delta_p);
+  }
+  LGS_HD int request_pose(int mode) {
+    for (int i = 0; i < 6; i++) x_t[i] = p[i] + dir[i] * a_t;
+    pose_mode = mode;
+    evals++;
+    pending = mode == 0 ? 1 : 2;
+    return kPose;
+  }
+  // NDT:144-162 after a line search that returned `step`; then the next Newton step or the end
+  LGS_HD int outer_update(double step) {
+    for (int i = 0; i < 6; i++) p[i] = p[i] + dir[i] * step;
+    if (nr_iterations > max_iter || (nr_iterations && (fabs(step) < trans_eps))) converged = 1;
+    nr_iterations++;
+    if (converged) {
+      trans_probability = score / n_in;  // NDT:170
+      return kDone;
+    }
+    return kSolve;
+  }
+
+  // Feeds the sums of the pending evaluation.  kSolve: call solve, then after_solve.  kPose: build the
+  // transform and the tables of x_t (build_pose), mode pose_mode.  kHessian: computeHessian at the pose of the last
+  // command (its transform and tables are re-used).  kDone: results in nr_iterations / converged / trans_probability /
+  // final_T / p.
+  LGS_HD int consume(const double* sums) {
     const double mu = 1.e-4, nu = 0.9;
     const int max_step_iterations = 10;
-    bool newton = false, outer = false;
-    double step = 0;
     if (pending == 0) {
       take_sums(sums, 0);
-      newton = true;
-    } else if (pending == 1 || pending == 2) {
-      take_sums(sums, pending == 1 ? 0 : 1);
-      phi_t = -score;
-      d_phi_t = -dot6(g, dir);
-      psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
-      d_psi_t = d_phi_t - mu * d_phi_0;
-      if (pending == 2) {
-        if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
-          open_interval = 0;
-          f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
-          g_l = g_l + mu * d_phi_0;
-          f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
-          g_u = g_u + mu * d_phi_0;
-        }
-        if (open_interval)
-          interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t) ? 1 : 0;
-        else
-          interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t) ? 1 : 0;
-        step_iterations++;
-      }
-      // the loop condition of NDT:861
-      if (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
-        trials++;
-        if (open_interval)
-          a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
-        else
-          a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
-        a_t = std_max(std_min(a_t, step_max), step_min);
-        for (int i = 0; i < 6; i++) x_t[i] = p[i] + dir[i] * a_t;
-        pose_command(x_t, 1, c);
-        evals++;
-        pending = 2;
-        return true;
-      }
-      if (step_iterations) {  // NDT:927-928: the line search iterated, re-evaluate the Hessian in f64 at x_t:
-        c->mode = 2;          // *c still holds the transform and the tables of x_t (the contract of advance)
-        hess_recomputes++;
-        pending = 3;
-        return true;
-      }
-      step = a_t;
-      outer = true;
-    } else {
+      return kSolve;
+    }
+    if (pending == 3) {
       take_sums(sums, 2);
-      step = a_t;
-      outer = true;
+      return outer_update(a_t);
     }
-    while (true) {
-      if (outer) {  // NDT:144-162
-        for (int i = 0; i < 6; i++) p[i] = p[i] + dir[i] * step;
-        if (nr_iterations > max_iter || (nr_iterations && (fabs(step) < trans_eps))) converged = 1;
-        nr_iterations++;
-        if (converged) {
-          trans_probability = score / n_in;  // NDT:170
-          return false;
-        }
-        newton = true;
-        outer = false;
+    take_sums(sums, pending == 1 ? 0 : 1);
+    phi_t = -score;
+    d_phi_t = -dot6(g, dir);
+    psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
+    d_psi_t = d_phi_t - mu * d_phi_0;
+    if (pending == 2) {
+      if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+        open_interval = 0;
+        f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
+        g_l = g_l + mu * d_phi_0;
+        f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
+        g_u = g_u + mu * d_phi_0;
       }
-      if (newton) {  // NDT:127-139
-        newton = false;
-        double neg_g[6], delta_p[6];
-        for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
-        newton_solve(H, neg_g, delta_p);
-        double delta_p_norm = sqrt(dot6(delta_p, delta_p));
-        if (delta_p_norm == 0 || delta_p_norm != delta_p_norm) {
-          trans_probability = score / n_in;
-          converged = delta_p_norm == delta_p_norm ? 1 : 0;
-          early_exit = 1;
-          return false;
-        }
-        for (int i = 0; i < 6; i++) dir[i] = delta_p[i] / delta_p_norm;
-        // computeStepLengthMT (NDT:771-931), up to its first evaluation
-        step_max = step_size;
-        step_min = trans_eps / 2;
-        phi_0 = -score;
-        d_phi_0 = -dot6(g, dir);
-        if (d_phi_0 >= 0) {
-          if (d_phi_0 == 0) {  // NDT:790-791: no step
-            step = 0;
-            outer = true;
-            continue;
-          }
-          d_phi_0 *= -1;
-          for (int i = 0; i < 6; i++) dir[i] *= -1;
-        }
-        step_iterations = 0;
-        a_l = 0;
-        a_u = 0;
-        f_l = phi_0 - phi_0 - mu * d_phi_0 * a_l;  // auxiliaryFunction_PsiMT (NDT.h:430-436)
-        g_l = d_phi_0 - mu * d_phi_0;              // auxiliaryFunction_dPsiMT (NDT.h:438-447)
-        f_u = phi_0 - phi_0 - mu * d_phi_0 * a_u;
-        g_u = d_phi_0 - mu * d_phi_0;
-        interval_converged = (step_max - step_min) < 0 ? 1 : 0;
-        open_interval = 1;
-        a_t = std_max(std_min(delta_p_norm, step_max), step_min);
-        for (int i = 0; i < 6; i++) x_t[i] = p[i] + dir[i] * a_t;
-        pose_command(x_t, 0, c);
-        evals++;
-        pending = 1;
-        return true;
-      }
+      if (open_interval)
+        interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t) ? 1 : 0;
+      else
+        interval_converged = update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t) ? 1 : 0;
+      step_iterations++;
     }
+    // the loop condition of NDT:861
+    if (!interval_converged && step_iterations < max_step_iterations && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
+      trials++;
+      if (open_interval)
+        a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+      else
+        a_t = trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+      a_t = std_max(std_min(a_t, step_max), step_min);
+      return request_pose(1);
+    }
+    if (step_iterations) {  // NDT:927-928: the line search iterated, re-evaluate the Hessian in f64 at x_t
+      hess_recomputes++;
+      pending = 3;
+      return kHessian;
+    }
+    return outer_update(a_t);
+  }
+
+  // with the Newton step in delta_p: NDT:130-139, then computeStepLengthMT (NDT:771-931) up to its first evaluation
+  LGS_HD int after_solve() {
+    const double mu = 1.e-4;
+    const double delta_p_norm = sqrt(dot6(delta_p, delta_p));
+    if (delta_p_norm == 0 || delta_p_norm != delta_p_norm) {
+      trans_probability = score / n_in;
+      converged = delta_p_norm == delta_p_norm ? 1 : 0;
+      early_exit = 1;
+      return kDone;
+    }
+    for (int i = 0; i < 6; i++) dir[i] = delta_p[i] / delta_p_norm;
+    step_max = step_size;
+    step_min = trans_eps / 2;
+    phi_0 = -score;
+    d_phi_0 = -dot6(g, dir);
+    if (d_phi_0 >= 0) {
+      if (d_phi_0 == 0) return outer_update(0.0);  // NDT:790-791: no step
+      d_phi_0 *= -1;
+      for (int i = 0; i < 6; i++) dir[i] *= -1;
+    }
+    step_iterations = 0;
+    a_l = 0;
+    a_u = 0;
+    f_l = phi_0 - phi_0 - mu * d_phi_0 * a_l;  // auxiliaryFunction_PsiMT (NDT.h:430-436)
+    g_l = d_phi_0 - mu * d_phi_0;              // auxiliaryFunction_dPsiMT (NDT.h:438-447)
+    f_u = phi_0 - phi_0 - mu * d_phi_0 * a_u;
+    g_u = d_phi_0 - mu * d_phi_0;
+    interval_converged = (step_max - step_min) < 0 ? 1 : 0;
+    open_interval = 1;
+    a_t = std_max(std_min(delta_p_norm, step_max), step_min);
+    return request_pose(0);
+  }
+
+  // kPose in three stages a driver may spread over threads (every index of a stage is independent of the others):
+  //   stage 0: trig_value(x_t, k, &trig), k = 0..11
+  //   stage 1: pose_stage1(i), i = 0..2 (the three axis rotations) and angle_table_store(trig, codes, e, ...), e = 0..68
+  //   stage 2: pose_stage2(i), i = 0..8 (Rx * Ry);  stage 3: pose_stage3(i), i = 0..8 ((Rx * Ry) * Rz);  stage 4: pose_stage4(i), i = 0..15
+  LGS_HD void pose_stage1(int i) {
+    if (i == 0) angle_axis_unit<0>(trig.sf[0], trig.cf[0], Rx);
+    else if (i == 1) angle_axis_unit<1>(trig.sf[1], trig.cf[1], Ry);
+    else angle_axis_unit<2>(trig.sf[2], trig.cf[2], Rz);
+  }
+  LGS_HD void pose_stage2(int i) { Rxy[i] = mul3f_entry(Rx, Ry, i / 3, i % 3); }
+  LGS_HD void pose_stage3(int i) { R[i] = mul3f_entry(Rxy, Rz, i / 3, i % 3); }
+  // stages 1-4 for ONE entry of the transform without any exchange between threads: thread i (0..15) builds the three axis
+  // rotations and row (i & 3) of Rx * Ry in registers - redundantly, with the functions the staged form calls, so the bits
+  // are the same - and finishes its own entry.  No barriers, no shared-memory round trips: the dependency chain is what counts
+  // on a GPU thread.
+  LGS_HD void pose_entry(int i, Command* c) {
+    const int col = i >> 2, row = i & 3;
+    float v = (i % 5 == 0) ? 1.0f : 0.0f;
+    if (row < 3 && col < 3) {
+      float ax_[9], ay_[9], az_[9];
+      angle_axis_unit<0>(trig.sf[0], trig.cf[0], ax_);
+      angle_axis_unit<1>(trig.sf[1], trig.cf[1], ay_);
+      angle_axis_unit<2>(trig.sf[2], trig.cf[2], az_);
+      float rxy[9];
+      rxy[row * 3 + 0] = mul3f_entry(ax_, ay_, row, 0);
+      rxy[row * 3 + 1] = mul3f_entry(ax_, ay_, row, 1);
+      rxy[row * 3 + 2] = mul3f_entry(ax_, ay_, row, 2);
+      v = mul3f_entry(rxy, az_, row, col);
+    }
+    if (col == 3 && row < 3) v = static_cast<float>(x_t[row]);
+    final_T[i] = v;
+    c->T[i] = v;
+    if (i == 0) c->mode = pose_mode;
+  }
+  LGS_HD void pose_stage4(int i, Command* c) {  // entry i of the column-major transform (NDT.h:214-231); i = 0..15
+    const int col = i >> 2, row = i & 3;
+    float v = (i % 5 == 0) ? 1.0f : 0.0f;
+    if (row < 3 && col < 3) v = R[row * 3 + col];
+    if (col == 3 && row < 3) v = static_cast<float>(x_t[row]);
+    final_T[i] = v;
+    c->T[i] = v;
+    if (i == 0) c->mode = pose_mode;
+  }
+
+  // the whole step on one thread (host driver): returns true and fills *c when another evaluation is needed.  *c must be
+  // the object the previous call (or begin) filled: computeHessian re-uses its transform and tables.
+  LGS_HD bool advance(const double* sums, Command* c) {
+    int action = consume(sums);
+    while (action == kSolve) {
+      solve();
+      action = after_solve();
+    }
+    if (action == kDone) return false;
+    if (action == kHessian) {
+      c->mode = 2;
+      return true;
+    }
+    trig_of_pose(x_t, &trig);
+    for (int i = 0; i < 3; i++) pose_stage1(i);
+    for (int e = 0; e < 69; e++) angle_table_store(trig, codes, e, c->j_ang_d, c->h_ang_d, c->j_ang, c->h_ang);
+    for (int i = 0; i < 9; i++) pose_stage2(i);
+    for (int i = 0; i < 9; i++) pose_stage3(i);
+    for (int i = 0; i < 16; i++) pose_stage4(i, c);
+    return true;
   }
 };
 

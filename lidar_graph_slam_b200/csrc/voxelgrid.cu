@@ -43,13 +43,20 @@ __global__ void bbox_init_kernel(BBoxAcc* acc) {
   }
 }
 
+__device__ __forceinline__ bool finite3(const float4& p) {
+  return (__float_as_uint(p.x) & 0x7f800000u) != 0x7f800000u && (__float_as_uint(p.y) & 0x7f800000u) != 0x7f800000u &&
+         (__float_as_uint(p.z) & 0x7f800000u) != 0x7f800000u;
+}
+
+// pcl::VoxelGrid / getMinMax3D / VGC:210-215 skip points with a non-finite coordinate (clouds that are not is_dense);
+// here every cloud is treated that way: a NaN or Inf point never reaches the bounding box or a voxel.
 __device__ __forceinline__ bool crop_keep(const float4& p, const CropParams& cp) {
-  bool keep = true;
+  bool keep = finite3(p);
   if (cp.range_min >= 0.0) {
     // Eigen Vector3f::norm(): sqrt(x*x + (y*y + z*z)) in f32 (unrolled 3-element redux), compared in f64
     float n2 = __fadd_rn(__fmul_rn(p.x, p.x), __fadd_rn(__fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z)));
     float nrm = __fsqrt_rn(n2);
-    keep = cp.range_min < static_cast<double>(nrm);
+    keep = keep && cp.range_min < static_cast<double>(nrm);
   }
   if (cp.use_box) {
     keep = keep && (cp.box[0] < p.x && p.x < cp.box[1]) && (cp.box[2] < p.y && p.y < cp.box[3]) && (cp.box[4] < p.z && p.z < cp.box[5]);
@@ -221,7 +228,7 @@ int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float 
   LGS_REQUIRE(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0, "leaf size must be positive");
   if (n == 0) return LGS_OK;
   cudaStream_t st = ctx->stream;
-  const bool cropping = range_min >= 0.0 || box6 != nullptr;
+  const bool cropping = true;  // the keep mask is always materialised: it also carries the finiteness test
 
   // arenas: tmp0 keep flags | tmp1 keys | tmp2 vals | tmp3 keys_alt | tmp4 vals_alt | tmp5 head flags, seg_start | tmp6 small
   if (cropping) LGS_TRY(ctx->tmp[0].reserve(n));
@@ -268,8 +275,13 @@ int build_sorted_voxels(lgs_ctx* ctx, const float4* pts, int64_t n, const float 
   }
   // overflow refusal (PCL voxel_grid.hpp; same test at VGC:75-84)
   int64_t d[3];
-  for (int a = 0; a < 3; a++) d[a] = static_cast<int64_t>((mx[a] - mn[a]) * inv[a]) + 1;
-  if (d[0] * d[1] * d[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+  bool too_large = false;
+  for (int a = 0; a < 3; a++) {
+    const float ext = (mx[a] - mn[a]) * inv[a];
+    if (!(ext < 2147483648.0f)) too_large = true;  // also catches an extent that overflowed to inf: no float-to-int cast of it
+    d[a] = too_large ? 0 : static_cast<int64_t>(ext) + 1;
+  }
+  if (too_large || d[0] * d[1] * d[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
     out->status = LGS_VG_REFUSED_OVERFLOW;
     if (voxel_idx_dev) LGS_CUDA(cudaMemsetAsync(voxel_idx_dev, 0xFF, n * sizeof(int), st));
     if (member_rank_dev) LGS_CUDA(cudaMemsetAsync(member_rank_dev, 0xFF, n * sizeof(int), st));

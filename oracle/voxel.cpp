@@ -32,6 +32,9 @@ void prefilter_voxel_grid(const P4* pts, size_t n, const float leaf[3], int min_
   kept.reserve(n);
   for (size_t i = 0; i < n; i++) {
     const P4& p = pts[i];
+    // pcl::VoxelGrid::applyFilter / getMinMax3D on a cloud that is not is_dense (restated at VGC:210-215): points with a
+    // non-finite coordinate are skipped.  Every cloud is treated as not dense here (a dense cloud has none to skip).
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
     if (range_min >= 0.0) {
       const float norm = std::sqrt(sum3f(p.x * p.x, p.y * p.y, p.z * p.z));  // getVector3fMap().norm()
       const double distance = norm;
@@ -121,13 +124,22 @@ void VoxelGridCovariance::build(const P4* pts, size_t n) {
     refused = true;
     return;
   }
+  // VGC:210-215 (and getMinMax3D at VGC:67): a cloud that is not is_dense has its non-finite points skipped
+  auto finite = [&](size_t i) { return std::isfinite(pts[i].x) && std::isfinite(pts[i].y) && std::isfinite(pts[i].z); };
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  size_t n_finite = 0;
   for (size_t i = 0; i < n; i++) {
+    if (!finite(i)) continue;
+    n_finite++;
     const float c[3] = {pts[i].x, pts[i].y, pts[i].z};
     for (int a = 0; a < 3; a++) {
       mn[a] = std::min(mn[a], c[a]);
       mx[a] = std::max(mx[a], c[a]);
     }
+  }
+  if (n_finite == 0) {
+    refused = true;
+    return;
   }
   // VGC:75-84
   int64_t d[3];
@@ -148,6 +160,7 @@ void VoxelGridCovariance::build(const P4* pts, size_t n) {
 
   // first pass, VGC:209-263
   for (size_t cp = 0; cp < n; ++cp) {
+    if (!finite(cp)) continue;
     int ijk0 = static_cast<int>(std::floor(pts[cp].x * inv_leaf[0]) - static_cast<float>(min_b[0]));
     int ijk1 = static_cast<int>(std::floor(pts[cp].y * inv_leaf[1]) - static_cast<float>(min_b[1]));
     int ijk2 = static_cast<int>(std::floor(pts[cp].z * inv_leaf[2]) - static_cast<float>(min_b[2]));

@@ -206,6 +206,75 @@ def test_ndt_large_source_multi_tile(api, oracle):
     _compare_align(g, o, guess)
 
 
+def test_non_finite_points_are_skipped_like_pcl(api, oracle, velodyne_pair):
+    """Clouds that are not is_dense: pcl::VoxelGrid, getMinMax3D and VoxelGridCovariance (VGC:210-215) skip points with a NaN /
+    Inf coordinate.  Such rows must not reach the bounding box, a voxel, a centroid or an NDT leaf - with and without a crop."""
+    cloud = velodyne_pair["target"][:60000].copy()
+    rng = np.random.default_rng(3)
+    bad = rng.choice(len(cloud), 500, replace=False)
+    cloud[bad[:200], 0] = np.nan
+    cloud[bad[200:300], 2] = np.inf
+    cloud[bad[300:400], 1] = -np.inf
+    cloud[bad[400:], :3] = np.nan
+    for crop in (None, 1.0):
+        vg = api.VoxelGrid()
+        vg.setLeafSize(0.2)
+        if crop is not None:
+            vg.setRangeCrop(crop)
+        vg.setInputCloud(cloud)
+        out = vg.filter()
+        ref = oracle.voxel_grid(cloud, 0.2, range_min=-1.0 if crop is None else crop)
+        assert np.isfinite(out).all()
+        assert np.array_equal(vg.voxel_idx, ref["voxel_idx"]) and np.array_equal(vg.member_rank, ref["member_rank"])
+        assert np.array_equal(out, ref["points"])
+        assert (vg.voxel_idx[bad] == -1).all()
+    g, o = _ndt_pair(api, oracle, cloud, velodyne_pair["source"][:30000])
+    vo, valid = _compare_voxels(g, o)
+    assert np.isfinite(vo["mean"]).all() and valid.sum() > 100
+    g.align()
+    o.align()
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD and g.result.iterations == o.nr_iterations  # (getFitnessScore's kd-tree over NaN rows is not defined)
+    # nothing finite at all: the grid is empty, the align returns the guess without touching the device tables
+    g2 = api.NormalDistributionsTransform()
+    g2.setInputTarget(np.full((100, 4), np.nan, np.float32))
+    g2.setInputSource(velodyne_pair["source"][:1000])
+    g2.align()
+    assert g2.grid_info().refused and np.array_equal(g2.getFinalTransformation(), np.eye(4, dtype=np.float32))
+
+
+def test_ndt_device_resident_align_equals_host_stepped(api, velodyne_pair, oracle):
+    """The align as ONE cooperative launch (optimiser resident in CTA 0 of ndt_align_kernel) walks the same path as the host
+    stepping the same state machine with one launch per evaluation: identical iteration / evaluation / trial / computeHessian
+    counts and the same pose, on the bundled pair (several guesses, all three neighbourhoods) and on cfg 0."""
+    from lidar_graph_slam_b200 import synth
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    d = synth.ndt_scan_to_map()
+    cases = [(td, sd, dict(res=1.0, eps=0.01, it=64), [None, velodyne_pair["relative"].astype(np.float32), _pose(0.3, -0.2, 0.05, 0.03)]),
+             (td, sd, dict(res=2.0, eps=0.01, it=64, method=api.NDT_DIRECT1), [None]),
+             (td, sd, dict(res=1.0, eps=0.001, it=30, method=api.NDT_DIRECT26), [None]),
+             (d["target"], d["source"], dict(res=1.0, eps=0.01, it=64), [d["guess"]])]
+    launches = []
+    for tgt, src, kw, guesses in cases:
+        a, _ = _ndt_pair(api, oracle, tgt, src, **kw)
+        b, _ = _ndt_pair(api, oracle, tgt, src, **kw)
+        b.profile(1)  # per-evaluation timing: the host steps the optimiser
+        for G in guesses:
+            l0 = a.ctx.launch_count
+            a.align(G)
+            launches.append(a.ctx.launch_count - l0)
+            b.align(G)
+            ra, rb = a.result, b.result
+            assert (ra.iterations, ra.converged, ra.evaluations, ra.line_search_trials, ra.hessian_recomputes) == \
+                (rb.iterations, rb.converged, rb.evaluations, rb.line_search_trials, rb.hessian_recomputes)
+            t_err, r_err = pose_error(b.getFinalTransformation(), a.getFinalTransformation())
+            assert t_err < 1e-6 and r_err < 1e-6
+            assert ra.trans_probability == pytest.approx(rb.trans_probability, rel=1e-9)
+        b.profile(0)
+    assert all(l == 1 for l in launches), launches  # one kernel launch per align
+
+
 def test_ndt_cfg0_synthetic_scan_to_map(api, oracle):
     """BASELINE configs[0]: 120 000-point 64-beam sweep against a 1 000 000-point local map, DIRECT7, 1.0 m."""
     from lidar_graph_slam_b200 import synth

@@ -381,6 +381,28 @@ def test_exact_sums_product_equals_oracle(tmp_path):
     assert out.returncode == 0 and "0 failures" in out.stdout, out.stdout[-2000:]
 
 
+def test_sinf_cosf_restatement_equals_libm(tmp_path):
+    """The device-resident NDT optimiser builds its f32 transforms on the GPU: its sinf / cosf (csrc/ndt_opt.cuh, a restatement
+    of glibc's) must return the C library's bits, or every transformed point moves.  Strided sweep of all |x| < 120."""
+    import subprocess
+    exe = str(tmp_path / "sincos_check")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "lidar_graph_slam_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "sincos_check.cpp"), "-o", exe, "-lm"])
+    out = subprocess.run([exe, "499"], capture_output=True, text=True)
+    assert out.returncode == 0 and " 0 failures" in out.stdout, out.stdout[-2000:]
+
+
+def test_ndt_optimiser_pieces_equal_reference_forms(tmp_path):
+    """csrc/ndt_opt.cuh on the host: the table-driven angular tables equal the reference's expressions (NDT:329-392) bit for bit, and
+    the Newton step's elimination equals the JacobiSVD solve (NDT:127-129) to 1e-9 and hands singular systems back to it."""
+    import subprocess
+    exe = str(tmp_path / "ndt_opt_check")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "lidar_graph_slam_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "ndt_opt_check.cpp"), "-o", exe, "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("0 failures"), out.stdout[-2000:]
+
+
 def test_ndt_convert_transform_host_function(oracle):
     """static convertTransform (NDT.h:214-238) is host arithmetic in the product too: bit-identical to the oracle's, no GPU needed."""
     from lidar_graph_slam_b200 import api
