@@ -4,6 +4,7 @@ import ctypes
 import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -317,6 +318,93 @@ def test_pcl_style_registrations_are_thread_count_invariant(oracle, velodyne_pai
     b.align()
     t_err, r_err = pose_error(velodyne_pair["relative"], np.linalg.inv(b.final_transformation.astype(np.float64)))
     assert b.converged and t_err < 0.05 and np.degrees(r_err) < 1.0
+
+
+def _guess_matrix(g):
+    if g is None:
+        return None
+    T = np.eye(4, dtype=np.float32)
+    c, s_ = np.cos(g[3]), np.sin(g[3])
+    T[:2, :2] = [[c, -s_], [s_, c]]
+    T[:3, 3] = g[:3]
+    return T
+
+
+def test_oracle_matches_independent_numpy_scipy_restatement(oracle, velodyne_pair):
+    """The second pin of the oracle: tests/golden/independent_restatement.py states NDT and FastGICP again with LAPACK
+    (eigh / svd / solve), scipy's cKDTree and Rotation, analytic pose derivatives and f64 arithmetic - none of the oracle's own
+    Jacobi / QR / LDLT / kd-tree code.  On the bundled Velodyne pair the C++ oracle must walk the same path: identical
+    iteration / evaluation / line-search / computeHessian counts, poses within 2e-6 (f32 transforms), scores and gradients to
+    1e-6, the f64 Hessian to 1e-9 - for three NDT configurations and two FastGICP ones.  (Frozen by make_reference_fixtures.py.)"""
+    fx = json.load(open(os.path.join(GOLDEN, "independent_restatement.json")))
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    vg = fx["voxel_grid"]["0.2"]
+    assert (len(td), len(sd)) == (vg["n_target"], vg["n_source"])
+    assert float(td.astype(np.float64).sum()) == vg["target_checksum"] and float(sd.astype(np.float64).sum()) == vg["source_checksum"]
+    for name, f in fx["ndt"].items():
+        n = oracle.NDT()
+        n.setNumThreads(1)
+        n.setResolution(f["resolution"])
+        n.setTransformationEpsilon(f["eps"])
+        n.setMaximumIterations(f["max_iter"])
+        n.setStepSize(0.1)
+        n.setInputTarget(td)
+        n.setInputSource(sd)
+        n.align(_guess_matrix(f["guess"]))
+        assert (n.nr_iterations, n.converged) == (f["iterations"], f["converged"]), name
+        assert (n.stats["derivative_evals"], n.stats["line_search_trials"], n.stats["hessian_recomputes"]) == \
+            (f["evaluations"], f["trials"], f["hessian_recomputes"]), name
+        np.testing.assert_allclose(n.final_transformation, np.array(f["T"]).reshape(4, 4), atol=2e-6)
+        assert n.trans_probability == pytest.approx(f["trans_probability"], rel=1e-5)
+        assert n.getFitnessScore() == pytest.approx(f["fitness"], rel=1e-5)
+        v = n.export_voxels()
+        assert (len(v["idx"]), int((v["n"] >= 6).sum())) == (f["n_voxels"], f["n_valid_voxels"])
+        p = np.array(f["probe"]["p"])
+        T = oracle.ndt_convert_transform(p)
+        s0, g0, H0 = n.derivatives(T, p, 0)
+        _, _, H2 = n.derivatives(T, p, 2)
+        Hn = np.array(f["probe"]["hessian"]).reshape(6, 6)
+        assert s0 == pytest.approx(f["probe"]["score"], rel=1e-6)
+        np.testing.assert_allclose(g0, f["probe"]["gradient"], rtol=0, atol=1e-6 * np.abs(g0).max())
+        np.testing.assert_allclose(H0, Hn, rtol=0, atol=1e-6 * np.abs(Hn).max())   # f32 terms against f64
+        np.testing.assert_allclose(H2, Hn, rtol=0, atol=1e-9 * np.abs(Hn).max())   # computeHessian is f64 on both sides
+    for name, f in fx["fast_gicp"].items():
+        g = oracle.FastGICP()
+        g.setNumThreads(1)
+        if "max_corr" in f["params"]:
+            g.setMaxCorrespondenceDistance(f["params"]["max_corr"])
+            g.setMaximumIterations(int(f["params"]["max_iter"]))
+            g.setTransformationEpsilon(f["params"]["trans_eps"])
+        g.setInputTarget(td)
+        g.setInputSource(sd)
+        g.align(_guess_matrix(f["guess"]))
+        assert (g.nr_iterations, g.converged, g.stats["linearize_calls"], g.stats["error_calls"]) == \
+            (f["iterations"], f["converged"], f["linearize_calls"], f["compute_error_calls"]), name
+        np.testing.assert_allclose(g.final_transformation, np.array(f["T"]).reshape(4, 4), atol=1e-6)
+        assert g.getFitnessScore() == pytest.approx(f["fitness"], rel=1e-6)
+
+
+def test_independent_restatement_reproduces_its_frozen_fixture(velodyne_pair):
+    """The frozen numbers are what the committed numpy / scipy code computes today (one NDT and one FastGICP case, live)."""
+    sys.path.insert(0, GOLDEN)
+    import independent_restatement as R
+    fx = json.load(open(os.path.join(GOLDEN, "independent_restatement.json")))
+    td, sd = R.voxel_grid(velodyne_pair["target"], 0.2), R.voxel_grid(velodyne_pair["source"], 0.2)
+    f = fx["ndt"]["product_offset_guess"]
+    n = R.NDT(resolution=f["resolution"], step_size=0.1, trans_eps=f["eps"], max_iter=f["max_iter"])
+    n.set_target(td)
+    n.set_source(sd)
+    n.align(_guess_matrix(f["guess"]))
+    assert (n.iterations, n.stats["evals"], n.stats["trials"], n.stats["hess"]) == (f["iterations"], f["evaluations"], f["trials"], f["hessian_recomputes"])
+    np.testing.assert_allclose(n.final_T, np.array(f["T"]).reshape(4, 4), atol=1e-7)
+    f = fx["fast_gicp"]["gtest_recipe"]
+    g = R.FastGICP()
+    g.set_target(td)
+    g.set_source(sd)
+    g.align()
+    assert g.iterations == f["iterations"]
+    np.testing.assert_allclose(g.final_T, np.array(f["T"]).reshape(4, 4), atol=1e-7)
 
 
 def test_knn_against_scipy(oracle, velodyne_pair):
