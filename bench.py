@@ -279,49 +279,71 @@ def loop_closure_bench(rank, world, device, n_total, n_host_pairs):
     return out
 
 
-def gicp_odometry_bench(device, stream, ctx, n_sweeps=8, reps=3):
-    """configs[2] in miniature (the GICP half of BASELINE's metric): scan-to-scan FastGICP over consecutive 120 000-ray
-    64-beam sweeps, each VoxelGrid 0.25 m + range crop (kitti.cpp:80-82), covariance reuse through swapSourceAndTarget
-    (kitti.cpp:115-125).  A frame = prefilter of the host sweep + setInputSource + align + swap; CUDA events per frame."""
+def gicp_odometry_bench(device, stream, ctx, n_sweeps):
+    """configs[2] (the GICP half of BASELINE's metric): scan-to-scan FastGICP over `n_sweeps` (1000) consecutive 120 000-ray
+    64-beam sweeps of a 1 km drive, each VoxelGrid 0.25 m + range crop (kitti.cpp:80-82), covariance reuse through
+    swapSourceAndTarget (kitti.cpp:115-125).  A frame = H2D of the pinned host sweep + prefilter + setInputSource + align +
+    swap; CUDA events per frame.  Also reports the accumulated trajectory's drift against the synthetic ground truth."""
     import torch
     from lidar_graph_slam_b200 import api, synth
-    sweeps, poses = synth.odometry_sequence(n_sweeps)
-    pinned = [torch.from_numpy(s).pin_memory() for s in sweeps]
+    sweeps_dev, poses = synth.long_drive(n_sweeps, device="cuda:%d" % device)
+    n_stage = min(n_sweeps, 64)  # a ring of pinned host buffers: the sweep of frame k arrives from host memory
+    ring = [torch.empty((sweeps_dev.shape[1], 4), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
     vg = api.VoxelGrid(ctx)
     vg.setLeafSize(0.25)
     vg.setRangeCrop(1.0)
     g = api.FastGICP(ctx)
     g.setMaxCorrespondenceDistance(1.0)
 
-    def frame(k, first):
-        # host sweep -> device once; the filtered cloud stays on the device for setInputSource (no D2H / H2D in between)
-        vg.setInputCloud(pinned[k].cuda(device, non_blocking=True))
+    def frame(k, host):
+        vg.setInputCloud(host.cuda(device, non_blocking=True))  # host sweep -> device once; the filtered cloud stays there
         ds = vg.filter(want_membership=False)
-        if first:
+        if k == 0:
             g.setInputTarget(ds)
-            return ds.shape[0]
+            return None, ds.shape[0]
         g.setInputSource(ds)
         g.align()
         T = g.getFinalTransformation()
         g.swapSourceAndTarget()
-        return T
+        return T, ds.shape[0]
 
-    ms, n_frames, err = 0.0, 0, 0.0
-    for r in range(reps + 1):  # first pass warms every buffer
-        frame(0, True)
-        for k in range(1, n_sweeps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            T = frame(k, False)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            if r:
-                ms += e0.elapsed_time(e1)
-                n_frames += 1
-                E = np.linalg.inv(np.linalg.inv(poses[k - 1]) @ poses[k]) @ T.astype(np.float64)
-                err = max(err, float(np.linalg.norm(E[:3, 3])))
-    return {"frames_per_sec": n_frames / (ms * 1e-3), "ms_per_frame": ms / n_frames, "frames": n_frames, "max_pose_error_m": err,
-            "method": "FastGICP k=20, max_corr 1.0; per frame: H2D of the 120000-ray pinned host sweep, VoxelGrid 0.25 m + range crop, setInputSource (device cloud), align, swapSourceAndTarget"}
+    for w in range(2):  # warm-up over the first frames
+        for k in range(min(4, n_sweeps)):
+            ring[k % n_stage].copy_(sweeps_dev[k])
+            frame(k, ring[k % n_stage])
+    ms, X, worst, worst_rot, n_pts, passes = [], np.eye(4), 0.0, 0.0, [], 0
+    for k in range(n_sweeps):
+        ring[k % n_stage].copy_(sweeps_dev[k])  # D2H staging of the synthetic sweep, outside the timed region
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        T, npt = frame(k, ring[k % n_stage])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        n_pts.append(npt)
+        if k:
+            ms.append(e0.elapsed_time(e1))
+            passes += g.result.evaluations + g.result.line_search_trials
+            E = np.linalg.inv(np.linalg.inv(poses[k - 1]) @ poses[k]) @ T.astype(np.float64)
+            worst = max(worst, float(np.linalg.norm(E[:3, 3])))
+            worst_rot = max(worst_rot, float(np.degrees(np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)))))
+            X = X @ T.astype(np.float64)
+    ms = np.array(ms)
+    D = np.linalg.inv(np.linalg.inv(poses[0]) @ poses[-1]) @ X
+    n_mean = float(np.mean(n_pts))
+    # algorithmic bytes of a frame (SURVEY.md section 8d): prefilter (16 N + 16 V) + k-NN covariances of the new cloud
+    # (16 + 24 B per point) + every linearisation / error pass (N_s (16 + 24 + 16 + 24))
+    n_rays = float(sweeps_dev.shape[1])
+    bytes_frame = 16 * n_rays + 16 * n_mean + 40 * n_mean + (passes / max(len(ms), 1)) * n_mean * 80
+    peak, _ = measured_peak_hbm()
+    fps = len(ms) / (ms.sum() * 1e-3)
+    del sweeps_dev
+    torch.cuda.empty_cache()
+    return {"frames_per_sec": fps, "ms_per_frame": {"mean": float(ms.mean()), "median": float(np.median(ms)), "min": float(ms.min()), "max": float(ms.max())},
+            "frames": int(len(ms)), "sweeps": n_sweeps, "mean_points_after_prefilter": n_mean, "passes_per_frame": passes / max(len(ms), 1),
+            "max_frame_pose_error_m": worst, "max_frame_rotation_error_deg": worst_rot, "trajectory_drift_m": float(np.linalg.norm(D[:3, 3])), "distance_driven_m": float(n_sweeps - 1),
+            "algorithmic_bytes_per_frame": bytes_frame, "achieved_gbs": bytes_frame * fps / 1e9, "frac_of_hbm_peak": bytes_frame * fps / 1e9 / peak,
+            "method": "FastGICP k=20, max_corr 1.0; per frame: H2D of the 120000-ray pinned host sweep, VoxelGrid 0.25 m + range crop, setInputSource (device cloud), align, swapSourceAndTarget; poses[i] = poses[i-1] * T"}
 
 
 def main():
@@ -333,6 +355,7 @@ def main():
     ap.add_argument("--loop-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_PAIRS", 4096),
                     help="loop-closure candidates in TOTAL (BASELINE configs[4]: 4096; strong scaling over --gpus; 0 disables)")
     ap.add_argument("--loop-host-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_HOST_PAIRS", 128), help="sample of pairs verified from host arrays")
+    ap.add_argument("--odometry-sweeps", type=int, default=_env_int("LGS_BENCH_ODOMETRY_SWEEPS", 1000), help="configs[2]: sweeps of the GICP odometry run (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
@@ -468,7 +491,7 @@ def main():
     gicp_odo = None
     if rank == 0 and world == 1:  # reported at N = 1 only (single-scan odometry does not shard)
         try:
-            gicp_odo = gicp_odometry_bench(local_rank, stream, ctx)
+            gicp_odo = gicp_odometry_bench(local_rank, stream, ctx, args.odometry_sweeps) if args.odometry_sweeps > 0 else None
         except Exception as e:
             gicp_odo = {"error": repr(e)}
 

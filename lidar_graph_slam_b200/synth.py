@@ -299,6 +299,103 @@ def odometry_sequence(n_sweeps=8, n_beams=64, n_azimuth=1875, spacing=1.0, seed=
     return [d["sweep%d" % k] for k in range(n_sweeps)], [d["pose%d" % k] for k in range(n_sweeps)]
 
 
+# ---- cfg 2 at its full size: 1000 sweeps along a 1 km drive ------------------------------------------------------------------
+LONG_WORLD = dict(n_boxes=1800, n_cyl=2700, extent=600.0)  # the 400 m world's density over 1200 m x 1200 m
+
+
+def long_drive_pose(k, n_sweeps=1000, spacing=1.0):
+    """Pose of sweep k of the long drive: the 1 km spline of SURVEY section 8d, centred in the large world."""
+    x = (k - n_sweeps / 2) * spacing
+    return pose_matrix(x, 0.8 * np.sin(0.05 * x), 0.03 * np.sin(0.07 * x))
+
+
+def cast_sweep_torch(world, pose, frame, device, n_beams=64, n_azimuth=1875, elev=(-24.8, 2.0), noise_sigma=0.02):
+    """cast_sweep with the ray / primitive tests as torch ops on `device` (the same geometry, f64; the range noise is the
+    same counter-based stream, drawn with numpy).  Thousand-sweep workloads (cfg 2) are cast in seconds instead of tens of
+    minutes.  Test-data generation only: the product never calls this.  Returns a float32 (n, 4) tensor on `device`."""
+    import torch
+    f64 = torch.float64
+    dirs_s = torch.from_numpy(beam_directions(n_beams, n_azimuth, elev[0], elev[1])).to(device)
+    R = torch.from_numpy(np.ascontiguousarray(pose[:3, :3])).to(device)
+    o_np = pose[:3, 3]
+    n = dirs_s.shape[0]
+    bc = 0.5 * (world.box_min + world.box_max)
+    br = 0.5 * np.linalg.norm(world.box_max - world.box_min, axis=1)
+    bsel = np.linalg.norm(bc[:, :2] - o_np[None, :2], axis=1) < R_MAX + br
+    csel = np.linalg.norm(world.cyl_c - o_np[None, :2], axis=1) < R_MAX + 1.0
+    bmin = torch.from_numpy(world.box_min[bsel]).to(device)
+    bmax = torch.from_numpy(world.box_max[bsel]).to(device)
+    cc = torch.from_numpy(world.cyl_c[csel]).to(device)
+    cr = torch.from_numpy(world.cyl_r[csel]).to(device)
+    ch = torch.from_numpy(world.cyl_h[csel]).to(device)
+    o = torch.from_numpy(np.ascontiguousarray(o_np)).to(device)
+    inf = torch.tensor(float("inf"), dtype=f64, device=device)
+    d = dirs_s @ R.T
+    tg = torch.where(d[:, 2] < -1e-9, -o[2] / d[:, 2], inf)
+    tb = tg.clone()
+    ci = torch.where(torch.isfinite(tg), d[:, 2].abs(), torch.zeros_like(tg))
+    ar = torch.arange(n, device=device)
+    if bmin.shape[0]:
+        inv = 1.0 / d
+        t0 = (bmin[None, :, :] - o[None, None, :]) * inv[:, None, :]
+        t1 = (bmax[None, :, :] - o[None, None, :]) * inv[:, None, :]
+        tn, tf = torch.minimum(t0, t1), torch.maximum(t0, t1)
+        m01 = torch.maximum(tn[:, :, 0], tn[:, :, 1])
+        tnear = torch.maximum(m01, tn[:, :, 2])
+        axis = torch.where(tn[:, :, 1] > tn[:, :, 0], 1, 0)
+        axis = torch.where(tn[:, :, 2] > m01, 2, axis)
+        tfar = torch.minimum(torch.minimum(tf[:, :, 0], tf[:, :, 1]), tf[:, :, 2])
+        hit = (tnear <= tfar) & (tnear > 1e-6)
+        tnear = torch.where(hit, tnear, inf)
+        tt, j = tnear.min(dim=1)
+        ax = axis[ar, j]
+        upd = tt < tb
+        tb = torch.where(upd, tt, tb)
+        ci = torch.where(upd, d[ar, ax].abs(), ci)
+    if cc.shape[0]:
+        ox, oy = o[0] - cc[None, :, 0], o[1] - cc[None, :, 1]
+        a = (d[:, 0] ** 2 + d[:, 1] ** 2)[:, None]
+        b = 2.0 * (d[:, 0:1] * ox + d[:, 1:2] * oy)
+        c = ox * ox + oy * oy - cr[None, :] ** 2
+        disc = b * b - 4.0 * a * c
+        tc = (-b - torch.sqrt(torch.where(disc > 0, disc, torch.full_like(disc, float("nan"))))) / (2.0 * a)
+        zc = o[2] + tc * d[:, 2:3]
+        ok = (disc > 0) & (tc > 1e-6) & (zc >= 0.0) & (zc <= ch[None, :])
+        tc = torch.where(ok, tc, inf)
+        tt, j = tc.min(dim=1)
+        upd = tt < tb
+        tsafe = torch.where(torch.isfinite(tt), tt, torch.zeros_like(tt))
+        hx = o[0] + tsafe * d[:, 0] - cc[j, 0]
+        hy = o[1] + tsafe * d[:, 1] - cc[j, 1]
+        cosc = (hx * d[:, 0] + hy * d[:, 1]).abs() / torch.clamp(torch.hypot(hx, hy), min=1e-9)
+        tb = torch.where(upd, tt, tb)
+        ci = torch.where(upd, torch.nan_to_num(cosc), ci)
+    rng = tb + noise_sigma * torch.from_numpy(_normal(frame, n)).to(device)
+    valid = torch.isfinite(tb) & (rng >= R_MIN) & (rng <= R_MAX)
+    pts = dirs_s * torch.where(valid, rng, torch.zeros_like(rng))[:, None]
+    pw = pts @ R.T
+    wx, wy = pw[:, 0] + o[0], pw[:, 1] + o[1]
+    is_ground = valid & ((pw[:, 2] + o[2]).abs() < 0.2)
+    bump = 0.02 * (0.6 * torch.sin(0.31 * wx + 1.3) * torch.cos(0.27 * wy) + 0.4 * torch.sin(0.73 * wx - 0.41 * wy + 0.5))
+    pts[:, 2] += torch.where(is_ground, bump, torch.zeros_like(bump))
+    out = torch.zeros((n, 4), dtype=torch.float32, device=device)
+    out[:, :3] = torch.where(valid[:, None], pts, torch.zeros_like(pts)).to(torch.float32)
+    out[:, 3] = torch.where(valid, ci, torch.zeros_like(ci)).to(torch.float32)
+    return out
+
+
+def long_drive(n_sweeps=1000, device="cuda", n_beams=64, n_azimuth=1875, spacing=1.0, seed=SEED):
+    """cfg 2: `n_sweeps` consecutive 64-beam sweeps (120 000 rays each) 1 m apart along the 1 km spline, with their true
+    poses.  Returns (float32 tensor (n_sweeps, n_rays, 4) on `device`, list of 4x4 poses)."""
+    import torch
+    w = World(seed, **LONG_WORLD)
+    poses = [long_drive_pose(k, n_sweeps, spacing) for k in range(n_sweeps)]
+    out = torch.empty((n_sweeps, n_beams * n_azimuth, 4), dtype=torch.float32, device=device)
+    for k in range(n_sweeps):
+        out[k] = cast_sweep_torch(w, poses[k], 60_000 + k, device, n_beams=n_beams, n_azimuth=n_azimuth)
+    return out, poses
+
+
 def loop_pairs(n_pairs=8, n_keyframes=41, n_beams=64, n_azimuth=1875, scan_leaf=0.2, key_leaf=0.2, seed=SEED, n_unique=4):
     """cfg 4: (scan, submap) candidate pairs.  scan = scan_leaf-filtered sweep expressed in the map frame with a
     seeded offset <= (2 m, 5 deg) from its true pose; submap = concatenation of `n_keyframes` consecutive keyframe

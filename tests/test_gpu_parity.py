@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star / SURVEY.md section 8d): voxel indices, occupancy, membership and output order are
 bit-exact; voxel mean / inverse covariance rel 1e-9; final transforms within 1e-4 m / 1e-4 rad; fitness and
 transformation probability within 1e-5 relative; identical iteration counts and convergence flags."""
+import os
+
 import numpy as np
 import pytest
 
@@ -832,6 +834,73 @@ def test_gicp_cfg2_synthetic_odometry(api, oracle):
         assert t_err < 0.1 and r_err < np.radians(1.0)
         for x in (g, o):
             x.swapSourceAndTarget()
+
+
+def test_gicp_cfg2_long_drive_1000_sweeps(api, oracle):
+    """BASELINE configs[2] at its full size (kitti.cpp:80-82, 115-138): scan-to-scan FastGICP odometry over 1000 consecutive
+    120 000-ray sweeps of a 1 km drive, VoxelGrid 0.25 m + range crop, max_corr 1.0, covariance reuse through
+    swapSourceAndTarget, pose accumulated as poses[i] = poses[i-1] * T.
+      * every frame: converged, per-frame pose within 3 cm / 0.1 deg of the synthetic ground truth (the accumulated
+        trajectory's drift is whatever scan-to-scan GICP drifts on this scene - it is compared with the oracle, not the truth);
+      * a sample of frames (every 25th + a contiguous run of 24) against the oracle at the full tolerances - per-frame T within
+        1e-4 m / 1e-4 rad, same nr_iterations - and the trajectory accumulated over the contiguous run within 5e-4 m."""
+    import torch
+    from lidar_graph_slam_b200 import synth
+    n = int(os.environ.get("LGS_CFG2_SWEEPS", 1000))
+    sweeps, poses = synth.long_drive(n, device="cuda")
+    vg = api.VoxelGrid()
+    vg.setLeafSize(0.25)
+    vg.setRangeCrop(1.0)
+    g = api.FastGICP()
+    g.setMaxCorrespondenceDistance(1.0)
+    run0 = n // 2
+    sample = sorted(set(range(25, n, 25)) | set(range(run0, min(run0 + 24, n))))
+    need = set(sample) | {k - 1 for k in sample}
+    host, rel, iters, n_pts = {}, [None], [0], []
+    for k in range(n):
+        vg.setInputCloud(sweeps[k])
+        ds = vg.filter(want_membership=False)
+        n_pts.append(int(ds.shape[0]))
+        if k in need:
+            host[k] = ds.cpu().numpy()
+        if k == 0:
+            g.setInputTarget(ds)
+            continue
+        g.setInputSource(ds)
+        g.align()
+        assert g.hasConverged(), k
+        rel.append(g.getFinalTransformation().astype(np.float64))
+        iters.append(g.result.iterations)
+        g.swapSourceAndTarget()
+    assert min(n_pts) > 15000
+    # ground truth: per-frame and accumulated
+    X = np.eye(4)
+    worst_t = worst_r = 0.0
+    for k in range(1, n):
+        true_rel = np.linalg.inv(poses[k - 1]) @ poses[k]
+        t_err, r_err = pose_error(true_rel, rel[k])
+        worst_t, worst_r = max(worst_t, t_err), max(worst_r, r_err)
+        X = X @ rel[k]
+    assert worst_t < 0.03 and worst_r < np.radians(0.1), (worst_t, worst_r)
+    assert np.isfinite(X).all()
+    # the oracle on the sampled frames
+    acc_g, acc_o = np.eye(4), np.eye(4)
+    for k in sample:
+        o = oracle.FastGICP()
+        o.setMaxCorrespondenceDistance(1.0)
+        o.setInputTarget(host[k - 1])
+        o.setInputSource(host[k])
+        o.align()
+        t_err, r_err = pose_error(o.final_transformation, rel[k])
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD, (k, t_err, r_err)
+        assert iters[k] == o.nr_iterations and o.converged, k
+        if run0 <= k < run0 + 24:
+            acc_g = acc_g @ rel[k]
+            acc_o = acc_o @ o.final_transformation.astype(np.float64)
+    t_err, r_err = pose_error(acc_o, acc_g)
+    assert t_err < 5e-4 and r_err < 5e-4, (t_err, r_err)
+    del sweeps
+    torch.cuda.empty_cache()
 
 
 def test_batch_loop_closure_matches_single_pair_runs(api, oracle):
