@@ -276,6 +276,11 @@ def loop_closure_bench(rank, world, device, n_total, n_host_pairs):
         except Exception as e:
             out["from_host_arrays"] = {"error": repr(e)}
     comm.close()
+    del kf
+    import gc
+    gc.collect()
+    api.batch_release()
+    torch.cuda.synchronize()
     return out
 
 
@@ -307,10 +312,14 @@ def gicp_odometry_bench(device, stream, ctx, n_sweeps):
         g.swapSourceAndTarget()
         return T, ds.shape[0]
 
-    for w in range(2):  # warm-up over the first frames
-        for k in range(min(4, n_sweeps)):
-            ring[k % n_stage].copy_(sweeps_dev[k])
-            frame(k, ring[k % n_stage])
+    import gc
+    gc.collect()  # device buffers of earlier bench sections are released now, not inside a timed frame
+    torch.cuda.synchronize()
+    for k in list(range(0, n_sweeps, max(1, n_sweeps // 24))) + [0, 1, 2, 3]:  # warm-up across the drive: every staging buffer reaches its final size
+        ring[k % n_stage].copy_(sweeps_dev[k])
+        frame(k if k < 4 else 1, ring[k % n_stage])
+    ring[0].copy_(sweeps_dev[0])
+    frame(0, ring[0])
     ms, X, worst, worst_rot, n_pts, passes = [], np.eye(4), 0.0, 0.0, [], 0
     for k in range(n_sweeps):
         ring[k % n_stage].copy_(sweeps_dev[k])  # D2H staging of the synthetic sweep, outside the timed region
@@ -346,6 +355,63 @@ def gicp_odometry_bench(device, stream, ctx, n_sweeps):
             "method": "FastGICP k=20, max_corr 1.0; per frame: H2D of the 120000-ray pinned host sweep, VoxelGrid 0.25 m + range crop, setInputSource (device cloud), align, swapSourceAndTarget; poses[i] = poses[i-1] * T"}
 
 
+def big_map_bench(device, stream, ctx, sweeps_dev, guesses, poses, reps=12):
+    """configs[3]: NDT scan-to-submap against the 20 M-point rolling map at 1.0 m and 0.5 m: target build (voxelisation of all
+    20 M resident points, what a key-frame change costs today) and aligns/s with the map resident, with their HBM fractions."""
+    import torch
+    from lidar_graph_slam_b200 import api, synth
+    d = synth.rolling_map()
+    tgt = torch.from_numpy(d["target"]).cuda(device)
+    peak, _ = measured_peak_hbm()
+    out = {"n_target": int(tgt.shape[0])}
+    for res in (1.0, 0.5):
+        ndt = api.NormalDistributionsTransform(ctx)
+        ndt.setResolution(res)
+        ndt.setStepSize(NDT_PARAMS["step"])
+        ndt.setTransformationEpsilon(NDT_PARAMS["eps"])
+        ndt.setMaximumIterations(NDT_PARAMS["max_iter"])
+        ndt.setInputTarget(tgt)
+        builds = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ndt.setInputTarget(tgt)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            builds.append(e0.elapsed_time(e1))
+        gi = ndt.grid_info()
+        src = torch.from_numpy(d["source"]).cuda(device)
+        ndt.setInputSource(src)
+        ndt.align(d["guess"])
+        ndt.profile(2)
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ndt.setInputSource(src)
+            ndt.align(d["guess"])
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        prof = ndt.profile(0)
+        E = np.linalg.inv(d["T_true"]) @ ndt.getFinalTransformation().astype(np.float64)
+        nl = max(prof["align_launches"], 1)
+        alg = (prof["evaluations"] * prof["n_source"] * (16 + 7 * 8) + 40.0 * prof["terms"]) / nl
+        kms = prof["align_ms"] / nl
+        build_bytes = 16.0 * tgt.shape[0] + 48.0 * gi.n_voxels
+        bms = float(np.median(builds))
+        out["res_%.1f" % res] = {"target_build_ms": bms, "target_build_gbs": build_bytes / (bms * 1e-3) / 1e9, "target_build_frac_of_hbm_peak": build_bytes / (bms * 1e-3) / 1e9 / peak,
+                                 "voxels": int(gi.n_voxels), "valid_voxels": int(gi.n_valid), "cell_table": "dense" if gi.dense else "hash",
+                                 "aligns_per_sec": 1e3 / float(np.median(ms)), "ms_per_align_median": float(np.median(ms)), "iterations": int(ndt.result.iterations),
+                                 "evaluations": int(ndt.result.evaluations + ndt.result.hessian_recomputes), "align_kernel_ms": kms,
+                                 "align_kernel_gbs": alg / (kms * 1e-3) / 1e9 if kms > 0 else 0.0, "align_kernel_frac_of_hbm_peak": alg / (kms * 1e-3) / 1e9 / peak if kms > 0 else 0.0,
+                                 "pose_error_m": float(np.linalg.norm(E[:3, 3]))}
+        del ndt
+    del tgt
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,6 +423,7 @@ def main():
     ap.add_argument("--loop-host-pairs", type=int, default=_env_int("LGS_BENCH_LOOP_HOST_PAIRS", 128), help="sample of pairs verified from host arrays")
     ap.add_argument("--odometry-sweeps", type=int, default=_env_int("LGS_BENCH_ODOMETRY_SWEEPS", 1000), help="configs[2]: sweeps of the GICP odometry run (0 disables)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-big-map", action="store_true", help="skip configs[3] (20 M-point map)")
     args = ap.parse_args()
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
 
@@ -495,6 +562,13 @@ def main():
         except Exception as e:
             gicp_odo = {"error": repr(e)}
 
+    big = None
+    if rank == 0 and world == 1 and not args.no_big_map:
+        try:
+            big = big_map_bench(local_rank, stream, ctx, sweeps_dev, guesses, poses)
+        except Exception as e:
+            big = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(target, sweeps, guesses)
@@ -529,7 +603,7 @@ def main():
                                                           "ndt_derivatives_kernel<1> (score + g)": prof1["grad_ms"] / max(prof1["grad_launches"], 1),
                                                           "ndt_derivatives_kernel<2> (f64 Hessian)": prof1["h64_ms"] / max(prof1["h64_launches"], 1),
                                                           "note": "the same evaluation body launched once per evaluation (host-stepped optimiser), separate pass"}},
-            "cpu_baseline": cpu, "clocks": clocks, "loop_closure": loop, "gicp_odometry": gicp_odo,
+            "cpu_baseline": cpu, "clocks": clocks, "loop_closure": loop, "gicp_odometry": gicp_odo, "big_map_20m": big,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

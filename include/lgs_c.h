@@ -174,7 +174,10 @@ int lgs_ndt_set_search_method(lgs_ndt* ndt, int32_t method);            /* NDT.h
  * the target cloud in place and passes the same pointer again (LSM:187-212). */
 int lgs_ndt_set_target(lgs_ndt* ndt, const void* pts, int64_t n, int32_t stride_bytes);
 int lgs_ndt_set_source(lgs_ndt* ndt, const void* pts, int64_t n, int32_t stride_bytes);   /* setInputSource, LSM:162 */
-/* device-resident variants (packed float4 xyzi already in HBM) */
+/* device-resident variants (packed float4 xyzi already in HBM).  Lifetime contract of every *_dev setter in this header:
+ * the cloud is copied device-to-device on the CONTEXT's stream and the call may return before the copy has run, so
+ * pts_dev must stay valid (and unmodified) until lgs_ctx_synchronize(ctx) or any later call on the same object that
+ * returns a result to the host; a context created on the caller's own stream makes this ordinary stream ordering. */
 int lgs_ndt_set_target_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
 int lgs_ndt_set_source_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
 /* align (pcl::Registration::align + NDT:80-171, LSM:165, GBS:318).  guess may be NULL (identity).
@@ -314,6 +317,10 @@ int lgs_icp_set_maximum_iterations(lgs_icp* icp, int32_t n);               /* GB
 int lgs_icp_set_transformation_epsilon(lgs_icp* icp, double eps);          /* GBS:147 (compared with the SQUARED translation, as in PCL) */
 int lgs_icp_set_transformation_rotation_epsilon(lgs_icp* icp, double eps); /* cos(angle) threshold; 0 = 1 - transformation_epsilon */
 int lgs_icp_set_euclidean_fitness_epsilon(lgs_icp* icp, double eps);       /* GBS:148 (relative MSE threshold) */
+/* The convergence criteria object lives in the ICP object, as in PCL: the previous-MSE it compares with survives from one
+ * align to the next.  This gives it the state of a newly constructed pcl::IterativeClosestPoint (the loop-closure batch
+ * calls it per pair so that a record does not depend on which pair its worker verified before). */
+int lgs_icp_reset_convergence_criteria(lgs_icp* icp);
 int lgs_icp_set_source(lgs_icp* icp, const void* pts, int64_t n, int32_t stride_bytes);
 int lgs_icp_set_target(lgs_icp* icp, const void* pts, int64_t n, int32_t stride_bytes);
 int lgs_icp_set_source_dev(lgs_icp* icp, const float* pts_dev, int64_t n);
@@ -355,6 +362,9 @@ int lgs_keyframes_size(lgs_keyframes* kf, int64_t* count, int64_t* total_points)
  * accumulate_distance_threshold of path behind `latest_id` and closer to it than search_for_candidate_threshold;
  * *nearest = the single candidate optimization_callback picks (GBS:263-280), -1 if none.  candidates may be NULL. */
 int lgs_keyframes_set_accum_distance(lgs_keyframes* kf, int32_t id, double accum_distance);
+/* key_frame.pose.position as the f64 geometry_msgs value (GBS:163-171 compares those); without it the loop detection falls
+ * back to the f32 translation of the pose matrix, which can flip a candidate sitting on the 15 m / 100 m thresholds */
+int lgs_keyframes_set_position(lgs_keyframes* kf, int32_t id, const double* xyz);
 int lgs_keyframes_detect_loop(lgs_keyframes* kf, int32_t latest_id, double accumulate_distance_threshold, double search_for_candidate_threshold,
                               int32_t* candidates, int32_t capacity, int32_t* n_candidates, int32_t* nearest);
 /* sub-map = concatenation, in the order of ids[], of pcl::transformPointCloud(key frame, pose); leaf > 0 applies

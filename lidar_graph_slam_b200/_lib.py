@@ -140,6 +140,7 @@ SYMBOLS = {
     "lgs_icp_set_transformation_epsilon": (_i32, [_vp, _f64]),
     "lgs_icp_set_transformation_rotation_epsilon": (_i32, [_vp, _f64]),
     "lgs_icp_set_euclidean_fitness_epsilon": (_i32, [_vp, _f64]),
+    "lgs_icp_reset_convergence_criteria": (_i32, [_vp]),
     "lgs_icp_set_source": (_i32, [_vp, _vp, _i64, _i32]),
     "lgs_icp_set_target": (_i32, [_vp, _vp, _i64, _i32]),
     "lgs_icp_set_source_dev": (_i32, [_vp, _vp, _i64]),
@@ -157,6 +158,7 @@ SYMBOLS = {
     "lgs_keyframes_size": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "lgs_keyframes_assemble": (_i32, [_vp, _vp, _i32, _f32, C.POINTER(_vp), C.POINTER(_i64)]),
     "lgs_keyframes_set_accum_distance": (_i32, [_vp, _i32, _f64]),
+    "lgs_keyframes_set_position": (_i32, [_vp, _i32, _vp]),
     "lgs_keyframes_detect_loop": (_i32, [_vp, _i32, _f64, _f64, _vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "lgs_batch_align_keyframes": (_i32, [_vp, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "lgs_batch_align": (_i32, [_i32, _vp, C.POINTER(BatchParams), _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),

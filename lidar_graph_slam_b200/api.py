@@ -280,6 +280,10 @@ class _Registration:
         if _is_torch(cloud):
             p, n = _dev_cloud(cloud, self.ctx)
             check(self._fn("set_%s_dev" % which)(self._h, p, n))
+            if not self.ctx.shares_torch_stream(cloud.device):
+                # the library copies the tensor on its own stream, which torch's caching allocator does not know: finish the
+                # copy before the caller can drop the tensor and have its memory recycled
+                self.ctx.synchronize()
         else:
             _, p, n, stride = _host_cloud(cloud)
             check(self._fn("set_%s" % which)(self._h, p, n, stride))
@@ -556,6 +560,11 @@ class KeyFrameArray:
         c = C.c_int64()
         check(self._L.lgs_keyframes_size(self._h, C.byref(c), None))
         return c.value
+
+    def set_position(self, kid, xyz):
+        """key_frame.pose.position in f64 (what detect_loop_with_accum_dist compares, GBS:163-171)."""
+        p = np.ascontiguousarray(xyz, np.float64)
+        check(self._L.lgs_keyframes_set_position(self._h, int(kid), p.ctypes.data_as(C.c_void_p)))
 
     def set_accum_distance(self, kid, accum_distance):
         check(self._L.lgs_keyframes_set_accum_distance(self._h, int(kid), float(accum_distance)))

@@ -138,6 +138,7 @@ int run_pair(lgs_ctx* ctx, lgs_gicp* gicp, lgs_ndt* ndt, lgs_icp* icp, lgs_gicp_
     else
       LGS_TRY(lgs_icp_set_source(icp, S->scans[i], S->n_scan[i], S->stride));
     clk.lap(3);
+    LGS_TRY(lgs_icp_reset_convergence_criteria(icp));  // every pair starts from a fresh criteria object (order independence)
     LGS_TRY(lgs_icp_align(icp, guess, &rec, nullptr));
     clk.lap(4);
     arm_record();

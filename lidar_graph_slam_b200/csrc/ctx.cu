@@ -62,8 +62,21 @@ int adopt_cloud_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, DevBuf* dst) 
 // ---- persistent evaluators (persist.cuh) ----------------------------------------------------------------------------
 static std::atomic<int> g_persist_owner[64];
 
+// The resident grids are sized for the B200's 148 SMs (kNumSMs) and need every CTA co-resident: on a device, MIG slice or MPS
+// share with fewer SMs the CTAs that do not fit would never start while the resident ones spin.  Checked once per device.
+static bool device_holds_resident_grids(int device) {
+  static int sms[64] = {};
+  if (sms[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) v = -1;
+    sms[device] = v > 0 ? v : -1;
+  }
+  return sms[device] >= kNumSMs;
+}
+
 bool persist_try_acquire(int device) {
   if (device < 0 || device >= 64) return false;
+  if (!device_holds_resident_grids(device)) return false;
   int expected = 0;
   return g_persist_owner[device].compare_exchange_strong(expected, 1, std::memory_order_acquire);
 }

@@ -180,6 +180,12 @@ struct lgs_icp {
   int convergence_state = 0;
   double last_mse = 0;
   int64_t last_correspondences = 0;
+  // pcl::registration::DefaultConvergenceCriteria lives in the ICP object: correspondences_prev_mse_ and the
+  // similar-transforms counter are set in its constructor only, so the first iteration of a second align on the same
+  // object is compared with the last MSE of the align before (the reference re-uses one registration_ for every loop
+  // closure, GBS:145-148).  lgs_icp_reset_convergence_criteria gives the state of a freshly constructed object.
+  double crit_prev_mse = std::numeric_limits<double>::max();
+  int crit_state = 0, crit_similar = 0;
   // persistent evaluator (inside lgs_icp_align only)
   bool allow_session = false, session_active = false, session_broken = false;
   int session_device = -1;
@@ -403,6 +409,13 @@ int lgs_icp_set_maximum_iterations(lgs_icp* g, int32_t n) { LGS_REQUIRE(g, "null
 int lgs_icp_set_transformation_epsilon(lgs_icp* g, double e) { LGS_REQUIRE(g, "null"); g->trans_eps = e; return LGS_OK; }
 int lgs_icp_set_transformation_rotation_epsilon(lgs_icp* g, double e) { LGS_REQUIRE(g, "null"); g->rot_eps = e; return LGS_OK; }
 int lgs_icp_set_euclidean_fitness_epsilon(lgs_icp* g, double e) { LGS_REQUIRE(g, "null"); g->fitness_eps = e; return LGS_OK; }
+int lgs_icp_reset_convergence_criteria(lgs_icp* g) {
+  LGS_REQUIRE(g, "null");
+  g->crit_prev_mse = std::numeric_limits<double>::max();
+  g->crit_state = 0;
+  g->crit_similar = 0;
+  return LGS_OK;
+}
 
 int lgs_icp_set_source(lgs_icp* g, const void* pts, int64_t n, int32_t stride) {
   LGS_REQUIRE(g, "null");
@@ -457,6 +470,9 @@ static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* re
   LGS_CUDA(cudaMemcpyAsync(g->cloud.p, g->source.p, static_cast<size_t>(g->n_source) * 16, cudaMemcpyDeviceToDevice, st));
   identity16f(T);
   Criteria crit;
+  crit.prev_mse = g->crit_prev_mse;
+  crit.state = g->crit_state;
+  crit.similar = g->crit_similar;
   crit.max_iterations = g->max_iterations;
   crit.rel_thr = g->fitness_eps;
   crit.trans_thr = g->trans_eps;
@@ -483,6 +499,9 @@ static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* re
   } while (crit.state == kNotConverged);
   end_session(g);
   g->convergence_state = crit.state;
+  g->crit_prev_mse = crit.prev_mse;
+  g->crit_state = crit.state;
+  g->crit_similar = crit.similar;
   memcpy(res->T, g->final_T, sizeof(g->final_T));
   res->iterations = nr_iterations;
   res->converged = converged ? 1 : 0;

@@ -67,6 +67,8 @@ struct lgs_keyframes {
     int64_t n = 0;
     float pose[16];
     double accum_distance = 0;  // key_frame.accum_distance (LSM:193): path length at this key frame
+    double position[3] = {0, 0, 0};  // key_frame.pose.position in f64 (geometry_msgs), what detect_loop compares (GBS:163-171)
+    bool have_position = false;
   };
   std::vector<Chunk*> chunks;
   std::vector<Frame> frames;
@@ -214,6 +216,7 @@ int lgs_keyframes_set_pose(lgs_keyframes* kf, int32_t id, const float* pose16) {
   LGS_REQUIRE(kf && pose16, "null argument");
   LGS_REQUIRE(id >= 0 && id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
   memcpy(kf->frames[id].pose, pose16, sizeof(float) * 16);
+  kf->frames[id].have_position = false;  // the f64 position, if any, belonged to the old pose
   return LGS_OK;
 }
 
@@ -247,6 +250,14 @@ int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids,
   return LGS_OK;
 }
 
+int lgs_keyframes_set_position(lgs_keyframes* kf, int32_t id, const double* xyz) {
+  LGS_REQUIRE(kf && xyz, "null argument");
+  LGS_REQUIRE(id >= 0 && id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
+  for (int a = 0; a < 3; a++) kf->frames[id].position[a] = xyz[a];
+  kf->frames[id].have_position = true;
+  return LGS_OK;
+}
+
 int lgs_keyframes_set_accum_distance(lgs_keyframes* kf, int32_t id, double accum_distance) {
   LGS_REQUIRE(kf, "null argument");
   LGS_REQUIRE(id >= 0 && id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
@@ -262,13 +273,14 @@ int lgs_keyframes_detect_loop(lgs_keyframes* kf, int32_t latest_id, double accum
   LGS_REQUIRE(kf && n_candidates, "null argument");
   LGS_REQUIRE(latest_id >= 0 && latest_id < static_cast<int32_t>(kf->frames.size()), "key frame id out of range");
   const auto& L = kf->frames[latest_id];
-  const double lp[3] = {L.pose[12], L.pose[13], L.pose[14]};
+  auto pos = [](const lgs_keyframes::Frame& f, int a) { return f.have_position ? f.position[a] : static_cast<double>(f.pose[12 + a]); };
+  const double lp[3] = {pos(L, 0), pos(L, 1), pos(L, 2)};
   int32_t cnt = 0, best = -1;
   double min_dist = std::numeric_limits<double>::max();
   for (int32_t id = 0; id < static_cast<int32_t>(kf->frames.size()); id++) {
     const auto& f = kf->frames[id];
     if ((L.accum_distance - f.accum_distance) < accumulate_distance_threshold) continue;
-    const double dx = lp[0] - f.pose[12], dy = lp[1] - f.pose[13], dz = lp[2] - f.pose[14];
+    const double dx = lp[0] - pos(f, 0), dy = lp[1] - pos(f, 1), dz = lp[2] - pos(f, 2);
     const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
     if (dist < search_for_candidate_threshold) {
       if (candidates && cnt < capacity) candidates[cnt] = id;

@@ -76,8 +76,63 @@ struct VoxelExport {  // f64 per-voxel data, ascending idx (parity hook + operan
   double* icov;  // 9
 };
 
-__global__ void __launch_bounds__(128) voxel_stats_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ keys,
-                                                         const unsigned* __restrict__ vals, const int* __restrict__ seg_start, int n_seg,
+// pass 1 (VGC:233-237): mean_ += p ; cov_ += p p^T in f64, members in ascending point index - the reference's serial
+// order, which is what makes the sums (and with them the validity flags) bit-identical to the oracle's.  One WARP per
+// voxel.  The lanes fetch 32 members at a time (index, then point: two dependent gathers, pipelined two chunks deep; a
+// single thread would pay their latency once per member, and the largest voxel of a map - hundreds of points - used to set
+// the kernel's duration).  Every lane widens ITS member and forms the nine addends x, y, z, xx, xy, xz, yy, yz, zz once
+// (exactly the products the serial loop forms) and parks them in shared memory; then lane a (0..8) adds addend a of member
+// 0, 1, 2, ... in order.  Per member that is one shared-memory read off the critical path and one DADD on it: ~8 cycles,
+// the latency of the addition chain that the order fixes (tools/microbench/chain.cu; selecting operands per member after
+// three shuffles costs 47, a per-lane `?:` that compiles to divergent branches 260).
+constexpr int kSumsPerVoxel = 9;
+constexpr int kSumsWarps = 8;
+__global__ void __launch_bounds__(kSumsWarps * 32) voxel_sums_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ vals,
+                                                                    const int* __restrict__ seg_start, int n_seg, int64_t n_pts, double* __restrict__ sums) {
+  __shared__ double addend[kSumsWarps][2][32][kSumsPerVoxel];  // [warp][buffer][member][addend], 36 KB
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= n_seg) return;
+  const int b = seg_start[v];
+  const int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_pts);
+  auto park = [&](int buf, const float4& p) {
+    const double x = static_cast<double>(p.x), y = static_cast<double>(p.y), z = static_cast<double>(p.z);
+    double* a = addend[warp][buf][lane];
+    a[0] = x;
+    a[1] = y;
+    a[2] = z;
+    a[3] = __dmul_rn(x, x);
+    a[4] = __dmul_rn(x, y);
+    a[5] = __dmul_rn(x, z);
+    a[6] = __dmul_rn(y, y);
+    a[7] = __dmul_rn(y, z);
+    a[8] = __dmul_rn(z, z);
+  };
+  double acc = 0.0;
+  const int col = lane < kSumsPerVoxel ? lane : 0;
+  float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b + lane < e) cur = __ldg(pts + __ldg(vals + b + lane));
+  int idx_next = b + 32 + lane < e ? static_cast<int>(__ldg(vals + b + 32 + lane)) : -1;
+  int buf = 0;
+  for (int c0 = b; c0 < e; c0 += 32, buf ^= 1) {
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx_next >= 0) nxt = __ldg(pts + idx_next);  // points of the next chunk and indices of the one after: in flight
+    idx_next = c0 + 64 + lane < e ? static_cast<int>(__ldg(vals + c0 + 64 + lane)) : -1;
+    park(buf, cur);
+    __syncwarp();
+    const int cnt = min(32, e - c0);
+    const double* mine = &addend[warp][buf][0][col];
+#pragma unroll 8
+    for (int t = 0; t < cnt; t++) acc = __dadd_rn(acc, mine[t * kSumsPerVoxel]);
+    cur = nxt;  // (the other buffer is parked next: a lane still reading this one is never overtaken by more than one chunk,
+  }             //  and the __syncwarp above separates its reads from the writes two chunks later)
+  if (lane < kSumsPerVoxel) sums[static_cast<size_t>(v) * kSumsPerVoxel + lane] = acc;
+}
+
+// pass 2 (VGC:282-367): one thread per voxel finishes mean / covariance / eigen regularisation / inverse and publishes the
+// lookup record and the cell-table entry.
+__global__ void __launch_bounds__(128) voxel_stats_kernel(const double* __restrict__ sums, const unsigned* __restrict__ keys,
+                                                         const int* __restrict__ seg_start, int n_seg,
                                                          int64_t n_pts, int min_pts, double eig_mult, VoxelExport ex, VoxelRec* __restrict__ recs,
                                                          int* __restrict__ dense_table, int* __restrict__ hkeys, int* __restrict__ hvals,
                                                          unsigned hmask, int* __restrict__ n_valid) {
@@ -86,15 +141,8 @@ __global__ void __launch_bounds__(128) voxel_stats_kernel(const float4* __restri
   const int b = seg_start[v];
   const int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_pts);
   const int key = static_cast<int>(keys[b]);
-  // pass 1 (VGC:233-237): mean_ += p ; cov_ += p p^T, f64, ascending point index
-  double s0 = 0, s1 = 0, s2 = 0, c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-  for (int j = b; j < e; j++) {
-    float4 p = pts[vals[j]];
-    double x = p.x, y = p.y, z = p.z;
-    s0 += x; s1 += y; s2 += z;
-    c00 += x * x; c01 += x * y; c02 += x * z;
-    c11 += y * y; c12 += y * z; c22 += z * z;
-  }
+  const double* sv = sums + static_cast<size_t>(v) * kSumsPerVoxel;
+  const double s0 = sv[0], s1 = sv[1], s2 = sv[2], c00 = sv[3], c01 = sv[4], c02 = sv[5], c11 = sv[6], c12 = sv[7], c22 = sv[8];
   int n = e - b;
   double cov[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
   double sum[3] = {s0, s1, s2};
@@ -302,7 +350,7 @@ struct lgs_ndt {
   int dense = 1;
   int64_t n_voxels = 0, n_valid = 0;
   int min_b[3] = {0, 0, 0}, max_b[3] = {0, 0, 0}, div_b[3] = {0, 0, 0};
-  DevBuf table, hkeys, recs, ex_idx, ex_n, ex_mean, ex_cov, ex_icov, small;
+  DevBuf table, hkeys, recs, ex_idx, ex_n, ex_mean, ex_cov, ex_icov, small, vsums;
   unsigned hmask = 0;
   // reduction scratch
   DevBuf partials, result;
@@ -488,7 +536,10 @@ int build_grid(lgs_ndt* n) {
     LGS_CUDA(cudaMemsetAsync(n->hkeys.p, 0xFF, cap * 4, st));
   }
   VoxelExport ex{n->ex_idx.as<int>(), n->ex_n.as<int>(), n->ex_mean.as<double>(), n->ex_cov.as<double>(), n->ex_icov.as<double>()};
-  voxel_stats_kernel<<<grid_for(V, 128), 128, 0, st>>>(n->target.as<float4>(), sv.keys, sv.vals, sv.seg_start, V, sv.n_kept, 6, 0.01, ex,
+  LGS_TRY(n->vsums.reserve(static_cast<size_t>(V) * kSumsPerVoxel * sizeof(double)));
+  voxel_sums_kernel<<<grid_for(static_cast<int64_t>(V) * 32, 256), 256, 0, st>>>(n->target.as<float4>(), sv.vals, sv.seg_start, V, sv.n_kept, n->vsums.as<double>());
+  ctx->launches++;
+  voxel_stats_kernel<<<grid_for(V, 128), 128, 0, st>>>(n->vsums.as<double>(), sv.keys, sv.seg_start, V, sv.n_kept, 6, 0.01, ex,
                                                       n->recs.as<VoxelRec>(), n->dense ? n->table.as<int>() : nullptr, n->hkeys.as<int>(),
                                                       n->table.as<int>(), n->hmask, n->small.as<int>());
   ctx->launches++;
@@ -773,7 +824,7 @@ void lgs_ndt_destroy(lgs_ndt* n) {
   cudaStreamSynchronize(n->ctx->stream);
   n->align_dev.release();
   for (DevBuf* b : {&n->target, &n->source, &n->out_cloud, &n->table, &n->hkeys, &n->recs, &n->ex_idx, &n->ex_n, &n->ex_mean, &n->ex_cov, &n->ex_icov,
-                    &n->small, &n->partials, &n->result})
+                    &n->small, &n->partials, &n->result, &n->vsums})
     b->release();
   n->nn.release();
   delete n;

@@ -171,6 +171,9 @@ void PclICP::align(const float* guess, std::vector<P4>* out) {
     cloud = source;
   identity_f(transformation);
   Criteria crit;
+  crit.prev_mse = crit_prev_mse;
+  crit.state = crit_state;
+  crit.iterations_similar_transforms = crit_similar;
   crit.max_iterations = max_iterations;
   crit.mse_threshold_relative = euclidean_fitness_epsilon;
   crit.translation_threshold = transformation_epsilon;
@@ -191,6 +194,9 @@ void PclICP::align(const float* guess, std::vector<P4>* out) {
     converged = crit.has_converged(nr_iterations, transformation, last_mse);
   } while (crit.state == ICP_NOT_CONVERGED);
   convergence_state = crit.state;
+  crit_prev_mse = crit.prev_mse;
+  crit_state = crit.state;
+  crit_similar = crit.iterations_similar_transforms;
   if (out) {
     out->resize(source.size());
     for (size_t i = 0; i < source.size(); i++) (*out)[i] = transform_point(final_transformation, source[i]);

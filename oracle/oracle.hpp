@@ -304,6 +304,10 @@ struct PclICP {
   int convergence_state = ICP_NOT_CONVERGED;
   double last_mse = 0;
   long last_correspondences = 0;
+  // DefaultConvergenceCriteria is a member of pcl::IterativeClosestPoint: its previous MSE, state and similar-transforms
+  // counter survive from one align to the next (they are initialised in its constructor only)
+  double crit_prev_mse = 1.7976931348623157e308;
+  int crit_state = ICP_NOT_CONVERGED, crit_similar = 0;
 
   PclICP();
   void setInputSource(const P4* p, size_t n);

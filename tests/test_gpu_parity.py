@@ -836,6 +836,76 @@ def test_gicp_cfg2_synthetic_odometry(api, oracle):
             x.swapSourceAndTarget()
 
 
+def test_gicp_clear_source_and_target(api, oracle, velodyne_pair):
+    """clearSource / clearTarget (FG:60-69): the cloud, its tree and its covariances are gone - align refuses to run - and setting
+    the clouds again gives the registration of a fresh object, bit for bit."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    g = api.FastGICP()
+    g.setInputTarget(t2)
+    g.setInputSource(s2)
+    g.align()
+    T0, it0 = g.getFinalTransformation().copy(), g.result.iterations
+    g.clearSource()
+    with pytest.raises(RuntimeError):
+        g.align()
+    g.setInputSource(s2)
+    g.clearTarget()
+    with pytest.raises(RuntimeError):
+        g.align()
+    g.setInputTarget(t2)
+    g.align()
+    assert np.array_equal(g.getFinalTransformation(), T0) and g.result.iterations == it0
+    g.clearSource()
+    g.clearTarget()
+    g.setInputSource(t2)   # the roles swapped after a full clear
+    g.setInputTarget(s2)
+    g.align()
+    o = oracle.FastGICP()
+    o.setInputSource(t2)
+    o.setInputTarget(s2)
+    o.align()
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    assert t_err < T_TOL_M and r_err < R_TOL_RAD and g.result.iterations == o.nr_iterations
+
+
+def test_ndt_align_fills_the_output_cloud(api, oracle, velodyne_pair):
+    """align(output, guess) (LSM:164-165): the output cloud is the source transformed by the final transformation with
+    pcl::transformPointCloud's arithmetic - bit for bit, intensities carried over - for the device-resident align and the
+    host-stepped one."""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    for stepped in (False, True):
+        g, _ = _ndt_pair(api, oracle, td, sd)
+        if stepped:
+            g.profile(1)
+        out = g.align(_pose(0.2, -0.1, 0.02, 0.01), want_output=True)
+        assert out.shape == sd.shape
+        assert np.array_equal(out, oracle.transform_point_cloud(sd, g.getFinalTransformation()))
+        if stepped:
+            g.profile(0)
+
+
+def test_keyframe_loop_detection_uses_f64_positions(api):
+    """detect_loop_with_accum_dist compares the f64 positions of geometry_msgs poses (GBS:163-171): a key frame 15 m - 1e-9 away
+    is a candidate, which the f32 pose matrix alone (15.000000 exactly) would reject (dist < threshold is strict)."""
+    kf = api.KeyFrameArray()
+    pts = np.zeros((10, 4), np.float32)
+    pos = [(0.0, 0.0), (60.0, 0.0), (120.0, 0.0), (15.0 - 1e-9, 0.0)]
+    acc = [0.0, 60.0, 120.0, 225.0]
+    for (x, y), a in zip(pos, acc):
+        P = np.eye(4, dtype=np.float32)
+        P[:3, 3] = [x, y, 0.0]
+        kid = kf.push(pts, P)
+        kf.set_accum_distance(kid, a)
+    cand, nearest = kf.detect_loop(3, accumulate_distance_threshold=100.0, search_for_candidate_threshold=15.0)
+    assert list(cand) == [] and nearest == -1          # f32: |15.0 - 0.0| < 15 is false
+    for kid, (x, y) in enumerate(pos):
+        kf.set_position(kid, [x, y, 0.0])
+    cand, nearest = kf.detect_loop(3, accumulate_distance_threshold=100.0, search_for_candidate_threshold=15.0)
+    assert list(cand) == [0] and nearest == 0
+
+
 def test_gicp_cfg2_long_drive_1000_sweeps(api, oracle):
     """BASELINE configs[2] at its full size (kitti.cpp:80-82, 115-138): scan-to-scan FastGICP odometry over 1000 consecutive
     120 000-ray sweeps of a 1 km drive, VoxelGrid 0.25 m + range crop, max_corr 1.0, covariance reuse through
