@@ -435,11 +435,24 @@ class KeyFrameArray {
 #include <pcl/registration/registration.h>
 namespace lgs {
 
+// pcl::Registration::initCompute() (called by the non-virtual align shell) rebuilds PCL's FLANN kd-tree over the target after
+// every setInputTarget unless the search method was installed with force_no_recompute: the adapters install an empty tree
+// that way, so no host-side kd-tree over the 1 M-point map is ever built.  getFitnessScore is not virtual either: call it
+// through the adapter type.
+template <typename Reg>
+inline void lgs_skip_pcl_target_tree(Reg* reg) {
+  typename Reg::KdTreePtr tree(new typename Reg::KdTree);
+  reg->setSearchMethodTarget(tree, /*force_no_recompute=*/true);
+}
+
 class PclNdtAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> {
  public:
   using Base = pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>;
   NormalDistributionsTransform impl;
-  PclNdtAdapter() { reg_name_ = "lgs::NormalDistributionsTransform"; }
+  PclNdtAdapter() {
+    reg_name_ = "lgs::NormalDistributionsTransform";
+    lgs_skip_pcl_target_tree(this);
+  }
   void setInputTarget(const Base::PointCloudTargetConstPtr& cloud) override {
     Base::setInputTarget(cloud);
     lgs_ndt_set_target(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
@@ -476,7 +489,10 @@ class PclGicpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> 
  public:
   using Base = pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>;
   FastGICP impl;
-  PclGicpAdapter() { reg_name_ = "lgs::FastGICP"; }
+  PclGicpAdapter() {
+    reg_name_ = "lgs::FastGICP";
+    lgs_skip_pcl_target_tree(this);
+  }
   void setInputTarget(const Base::PointCloudTargetConstPtr& cloud) override {
     Base::setInputTarget(cloud);
     lgs_gicp_set_target(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
@@ -519,6 +535,7 @@ class PclGicpOmpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZ
   GeneralizedIterativeClosestPoint impl;
   PclGicpOmpAdapter() {
     reg_name_ = "lgs::GeneralizedIterativeClosestPoint";
+    lgs_skip_pcl_target_tree(this);
     max_iterations_ = 200;            // gicp_omp.h:121-125
     transformation_epsilon_ = 5e-4;
     corr_dist_threshold_ = 5.;
@@ -560,7 +577,10 @@ class PclIcpAdapter : public pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> {
  public:
   using Base = pcl::Registration<pcl::PointXYZI, pcl::PointXYZI>;
   IterativeClosestPoint impl;
-  PclIcpAdapter() { reg_name_ = "lgs::IterativeClosestPoint"; }
+  PclIcpAdapter() {
+    reg_name_ = "lgs::IterativeClosestPoint";
+    lgs_skip_pcl_target_tree(this);
+  }
   void setInputTarget(const Base::PointCloudTargetConstPtr& cloud) override {
     Base::setInputTarget(cloud);
     lgs_icp_set_target(impl.handle(), cloud->points.data(), static_cast<int64_t>(cloud->size()), sizeof(pcl::PointXYZI));
