@@ -20,11 +20,14 @@ namespace lgs {
 // ---------------------------------------------------------------------------------------------
 // covariances
 
+// list == nullptr: point i of n, neighbour row i.  Otherwise: point list[j] for j < *count, neighbour row j (lazy covariances).
 __global__ void __launch_bounds__(128) gicp_covariance_kernel(NNView v, const float4* __restrict__ pts, int n, int k, int regularization,
-                                                             const int* __restrict__ knn_idx, double* __restrict__ covs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // original point index
-  if (i >= n) return;
-  const int* nb = knn_idx + static_cast<size_t>(i) * k;
+                                                             const int* __restrict__ knn_idx, double* __restrict__ covs,
+                                                             const int* __restrict__ list, const int* __restrict__ count) {
+  const int j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j0 >= (list ? *count : n)) return;
+  const int i = list ? list[j0] : j0;  // original point index
+  const int* nb = knn_idx + static_cast<size_t>(j0) * k;
   // neighbors.rowwise().mean(): sequential sum over the k columns, divided by k (missing columns are zero)
   double s0 = 0, s1 = 0, s2 = 0;
   for (int j = 0; j < k; j++) {
@@ -101,14 +104,59 @@ int GicpCloud::ensure_covariances(lgs_ctx* ctx, int k, int regularization) {
     int* knn_idx = ctx->tmp[1].as<int>();
     LGS_TRY(nn_self_knn(ctx, nn, k, knn_idx, nullptr));
     gicp_covariance_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(nn.view(), pts.as<float4>(), static_cast<int>(n), k, regularization, knn_idx,
-                                                                     covs.as<double>());
+                                                                     covs.as<double>(), nullptr, nullptr);
     ctx->launches++;
     LGS_CUDA(cudaGetLastError());
   }
   covs_ready = true;
   covs_user = false;
+  covs_lazy = false;
   covs_k = k;
   covs_reg = regularization;
+  return LGS_OK;
+}
+
+// marks the target points that correspondences refer to and that have no covariance yet, and lists them
+__global__ void __launch_bounds__(256) gicp_mark_needed_kernel(const int* __restrict__ corr, int n_corr, int* __restrict__ done, int* __restrict__ list,
+                                                              int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_corr) return;
+  const int c = corr[i];
+  if (c < 0) return;
+  if (atomicExch(done + c, 1) == 0) list[atomicAdd(count, 1)] = c;
+}
+
+int GicpCloud::begin_lazy_covariances(lgs_ctx* ctx, int k, int regularization) {
+  LGS_REQUIRE(k >= 1 && k <= kMaxK, "k_correspondences must be in [1, 32]");
+  LGS_TRY(ensure_index(ctx));
+  const size_t np = static_cast<size_t>(n > 0 ? n : 1);
+  LGS_TRY(covs.reserve(np * 72));
+  LGS_TRY(cov_done.reserve(np * 4));
+  LGS_TRY(work_list.reserve(np * 4));
+  LGS_TRY(work_count.reserve(64));
+  LGS_CUDA(cudaMemsetAsync(cov_done.p, 0, np * 4, ctx->stream));
+  covs_lazy = true;
+  covs_ready = false;
+  covs_user = false;
+  covs_k = k;
+  covs_reg = regularization;
+  return LGS_OK;
+}
+
+int GicpCloud::cover_correspondences(lgs_ctx* ctx, const int* corr_dev, int64_t n_corr) {
+  if (!covs_lazy || n == 0 || n_corr == 0) return LGS_OK;
+  cudaStream_t st = ctx->stream;
+  const int64_t cap = std::min<int64_t>(n_corr, n);  // at most one new point per correspondence
+  LGS_TRY(ctx->tmp[1].reserve(static_cast<size_t>(cap) * covs_k * 4));
+  int* count = work_count.as<int>();
+  LGS_CUDA(cudaMemsetAsync(count, 0, 4, st));
+  gicp_mark_needed_kernel<<<grid_for(n_corr, 256), 256, 0, st>>>(corr_dev, static_cast<int>(n_corr), cov_done.as<int>(), work_list.as<int>(), count);
+  ctx->launches++;
+  LGS_TRY(nn_knn_list(ctx, nn, pts.as<float4>(), work_list.as<int>(), count, cap, covs_k, ctx->tmp[1].as<int>()));
+  gicp_covariance_kernel<<<grid_for(cap, 128), 128, 0, st>>>(nn.view(), pts.as<float4>(), static_cast<int>(n), covs_k, covs_reg, ctx->tmp[1].as<int>(),
+                                                           covs.as<double>(), work_list.as<int>(), count);
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
   return LGS_OK;
 }
 
@@ -356,7 +404,14 @@ int ensure_ready(lgs_gicp* g) {
     return LGS_ERR_STATE;
   }
   LGS_TRY(g->source->ensure_covariances(g->ctx, g->k, g->regularization));  // FG:104-109
-  LGS_TRY(g->target->ensure_covariances(g->ctx, g->k, g->regularization));
+  static const bool lazy_off = [] { const char* e = getenv("LGS_GICP_LAZY_TARGET"); return e && e[0] == '0'; }();
+  GicpCloud& T = *g->target;
+  const bool have = T.covs_ready && (T.covs_user || (T.covs_k == g->k && T.covs_reg == g->regularization));
+  if (have || lazy_off || g->target == g->source) {
+    LGS_TRY(T.ensure_covariances(g->ctx, g->k, g->regularization));
+  } else if (!(T.covs_lazy && T.covs_k == g->k && T.covs_reg == g->regularization)) {
+    LGS_TRY(T.begin_lazy_covariances(g->ctx, g->k, g->regularization));  // computed on first use (GicpCloud::cover_correspondences)
+  }
   LGS_TRY(g->target->ensure_index(g->ctx));
   const size_t n = static_cast<size_t>(std::max<int64_t>(g->source->n, 1));
   LGS_TRY(g->corr.reserve(n * 4));
@@ -400,10 +455,12 @@ int linearize(lgs_gicp* g, const double* T, double* cost, double* H, double* b) 
   gicp_correspondence_kernel<<<cgrid, kCorrBlock, 0, st>>>(g->target->nn.view(), g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P, g->corr.as<int>(),
                                                           g->nn_prev.as<int>(), g->have_seed ? 1 : 0);
   g->have_seed = true;
+  ctx->launches++;
+  LGS_TRY(g->target->cover_correspondences(ctx, g->corr.as<int>(), n));
   gicp_linearize_kernel<<<lin_grid(n), kLinBlock, 0, st>>>(g->source->pts.as<float4>(), g->target->pts.as<float4>(), n, P,
                                                           g->source->covs.as<double>(), g->target->covs.as<double>(), g->corr.as<int>(),
                                                           g->mahal.as<double>(), (H && b) ? 1 : 0, g->partials.as<double>(), result, counter, mb);
-  ctx->launches += 2;
+  ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   double h[kMailboxRecords];
   LGS_TRY(mailbox_wait(ctx, mb, 43, h));
@@ -502,6 +559,7 @@ int set_cloud(lgs_gicp* g, std::shared_ptr<GicpCloud>* slot, const void* pts, co
     c->nn_ready = false;
     c->covs_ready = false;
     c->covs_user = false;
+    c->covs_lazy = false;
   } else {
     c = std::make_shared<GicpCloud>();
   }

@@ -18,12 +18,24 @@ struct GicpCloud {
   bool covs_ready = false;
   int covs_k = 0, covs_reg = -1;
   bool covs_user = false;  // supplied through set*Covariances (FG:93-101): used as they are
+  // Lazy covariances (a TARGET whose covariances nobody has asked for yet): fast_gicp computes the k-NN covariance of every
+  // target point up front (FG:104-109, 241-298), but an align only ever reads those of the points some source point
+  // corresponds to - a third of a 65 000-point sub-map for a 27 000-point scan.  A covariance depends on the cloud alone, so
+  // computing it on first use gives the same bits; the k-NN search is the most expensive kernel of the loop-closure batch.
+  bool covs_lazy = false;
+  DevBuf cov_done, work_list, work_count;  // per point: covariance present; points to compute now; their number
   int ensure_index(lgs_ctx* ctx);
   int ensure_covariances(lgs_ctx* ctx, int k, int regularization);
+  int begin_lazy_covariances(lgs_ctx* ctx, int k, int regularization);
+  // computes the covariances of the not-yet-covered points among corr[0 .. n_corr) (device array, -1 = none)
+  int cover_correspondences(lgs_ctx* ctx, const int* corr_dev, int64_t n_corr);
   ~GicpCloud() {
     pts.release();
     covs.release();
     nn.release();
+    cov_done.release();
+    work_list.release();
+    work_count.release();
   }
 };
 

@@ -309,12 +309,36 @@ __global__ void __launch_bounds__(kKnnBlock) nn_knn_kernel(NNView v, const float
   }
 }
 
+// the same search for a device-side list of indexed points (lazy covariances, gicp.cu)
+__global__ void __launch_bounds__(kKnnBlock) nn_knn_list_kernel(NNView v, const float4* __restrict__ pts, const int* __restrict__ list,
+                                                               const int* __restrict__ count, int k, int* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = *count;
+  for (int t = blockIdx.x * kKnnWarps + warp; t < m; t += gridDim.x * kKnnWarps) {
+    const float4 qp = __ldg(pts + list[t]);
+    NNKBest B;
+    nn_searchk_warp(v, qp.x, qp.y, qp.z, lane, k, B);
+    if (lane < k) out_idx[static_cast<size_t>(t) * k + lane] = B.bi != 0x7fffffff ? B.bi : -1;
+  }
+}
+
 static int knn_grid(int64_t m) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((m + kKnnWarps - 1) / kKnnWarps, kNumSMs * 64))); }
 
 int nn_self_knn(lgs_ctx* ctx, const NNIndex& index, int k, int* out_idx_dev, float* out_d2_dev) {
   LGS_REQUIRE(k >= 1 && k <= kMaxK, "k must be in [1, 32]");
   if (index.n == 0) return LGS_OK;
   nn_knn_kernel<true><<<knn_grid(index.n), kKnnBlock, 0, ctx->stream>>>(index.view(), nullptr, static_cast<int>(index.n), k, out_idx_dev, out_d2_dev);
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  return LGS_OK;
+}
+
+int nn_knn_list(lgs_ctx* ctx, const NNIndex& index, const float4* pts, const int* list_dev, const int* count_dev, int64_t capacity, int k,
+                int* out_idx_dev) {
+  LGS_REQUIRE(k >= 1 && k <= kMaxK, "k must be in [1, 32]");
+  if (capacity == 0 || index.n == 0) return LGS_OK;
+  // a quarter of the capacity's grid: the list is usually much shorter than its bound and the kernel strides
+  nn_knn_list_kernel<<<std::max(1, knn_grid(capacity) / 4), kKnnBlock, 0, ctx->stream>>>(index.view(), pts, list_dev, count_dev, k, out_idx_dev);
   ctx->launches++;
   LGS_CUDA(cudaGetLastError());
   return LGS_OK;

@@ -72,6 +72,11 @@ int nn_fitness(lgs_ctx* ctx, const NNIndex& index, const float4* src, int64_t n_
 // n x k, rows addressed by ORIGINAL point index, ascending (d2, idx).
 int nn_self_knn(lgs_ctx* ctx, const NNIndex& index, int k, int* out_idx_dev, float* out_d2_dev);
 
+// k-NN of the indexed points list[0 .. *count_dev) (original point indices; the count lives in device memory, `capacity`
+// bounds it): row j of out_idx_dev belongs to point list[j].  No host round trip: the launch covers the capacity.
+int nn_knn_list(lgs_ctx* ctx, const NNIndex& index, const float4* pts, const int* list_dev, const int* count_dev, int64_t capacity, int k,
+                int* out_idx_dev);
+
 // k-NN of arbitrary queries (device float4), rows addressed by query index
 int nn_knn(lgs_ctx* ctx, const NNIndex& index, const float4* queries, int64_t m, int k, int* out_idx_dev, float* out_d2_dev);
 
