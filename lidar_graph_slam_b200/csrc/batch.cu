@@ -304,6 +304,7 @@ static int run_batch(BatchShared& S);
 extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans,
                                const int64_t* n_scan, const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes,
                                const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev) {
+  LGS_NVTX("lgs_batch_align");
   LGS_REQUIRE(params && records, "null argument");
   LGS_REQUIRE(n_pairs >= 0, "negative pair count");
   LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
@@ -331,6 +332,7 @@ extern "C" int lgs_batch_align(int device, void* cuda_stream, const lgs_batch_pa
 extern "C" int lgs_batch_align_keyframes(lgs_keyframes* kf, void* cuda_stream, const lgs_batch_params* params, int64_t n_pairs,
                                          const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
                                          const float* guesses16, int32_t pair_id0, lgs_align_result* records, void* records_dev) {
+  LGS_NVTX("lgs_batch_align_keyframes");
   LGS_REQUIRE(kf && params && records, "null argument");
   LGS_REQUIRE(n_pairs >= 0 && search_key_frame_num >= 0, "negative count");
   LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
@@ -436,6 +438,7 @@ int run_dist(lgs_comm* comm, int device, const int64_t* sizes, int64_t n_pairs, 
 extern "C" int lgs_batch_align_keyframes_dist(lgs_keyframes* kf, lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs,
                                               const int32_t* scan_ids, const int32_t* center_ids, int32_t search_key_frame_num,
                                               const float* guesses16, lgs_align_result* records_all, lgs_batch_dist_info* info) {
+  LGS_NVTX("lgs_batch_align_keyframes_dist");
   LGS_REQUIRE(kf && comm && params && (records_all || n_pairs == 0), "null argument");
   LGS_REQUIRE(n_pairs >= 0 && n_pairs < (int64_t(1) << 31) && search_key_frame_num >= 0, "count out of range");
   LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");
@@ -477,6 +480,7 @@ extern "C" int lgs_batch_align_keyframes_dist(lgs_keyframes* kf, lgs_comm* comm,
 extern "C" int lgs_batch_align_dist(lgs_comm* comm, const lgs_batch_params* params, int64_t n_pairs, const void* const* scans, const int64_t* n_scan,
                                     const void* const* submaps, const int64_t* n_submap, int32_t stride_bytes, const float* guesses16,
                                     lgs_align_result* records_all, lgs_batch_dist_info* info) {
+  LGS_NVTX("lgs_batch_align_dist");
   LGS_REQUIRE(comm && params && (records_all || n_pairs == 0), "null argument");
   LGS_REQUIRE(n_pairs >= 0 && n_pairs < (int64_t(1) << 31), "count out of range");
   LGS_REQUIRE(params->method >= LGS_METHOD_NDT && params->method <= LGS_METHOD_GICP_OMP, "unknown method");

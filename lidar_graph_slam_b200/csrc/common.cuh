@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/lgs_c.h"
 
 namespace lgs {
@@ -38,6 +40,14 @@ void set_error(const char* fmt, ...);
       return LGS_ERR_INVALID;                  \
     }                                          \
   } while (0)
+
+// NVTX range over an API call (the reference has no tracing; Nsight Systems / Compute timelines of a node
+// that links this library show one range per registration call).  nvtx3 is header-only and a no-op without a tool attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define LGS_NVTX(name) lgs::NvtxRange lgs_nvtx_range_(name)
 
 constexpr int kNumSMs = 148;  // B200
 

@@ -407,7 +407,10 @@ int ensure_ready(lgs_gicp* g) {
   static const bool lazy_off = [] { const char* e = getenv("LGS_GICP_LAZY_TARGET"); return e && e[0] == '0'; }();
   GicpCloud& T = *g->target;
   const bool have = T.covs_ready && (T.covs_user || (T.covs_k == g->k && T.covs_reg == g->regularization));
-  if (have || lazy_off || g->target == g->source) {
+  // worth it when the target is clearly larger than the source (scan against sub-map: a third of the target is ever matched);
+  // between clouds of similar size nearly every target point is matched within a few iterations and the up-front pass is cheaper
+  const bool small_target = 2 * T.n <= 3 * g->source->n;
+  if (have || lazy_off || small_target || g->target == g->source) {
     LGS_TRY(T.ensure_covariances(g->ctx, g->k, g->regularization));
   } else if (!(T.covs_lazy && T.covs_k == g->k && T.covs_reg == g->regularization)) {
     LGS_TRY(T.begin_lazy_covariances(g->ctx, g->k, g->regularization));  // computed on first use (GicpCloud::cover_correspondences)
@@ -680,6 +683,7 @@ int lgs_gicp_clear_source(lgs_gicp* g) { LGS_REQUIRE(g, "null"); g->source.reset
 int lgs_gicp_clear_target(lgs_gicp* g) { LGS_REQUIRE(g, "null"); g->target.reset(); return LGS_OK; }
 
 int lgs_gicp_align(lgs_gicp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
+  LGS_NVTX("lgs_gicp_align");
   LGS_REQUIRE(g && res, "null argument");
   LGS_TRY(gicp_align_impl(g, guess16, res));
   if (out_cloud && g->source->n) {  // LSQ:77-78
@@ -699,6 +703,7 @@ int lgs_gicp_align(lgs_gicp* g, const float* guess16, lgs_align_result* res, flo
 }
 
 int lgs_gicp_fitness(lgs_gicp* g, double max_range, double* fitness) {
+  LGS_NVTX("lgs_gicp_fitness");
   LGS_REQUIRE(g && fitness, "null argument");
   return gicp_fitness_impl(g, max_range, fitness);
 }

@@ -954,6 +954,7 @@ int lgs_gicp_omp_set_target_dev(lgs_gicp_omp* g, const float* pts_dev, int64_t n
 static int gicp_omp_align_body(lgs_gicp_omp* g, const float* guess16, lgs_align_result* res, float* out_cloud);
 
 int lgs_gicp_omp_align(lgs_gicp_omp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
+  LGS_NVTX("lgs_gicp_omp_align");
   LGS_REQUIRE(g && res, "null argument");
   g->allow_session = true;
   const int rc = gicp_omp_align_body(g, guess16, res, out_cloud);

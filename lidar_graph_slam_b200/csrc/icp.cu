@@ -440,6 +440,7 @@ int lgs_icp_set_target_dev(lgs_icp* g, const float* pts_dev, int64_t n) {
 static int icp_align_body(lgs_icp* g, const float* guess16, lgs_align_result* res, float* out_cloud);
 
 int lgs_icp_align(lgs_icp* g, const float* guess16, lgs_align_result* res, float* out_cloud) {
+  LGS_NVTX("lgs_icp_align");
   LGS_REQUIRE(g && res, "null argument");
   g->allow_session = true;
   int rc = icp_align_body(g, guess16, res, out_cloud);

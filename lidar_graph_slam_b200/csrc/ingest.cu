@@ -102,6 +102,7 @@ using namespace lgs;
 extern "C" {
 
 int lgs_cloud_from_pointcloud2(lgs_ctx* ctx, const void* data, const lgs_pc2_layout* L, float* out_dev, int64_t* n_points) {
+  LGS_NVTX("lgs_cloud_from_pointcloud2");
   LGS_REQUIRE(ctx && L && n_points, "null argument");
   LGS_REQUIRE(L->point_step >= 12 && L->point_step <= 256, "point_step must be in [12, 256]");
   LGS_REQUIRE(L->is_bigendian == 0, "big-endian PointCloud2 payloads are not supported");

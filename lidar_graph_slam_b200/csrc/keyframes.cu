@@ -232,6 +232,7 @@ int lgs_keyframes_size(lgs_keyframes* kf, int64_t* count, int64_t* total_points)
 }
 
 int lgs_keyframes_assemble(lgs_keyframes* kf, const int32_t* ids, int32_t n_ids, float leaf, float** out_dev, int64_t* n_out) {
+  LGS_NVTX("lgs_keyframes_assemble");
   LGS_REQUIRE(kf && out_dev && n_out && (ids || n_ids == 0), "null argument");
   lgs_ctx* ctx = kf->ctx;
   LGS_TRY(use_device(ctx));

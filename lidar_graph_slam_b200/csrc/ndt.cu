@@ -860,6 +860,7 @@ static int after_target(lgs_ndt* n) {
 }
 
 int lgs_ndt_set_target(lgs_ndt* n, const void* pts, int64_t cnt, int32_t stride) {
+  LGS_NVTX("lgs_ndt_set_target");
   LGS_REQUIRE(n, "null");
   LGS_TRY(use_device(n->ctx));
   LGS_TRY(upload_cloud(n->ctx, pts, cnt, stride, &n->target));
@@ -867,6 +868,7 @@ int lgs_ndt_set_target(lgs_ndt* n, const void* pts, int64_t cnt, int32_t stride)
   return after_target(n);
 }
 int lgs_ndt_set_target_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
+  LGS_NVTX("lgs_ndt_set_target_dev");
   LGS_REQUIRE(n, "null");
   LGS_TRY(use_device(n->ctx));
   LGS_TRY(adopt_cloud_dev(n->ctx, pts_dev, cnt, &n->target));
@@ -892,6 +894,7 @@ int lgs_ndt_set_source_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
 
 // pcl::Registration::align shell + computeTransformation (NDT:80-171)
 int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float* out_cloud) {
+  LGS_NVTX("lgs_ndt_align");
   LGS_REQUIRE(n && res, "null argument");
   memset(res, 0, sizeof(*res));
   if (!n->have_target || !n->have_source) {
@@ -942,6 +945,7 @@ int lgs_ndt_align(lgs_ndt* n, const float* guess16, lgs_align_result* res, float
 }
 
 int lgs_ndt_fitness(lgs_ndt* n, double max_range, double* fitness) {
+  LGS_NVTX("lgs_ndt_fitness");
   LGS_REQUIRE(n && fitness, "null argument");
   if (!n->have_target || !n->have_source) {
     set_error("lgs_ndt_fitness: target and source must be set");

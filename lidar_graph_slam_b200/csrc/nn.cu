@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(kKnnBlock) nn_knn_kernel(NNView v, const float
     NNKBest B;
     nn_searchk_warp(v, qp.x, qp.y, qp.z, lane, k, B);
     if (lane < k) {
-      const bool have = B.bi != 0x7fffffff;
-      out_idx[static_cast<size_t>(row) * k + lane] = have ? B.bi : -1;
-      if (out_d2) out_d2[static_cast<size_t>(row) * k + lane] = have ? B.bd : 0.f;
+      const bool have = B.bi() != 0x7fffffff;
+      out_idx[static_cast<size_t>(row) * k + lane] = have ? B.bi() : -1;
+      if (out_d2) out_d2[static_cast<size_t>(row) * k + lane] = have ? B.bd() : 0.f;
     }
   }
 }
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kKnnBlock) nn_knn_list_kernel(NNView v, const 
     const float4 qp = __ldg(pts + list[t]);
     NNKBest B;
     nn_searchk_warp(v, qp.x, qp.y, qp.z, lane, k, B);
-    if (lane < k) out_idx[static_cast<size_t>(t) * k + lane] = B.bi != 0x7fffffff ? B.bi : -1;
+    if (lane < k) out_idx[static_cast<size_t>(t) * k + lane] = B.bi() != 0x7fffffff ? B.bi() : -1;
   }
 }
 

@@ -174,17 +174,28 @@ __device__ __forceinline__ void nn_search1_warp_seeded(const NNView& v, float qx
 }
 
 // ---- k-NN -------------------------------------------------------------------------------------------------------
-// The warp holds a list of 32 candidates sorted ascending by (d2, idx), entry j in lane j; worst / worst_i
-// (warp-uniform) mirror entry k - 1.  Empty entries are (+inf, INT_MAX).
-struct NNKBest {
-  float bd;
-  int bi;
-  float worst;
-  int worst_i;
-  bool fresh;  // nothing inserted yet (warp-uniform)
-};
+// The warp holds a list of 32 candidates sorted ascending by (d2, idx), entry j in lane j.  A candidate is ONE 64-bit key:
+// the bit pattern of its squared distance (non-negative, so it orders like an unsigned integer) above its original index,
+// which makes the lexicographic (d2, idx) comparison a single unsigned 64-bit compare - the compare-exchange network of
+// the merge path is ~45 % of this kernel's instructions (ncu), and the two-float-one-int comparison was most of that.
+// worst (warp-uniform) mirrors the distance of entry k - 1.  Empty entries are (+inf, INT_MAX).
+typedef unsigned long long nnkey_t;
+constexpr nnkey_t kNNEmpty = (static_cast<nnkey_t>(0x7f800000u) << 32) | 0x7fffffffu;
+__device__ __forceinline__ nnkey_t nn_make_key(float d2, int idx) {
+  return (static_cast<nnkey_t>(__float_as_uint(d2)) << 32) | static_cast<unsigned>(idx);
+}
+__device__ __forceinline__ float nn_key_dist(nnkey_t k) { return __uint_as_float(static_cast<unsigned>(k >> 32)); }
+__device__ __forceinline__ int nn_key_index(nnkey_t k) { return static_cast<int>(static_cast<unsigned>(k)); }
 
-__device__ __forceinline__ bool nn_key_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+struct NNKBest {
+  nnkey_t key;      // this lane's list entry
+  nnkey_t worst_k;  // entry k - 1 (warp-uniform)
+  float worst;      // its distance
+  bool fresh;       // nothing inserted yet (warp-uniform)
+  // views used by the callers
+  __device__ __forceinline__ float bd() const { return nn_key_dist(key); }
+  __device__ __forceinline__ int bi() const { return nn_key_index(key); }
+};
 
 // candidates of one leaf below the current k-th distance from which one sort + merge (about 20 compare-exchange stages) is
 // cheaper than an insertion each (about 30 instructions per insertion; ncu: 84 insertions per query on a 0.25 m sweep)
@@ -192,83 +203,60 @@ constexpr int kMergeThreshold = 6;
 
 __device__ __forceinline__ void nnk_leaf(const NNView& v, int leaf, float qx, float qy, float qz, int lane, int k, NNKBest& B) {
   const int j = leaf * kLeaf + lane;
-  float d = __int_as_float(0x7f800000);
-  int oi = 0x7fffffff;
+  nnkey_t c = kNNEmpty;
   if (j < v.n) {
     const float4 p = __ldg(v.spts + j);
-    d = nn_dist2(qx, qy, qz, p);
-    oi = __float_as_int(p.w);
+    c = nn_make_key(nn_dist2(qx, qy, qz, p), __float_as_int(p.w));
   }
   unsigned q = 0;
-  if (!B.fresh) q = __ballot_sync(kFullMask, nn_key_less(d, oi, B.worst, B.worst_i));
+  if (!B.fresh) q = __ballot_sync(kFullMask, c < B.worst_k);
   if (B.fresh || __popc(q) >= kMergeThreshold) {
     // sort the leaf's 32 candidates (bitonic network over the lanes) ...
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
       for (int s = size >> 1; s > 0; s >>= 1) {
-        const float od = __shfl_xor_sync(kFullMask, d, s);
-        const int oo = __shfl_xor_sync(kFullMask, oi, s);
+        const nnkey_t o = __shfl_xor_sync(kFullMask, c, s);
         const bool want_min = ((lane & size) == 0) == ((lane & s) == 0);
-        const bool other_less = nn_key_less(od, oo, d, oi);
-        if (want_min == other_less) {  // min keeper takes a smaller partner, max keeper takes a partner that is not smaller
-          d = od;
-          oi = oo;
-        }
+        if (want_min == (o < c)) c = o;  // min keeper takes a smaller partner, max keeper takes a partner that is not smaller
       }
     }
     if (B.fresh) {
       // ... first leaf: the list is empty, the sorted candidates are the list
       B.fresh = false;
-      B.bd = d;
-      B.bi = oi;
+      B.key = c;
     } else {
       // ... a leaf with many candidates below the current bound: one merge instead of an insertion per candidate.  The 32
       // smallest of (list, candidates): lane j keeps the smaller of list[j] and candidates[31 - j] (that sequence is
-      // bitonic), then a bitonic merge sorts it.  Keys (d2, index) are distinct, so the result is the same list the
-      // insertions would have built.
-      const float rd = __shfl_sync(kFullMask, d, 31 - lane);
-      const int ri = __shfl_sync(kFullMask, oi, 31 - lane);
-      if (nn_key_less(rd, ri, B.bd, B.bi)) {
-        B.bd = rd;
-        B.bi = ri;
-      }
+      // bitonic), then a bitonic merge sorts it.  Keys are distinct, so the result is the list the insertions would build.
+      const nnkey_t r = __shfl_sync(kFullMask, c, 31 - lane);
+      if (r < B.key) B.key = r;
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) {
-        const float od = __shfl_xor_sync(kFullMask, B.bd, s);
-        const int oo = __shfl_xor_sync(kFullMask, B.bi, s);
+        const nnkey_t o = __shfl_xor_sync(kFullMask, B.key, s);
         const bool want_min = (lane & s) == 0;
-        const bool other_less = nn_key_less(od, oo, B.bd, B.bi);
-        if (want_min == other_less) {
-          B.bd = od;
-          B.bi = oo;
-        }
+        if (want_min == (o < B.key)) B.key = o;
       }
     }
   } else {
     while (q) {
       const int src = __ffs(q) - 1;
       q &= q - 1;
-      const float cd = __shfl_sync(kFullMask, d, src);
-      const int ci = __shfl_sync(kFullMask, oi, src);
-      if (!nn_key_less(cd, ci, B.worst, B.worst_i)) continue;  // the list tightened since the vote
-      const int pos = __popc(__ballot_sync(kFullMask, nn_key_less(B.bd, B.bi, cd, ci)));  // entries ahead of the candidate: a prefix
-      const float ud = __shfl_up_sync(kFullMask, B.bd, 1);
-      const int ui = __shfl_up_sync(kFullMask, B.bi, 1);
-      if (lane > pos) {
-        B.bd = ud;
-        B.bi = ui;
-      } else if (lane == pos) {
-        B.bd = cd;
-        B.bi = ci;
-      }
-      B.worst = __shfl_sync(kFullMask, B.bd, k - 1);
-      B.worst_i = __shfl_sync(kFullMask, B.bi, k - 1);
+      const nnkey_t cc = __shfl_sync(kFullMask, c, src);
+      if (!(cc < B.worst_k)) continue;  // the list tightened since the vote
+      const int pos = __popc(__ballot_sync(kFullMask, B.key < cc));  // entries ahead of the candidate: a prefix
+      const nnkey_t up = __shfl_up_sync(kFullMask, B.key, 1);
+      if (lane > pos)
+        B.key = up;
+      else if (lane == pos)
+        B.key = cc;
+      B.worst_k = __shfl_sync(kFullMask, B.key, k - 1);
     }
+    B.worst = nn_key_dist(B.worst_k);
     return;
   }
-  B.worst = __shfl_sync(kFullMask, B.bd, k - 1);
-  B.worst_i = __shfl_sync(kFullMask, B.bi, k - 1);
+  B.worst_k = __shfl_sync(kFullMask, B.key, k - 1);
+  B.worst = nn_key_dist(B.worst_k);
 }
 
 template <int LC>
@@ -288,11 +276,11 @@ __device__ __forceinline__ void nnk_descend(const NNView& v, int first, int coun
   }
 }
 
-// after the call lane j < k holds the j-th nearest indexed point in (B.bd, B.bi); bi == INT_MAX where the index has
-// fewer than k points
+// after the call lane j < k holds the j-th nearest indexed point in B.key (B.bd() / B.bi()); bi == INT_MAX where the index
+// has fewer than k points
 __device__ __forceinline__ void nn_searchk_warp(const NNView& v, float qx, float qy, float qz, int lane, int k, NNKBest& B) {
-  B.bd = B.worst = __int_as_float(0x7f800000);
-  B.bi = B.worst_i = 0x7fffffff;
+  B.key = B.worst_k = kNNEmpty;
+  B.worst = __int_as_float(0x7f800000);
   B.fresh = true;
   if (v.n_levels == 3)
     nnk_descend<2>(v, 0, v.cnt[2], qx, qy, qz, lane, k, B);

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kSorBlock) sor_mean_dist_kernel(NNView v, int 
     const float4 qp = __ldg(v.spts + t);  // sorted order: neighbouring warps walk the same part of the tree
     NNKBest B;
     nn_searchk_warp(v, qp.x, qp.y, qp.z, lane, k, B);
-    const float r = (lane >= 1 && lane < k && B.bi != 0x7fffffff) ? __fsqrt_rn(B.bd) : 0.f;
+    const float r = (lane >= 1 && lane < k && B.bi() != 0x7fffffff) ? __fsqrt_rn(B.bd()) : 0.f;
     double s = 0.0;
     for (int j = 1; j < k; j++) s = __dadd_rn(s, static_cast<double>(__shfl_sync(kFullMask, r, j)));  // ascending-neighbour order
     if (lane == 0) distances[__float_as_int(qp.w)] = static_cast<float>(__ddiv_rn(s, static_cast<double>(mean_k)));
@@ -167,6 +167,7 @@ int lgs_sor_set_negative(lgs_sor* s, int32_t negative) {
 
 int lgs_sor_filter_dev(lgs_sor* s, const float* pts_dev, int64_t n, float* out_pts_dev, uint8_t* out_keep_dev, float* out_distances_dev,
                        lgs_sor_info* info) {
+  LGS_NVTX("lgs_sor_filter_dev");
   LGS_REQUIRE(s && info, "null argument");
   LGS_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "point count out of range");
   LGS_TRY(lgs::use_device(s->ctx));
@@ -175,6 +176,7 @@ int lgs_sor_filter_dev(lgs_sor* s, const float* pts_dev, int64_t n, float* out_p
 
 int lgs_sor_filter(lgs_sor* s, const void* pts, int64_t n, int32_t stride_bytes, float* out_pts, uint8_t* out_keep, float* out_distances,
                    lgs_sor_info* info) {
+  LGS_NVTX("lgs_sor_filter");
   LGS_REQUIRE(s && info, "null argument");
   LGS_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "point count out of range");
   lgs_ctx* ctx = s->ctx;

@@ -387,6 +387,7 @@ extern "C" {
 int lgs_voxelgrid_filter_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, const float leaf[3], int32_t min_points_per_voxel, double range_min,
                              const double* box6, float* out_pts_dev, int32_t* out_voxel_idx_dev, int32_t* out_member_rank_dev,
                              lgs_voxelgrid_info* info) {
+  LGS_NVTX("lgs_voxelgrid_filter_dev");
   LGS_REQUIRE(ctx && info && leaf, "null argument");
   LGS_TRY(lgs::use_device(ctx));
   return lgs::voxelgrid_device(ctx, reinterpret_cast<const float4*>(pts_dev), n, leaf, min_points_per_voxel, range_min, box6,
@@ -396,6 +397,7 @@ int lgs_voxelgrid_filter_dev(lgs_ctx* ctx, const float* pts_dev, int64_t n, cons
 int lgs_voxelgrid_filter(lgs_ctx* ctx, const void* pts, int64_t n, int32_t stride_bytes, const float leaf[3], int32_t min_points_per_voxel,
                          double range_min, const double* box6, float* out_pts, int32_t* out_voxel_idx, int32_t* out_member_rank,
                          lgs_voxelgrid_info* info) {
+  LGS_NVTX("lgs_voxelgrid_filter");
   LGS_REQUIRE(ctx && info && leaf, "null argument");
   LGS_TRY(lgs::use_device(ctx));
   struct Arena {
