@@ -535,6 +535,18 @@ def main():
     peak, peak_src = measured_peak_hbm()
     traffic, traffic_src = ncu_traffic()
 
+    # where the align kernel's time goes (its own clock64 accounting, last align of the timed pass): the share the evaluating
+    # CTAs spend in the evaluation body, and what the body alone achieves against the roofline
+    step_dev(0)
+    bd = ndt.align_breakdown()
+    body_share = bd["raw"][0] / bd["total"] if bd["total"] > 0 else 0.0
+    breakdown = {"evaluation_body_share_of_kernel": body_share,
+                 "optimiser_cta": {k: bd[k] / bd["total"] for k in ("wait_grid", "add_rows", "optimiser", "publish")} if bd["total"] > 0 else None,
+                 "evaluation_body_gbs": achieved / body_share if body_share > 0 else None,
+                 "evaluation_body_frac_of_peak": achieved / body_share / peak if body_share > 0 else None,
+                 "note": "SM cycles of CTA 0 (evaluating) in deriv_eval / all cycles of the optimiser CTA; the rest of an evaluation is the grid-wide hand-over: "
+                         "waiting for the slowest CTA, adding the 147 rows, the Newton / More-Thuente step, publishing the next pose"}
+
     # the evaluation body alone, one launch per evaluation (the host steps the optimiser): what a single evaluation costs
     ndt.profile(1)
     for i in range(min(K, 12)):
@@ -598,7 +610,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "ndt_align_kernel<true> (one launch = one align: %.2f derivative evaluations + the optimiser between them)" % (prof["evaluations"] / n_launch),
                          "kernel_ms": kern_ms, "launches_timed": prof["align_launches"], "timed": "live, CUDA events on the launching stream around every launch of the timed region",
-                         "algorithmic_bytes": alg_bytes, "h_bar": hbar, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes, "h_bar": hbar, "peak_source": peak_src, "inside_the_kernel": breakdown,
                          "single_evaluation_kernels_ms": {"ndt_derivatives_kernel<0> (score + g + H)": prof1["hess_ms"] / max(prof1["hess_launches"], 1),
                                                           "ndt_derivatives_kernel<1> (score + g)": prof1["grad_ms"] / max(prof1["grad_launches"], 1),
                                                           "ndt_derivatives_kernel<2> (f64 Hessian)": prof1["h64_ms"] / max(prof1["h64_launches"], 1),
