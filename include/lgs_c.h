@@ -180,6 +180,17 @@ int lgs_ndt_set_source(lgs_ndt* ndt, const void* pts, int64_t n, int32_t stride_
  * returns a result to the host; a context created on the caller's own stream makes this ordinary stream ordering. */
 int lgs_ndt_set_target_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
 int lgs_ndt_set_source_dev(lgs_ndt* ndt, const float* pts_dev, int64_t n);
+/* The rolling local map of the scan matcher (LSM:187-212: on a key-frame change the node concatenates the last N key frames,
+ * transformed by their poses, and calls setInputTarget, which re-voxelises all of them).  Here the target is given as a
+ * list of key frames of a device-resident key-frame array and maintained INCREMENTALLY: the voxel partial sums of every
+ * key frame are cached per (pose, resolution); a call voxelises only the key frames it has not seen (typically the one
+ * that entered the window), drops those that left, and merges the cached sums in the order of ids[] - the order in which
+ * the reference concatenates.  The voxel table equals setInputTarget(assembled cloud): occupancy, counts and validity
+ * flags identical, means / covariances to the f64 rounding of adding per-frame sums (~1e-16 relative).  A moved key frame
+ * (lgs_keyframes_set_pose) is re-voxelised.  *frames_voxelised (optional): key frames voxelised from their points by this
+ * call.  getFitnessScore assembles the cloud on first use. */
+typedef struct lgs_keyframes lgs_keyframes;
+int lgs_ndt_set_target_keyframes(lgs_ndt* ndt, lgs_keyframes* kf, const int32_t* ids, int32_t n_ids, int32_t* frames_voxelised);
 /* align (pcl::Registration::align + NDT:80-171, LSM:165, GBS:318).  guess may be NULL (identity).
  * out_cloud: NULL or capacity n_source packed xyzi records = source transformed by the final T. */
 int lgs_ndt_align(lgs_ndt* ndt, const float* guess16, lgs_align_result* result, float* out_cloud);
@@ -347,7 +358,7 @@ int lgs_sort_pairs(lgs_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int3
 /*   replaces the per-key-frame fromROSMsg + transform_point_cloud + `*cloud += ...` loops and the */
 /*   re-upload of the assembled map: LSM:196-212 (local map, newest first) and GBS:297-313         */
 /*   (candidate neighbourhood, ascending index, then VoxelGrid).  A key frame is uploaded once.    */
-typedef struct lgs_keyframes lgs_keyframes;
+/* (lgs_keyframes is declared with lgs_ndt_set_target_keyframes above) */
 
 int lgs_keyframes_create(lgs_ctx* ctx, lgs_keyframes** out);
 void lgs_keyframes_destroy(lgs_keyframes* kf);

@@ -384,6 +384,15 @@ class NormalDistributionsTransform(_Registration):
         return dict(hess_launches=int(out[0]), hess_ms=out[1], grad_launches=int(out[2]), grad_ms=out[3], h64_launches=int(out[4]),
                     h64_ms=out[5], terms_last_eval=out[6], n_source=int(out[7]))
 
+    def setInputTargetKeyFrames(self, kf, ids):
+        """The rolling local map (LSM:187-212) as a list of key frames of a device-resident KeyFrameArray, maintained
+        incrementally (lgs_ndt_set_target_keyframes).  Returns the number of key frames voxelised from their points."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        nv = C.c_int32()
+        check(self._L.lgs_ndt_set_target_keyframes(self._h, kf._h, ids.ctypes.data_as(C.c_void_p), int(ids.size), C.byref(nv)))
+        self._nt = -1
+        return nv.value
+
     def align_breakdown(self):
         """SM cycles CTA 0 spent per phase of the last device-resident align (lgs_ndt_align_breakdown)."""
         out = np.zeros(16)

@@ -15,5 +15,6 @@ int keyframes_wait_resident(const lgs_keyframes* kf);
 int64_t keyframes_count(const lgs_keyframes* kf);
 int64_t keyframes_points(const lgs_keyframes* kf, int64_t id);  // points of key frame id
 int keyframes_device(const lgs_keyframes* kf);
+const float* keyframes_pose(const lgs_keyframes* kf, int64_t id);  // column-major 4x4 of key frame id
 
 }  // namespace lgs

@@ -20,8 +20,10 @@
 #include <utility>
 #include <vector>
 
+#include "keyframes.cuh"
 #include "math.cuh"
 #include "nn.cuh"
+#include "sort.cuh"
 #include "voxel_common.cuh"
 
 namespace lgs {
@@ -131,8 +133,10 @@ __global__ void __launch_bounds__(kSumsWarps * 32) voxel_sums_kernel(const float
 
 // pass 2 (VGC:282-367): one thread per voxel finishes mean / covariance / eigen regularisation / inverse and publishes the
 // lookup record and the cell-table entry.
+// counts: members per voxel when a voxel's entries are partial sums of several key frames (rolling map); otherwise the
+// segment length is the member count.
 __global__ void __launch_bounds__(128) voxel_stats_kernel(const double* __restrict__ sums, const unsigned* __restrict__ keys,
-                                                         const int* __restrict__ seg_start, int n_seg,
+                                                         const int* __restrict__ seg_start, const int* __restrict__ counts, int n_seg,
                                                          int64_t n_pts, int min_pts, double eig_mult, VoxelExport ex, VoxelRec* __restrict__ recs,
                                                          int* __restrict__ dense_table, int* __restrict__ hkeys, int* __restrict__ hvals,
                                                          unsigned hmask, int* __restrict__ n_valid) {
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(128) voxel_stats_kernel(const double* __restri
   const int key = static_cast<int>(keys[b]);
   const double* sv = sums + static_cast<size_t>(v) * kSumsPerVoxel;
   const double s0 = sv[0], s1 = sv[1], s2 = sv[2], c00 = sv[3], c01 = sv[4], c02 = sv[5], c11 = sv[6], c12 = sv[7], c22 = sv[8];
-  int n = e - b;
+  int n = counts ? counts[v] : e - b;
   double cov[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
   double sum[3] = {s0, s1, s2};
   double mean[3] = {s0 / n, s1 / n, s2 / n};  // VGC:293
@@ -208,6 +212,90 @@ __global__ void __launch_bounds__(128) voxel_stats_kernel(const double* __restri
       }
     }
     atomicAdd(n_valid, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rolling map: merging cached per-key-frame voxel partial sums (lgs_ndt_set_target_keyframes)
+
+// per key frame, after its own voxelisation: local voxel index and member count of every occupied voxel
+__global__ void __launch_bounds__(256) frame_pack_kernel(const unsigned* __restrict__ keys, const int* __restrict__ seg_start, int n_seg, int64_t n_kept,
+                                                        unsigned* __restrict__ out_keys, int* __restrict__ out_cnt) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_seg) return;
+  const int b = seg_start[v];
+  const int e = (v + 1 < n_seg) ? seg_start[v + 1] : static_cast<int>(n_kept);
+  out_keys[v] = keys[b];
+  out_cnt[v] = e - b;
+}
+
+constexpr int kMergeFrames = 40;  // key frames per gather launch (kernel parameter space); longer lists are split
+struct MergeSegments {
+  const unsigned* keys[kMergeFrames];
+  const int* cnt[kMergeFrames];
+  const double* sums[kMergeFrames];
+  int begin[kMergeFrames + 1];  // first entry of each frame (relative to this launch)
+  int fmin[kMergeFrames][3];    // the frame grid's min_b minus the map's min_b
+  int fdx[kMergeFrames], fdxy[kMergeFrames];
+  int gmul[3];
+  int count;
+};
+
+// every cached entry (frame-major, i.e. in the order the reference concatenates the key frames) gets its voxel index in the
+// MAP's grid; counts and sums are copied next to it
+__global__ void __launch_bounds__(256) frame_gather_kernel(const MergeSegments S, int out0, unsigned* __restrict__ gkeys, unsigned* __restrict__ gvals,
+                                                          int* __restrict__ ccnt, double* __restrict__ csum) {
+  __shared__ int begin[kMergeFrames + 1];
+  for (int t = threadIdx.x; t <= S.count; t += blockDim.x) begin[t] = S.begin[t];
+  __syncthreads();
+  const int total = begin[S.count];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = S.count - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (begin[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int l = i - begin[lo];
+    const unsigned key = S.keys[lo][l];
+    const int iz = static_cast<int>(key / static_cast<unsigned>(S.fdxy[lo]));
+    const int rem = static_cast<int>(key % static_cast<unsigned>(S.fdxy[lo]));
+    const int iy = rem / S.fdx[lo], ix = rem % S.fdx[lo];
+    const int g = (ix + S.fmin[lo][0]) * S.gmul[0] + (iy + S.fmin[lo][1]) * S.gmul[1] + (iz + S.fmin[lo][2]) * S.gmul[2];
+    const int o = out0 + i;
+    gkeys[o] = static_cast<unsigned>(g);
+    gvals[o] = static_cast<unsigned>(o);
+    ccnt[o] = S.cnt[lo][l];
+#pragma unroll
+    for (int c = 0; c < kSumsPerVoxel; c++) csum[static_cast<size_t>(o) * kSumsPerVoxel + c] = S.sums[lo][static_cast<size_t>(l) * kSumsPerVoxel + c];
+  }
+}
+
+struct MergeHeads {  // start offset of every run of equal map voxel indices (sort.cuh scan_select functor)
+  const unsigned* keys;
+  int* seg_start;
+  __device__ bool flag(int64_t i) const { return i == 0 || keys[i] != keys[i - 1]; }
+  __device__ void emit(int64_t i, int64_t pos, bool f) const {
+    if (f) seg_start[pos] = static_cast<int>(i);
+  }
+};
+
+// one thread per (map voxel, sum): the key frames' partial sums are added in key-frame order (the stable sort kept it)
+__global__ void __launch_bounds__(256) frame_merge_kernel(const unsigned* __restrict__ svals, const int* __restrict__ seg_start, int n_seg, int n_entries,
+                                                         const int* __restrict__ ccnt, const double* __restrict__ csum, double* __restrict__ msum,
+                                                         int* __restrict__ mcnt) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = t / (kSumsPerVoxel + 1), c = t % (kSumsPerVoxel + 1);
+  if (v >= n_seg) return;
+  const int b = seg_start[v];
+  const int e = (v + 1 < n_seg) ? seg_start[v + 1] : n_entries;
+  if (c == kSumsPerVoxel) {
+    int n = 0;
+    for (int j = b; j < e; j++) n += ccnt[svals[j]];
+    mcnt[v] = n;
+  } else {
+    double a = 0.0;
+    for (int j = b; j < e; j++) a = __dadd_rn(a, csum[static_cast<size_t>(svals[j]) * kSumsPerVoxel + c]);
+    msum[static_cast<size_t>(v) * kSumsPerVoxel + c] = a;
   }
 }
 
@@ -363,6 +451,25 @@ struct lgs_ndt {
   EvalParams P;
   int evals = 0, trials = 0, hess_recomputes = 0;
   double last_terms = 0;
+  // rolling map (lgs_ndt_set_target_keyframes): the target is a list of key frames of a device-resident key-frame array; every
+  // key frame's voxel partial sums are cached (per pose and resolution), a key-frame change voxelises only the new frame
+  struct FrameVox {
+    int32_t id = -1;
+    float pose[16];
+    float res = 0;
+    int64_t n_points = 0;
+    int n_vox = 0;
+    int min_b[3] = {0, 0, 0}, div_b[3] = {1, 1, 1}, max_b[3] = {0, 0, 0};
+    DevBuf keys, cnt, sums;  // n_vox: local linear voxel index (u32), members (int), 9 f64 sums
+    int64_t last_used = 0;
+  };
+  std::vector<FrameVox*> frame_cache;
+  const lgs_keyframes* roll_kf = nullptr;
+  std::vector<int32_t> roll_ids;
+  bool target_from_frames = false, target_cloud_stale = false;
+  int64_t roll_epoch = 0;
+  int roll_frames_voxelised = 0;  // key frames voxelised from their points by the last set_target_keyframes
+  DevBuf roll_frame, roll_gkeys, roll_gvals, roll_gkeys_alt, roll_gvals_alt, roll_ccnt, roll_csum, roll_msum, roll_mcnt, roll_seg, roll_small, roll_poses;
   // device-resident align (ndt_align_kernel): the hand-over block of the resident grid, and how the last align ran
   lgs::DevBuf align_dev;
   int align_launches = 0;      // ndt_align_kernel launches of the last align (1, or 0 when the host stepped the optimiser)
@@ -491,8 +598,52 @@ CellTable make_cell_table(const lgs_ndt* n) {
 
 int eval_grid(int64_t n) { return std::max(1, std::min(grid_for(n, kEvalBlock), kNumSMs * 4)); }
 
+// second half of the target build: from per-voxel sums (ascending voxel index) to records, export arrays and cell table
+int finish_grid(lgs_ndt* n, int V, uint64_t total_cells, const unsigned* keys, const int* seg_start, int64_t n_entries, const double* sums,
+                const int* counts) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  n->n_voxels = V;
+  n->dense = total_cells <= kDenseCellLimit ? 1 : 0;
+  LGS_TRY(n->recs.reserve(static_cast<size_t>(V) * sizeof(VoxelRec)));
+  LGS_TRY(n->ex_idx.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(n->ex_n.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(n->ex_mean.reserve(static_cast<size_t>(V) * 24));
+  LGS_TRY(n->ex_cov.reserve(static_cast<size_t>(V) * 72));
+  LGS_TRY(n->ex_icov.reserve(static_cast<size_t>(V) * 72));
+  LGS_TRY(n->small.reserve(64));
+  LGS_CUDA(cudaMemsetAsync(n->small.p, 0, 64, st));
+  if (n->dense) {
+    LGS_TRY(n->table.reserve(total_cells * 4));
+    LGS_CUDA(cudaMemsetAsync(n->table.p, 0xFF, total_cells * 4, st));
+    n->hmask = 0;
+  } else {
+    uint64_t cap = 1024;
+    while (cap < static_cast<uint64_t>(V) * 2) cap <<= 1;
+    n->hmask = static_cast<unsigned>(cap - 1);
+    LGS_TRY(n->table.reserve(cap * 4));
+    LGS_TRY(n->hkeys.reserve(cap * 4));
+    LGS_CUDA(cudaMemsetAsync(n->hkeys.p, 0xFF, cap * 4, st));
+  }
+  VoxelExport ex{n->ex_idx.as<int>(), n->ex_n.as<int>(), n->ex_mean.as<double>(), n->ex_cov.as<double>(), n->ex_icov.as<double>()};
+  voxel_stats_kernel<<<grid_for(V, 128), 128, 0, st>>>(sums, keys, seg_start, counts, V, n_entries, 6, 0.01, ex, n->recs.as<VoxelRec>(),
+                                                      n->dense ? n->table.as<int>() : nullptr, n->hkeys.as<int>(), n->table.as<int>(), n->hmask,
+                                                      n->small.as<int>());
+  ctx->launches++;
+  LGS_CUDA(cudaGetLastError());
+  LGS_TRY(ctx->pin.reserve(256));
+  int* h = ctx->pin.as<int>();
+  LGS_CUDA(cudaMemcpyAsync(h, n->small.p, 4, cudaMemcpyDeviceToHost, st));
+  LGS_CUDA(cudaStreamSynchronize(st));
+  n->n_valid = h[0];
+  n->grid_ready = true;
+  return LGS_OK;
+}
+
 // init() (NDT.h:276-283): (re)voxelise the target at the current resolution
+int build_grid_from_frames(lgs_ndt* n);
 int build_grid(lgs_ndt* n) {
+  if (n->target_from_frames) return build_grid_from_frames(n);
   lgs_ctx* ctx = n->ctx;
   cudaStream_t st = ctx->stream;
   n->grid_ready = false;
@@ -513,43 +664,189 @@ int build_grid(lgs_ndt* n) {
     n->div_b[a] = sv.div_b[a];
   }
   const int V = sv.n_seg;
-  n->n_voxels = V;
-  n->dense = sv.total_cells <= kDenseCellLimit ? 1 : 0;
-  LGS_TRY(n->recs.reserve(static_cast<size_t>(V) * sizeof(VoxelRec)));
-  LGS_TRY(n->ex_idx.reserve(static_cast<size_t>(V) * 4));
-  LGS_TRY(n->ex_n.reserve(static_cast<size_t>(V) * 4));
-  LGS_TRY(n->ex_mean.reserve(static_cast<size_t>(V) * 24));
-  LGS_TRY(n->ex_cov.reserve(static_cast<size_t>(V) * 72));
-  LGS_TRY(n->ex_icov.reserve(static_cast<size_t>(V) * 72));
-  LGS_TRY(n->small.reserve(64));
-  LGS_CUDA(cudaMemsetAsync(n->small.p, 0, 64, st));
-  if (n->dense) {
-    LGS_TRY(n->table.reserve(sv.total_cells * 4));
-    LGS_CUDA(cudaMemsetAsync(n->table.p, 0xFF, sv.total_cells * 4, st));
-    n->hmask = 0;
-  } else {
-    uint64_t cap = 1024;
-    while (cap < static_cast<uint64_t>(V) * 2) cap <<= 1;
-    n->hmask = static_cast<unsigned>(cap - 1);
-    LGS_TRY(n->table.reserve(cap * 4));
-    LGS_TRY(n->hkeys.reserve(cap * 4));
-    LGS_CUDA(cudaMemsetAsync(n->hkeys.p, 0xFF, cap * 4, st));
-  }
-  VoxelExport ex{n->ex_idx.as<int>(), n->ex_n.as<int>(), n->ex_mean.as<double>(), n->ex_cov.as<double>(), n->ex_icov.as<double>()};
   LGS_TRY(n->vsums.reserve(static_cast<size_t>(V) * kSumsPerVoxel * sizeof(double)));
   voxel_sums_kernel<<<grid_for(static_cast<int64_t>(V) * 32, 256), 256, 0, st>>>(n->target.as<float4>(), sv.vals, sv.seg_start, V, sv.n_kept, n->vsums.as<double>());
   ctx->launches++;
-  voxel_stats_kernel<<<grid_for(V, 128), 128, 0, st>>>(n->vsums.as<double>(), sv.keys, sv.seg_start, V, sv.n_kept, 6, 0.01, ex,
-                                                      n->recs.as<VoxelRec>(), n->dense ? n->table.as<int>() : nullptr, n->hkeys.as<int>(),
-                                                      n->table.as<int>(), n->hmask, n->small.as<int>());
-  ctx->launches++;
+  return finish_grid(n, V, sv.total_cells, sv.keys, sv.seg_start, sv.n_kept, n->vsums.as<double>(), nullptr);
+}
+
+// ---- rolling map ---------------------------------------------------------------------------------------------------
+static int bits_for_cells(uint64_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b) != 0) b++;
+  return b;
+}
+
+// voxel partial sums of ONE key frame (transformed by its pose) in the frame's own grid
+int voxelise_frame(lgs_ndt* n, const lgs_keyframes* kf, int32_t id, lgs_ndt::FrameVox* f) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  f->id = id;
+  memcpy(f->pose, keyframes_pose(kf, id), sizeof(f->pose));
+  f->res = n->resolution;
+  f->n_points = keyframes_points(kf, id);
+  f->n_vox = 0;
+  int64_t n_out = 0;
+  LGS_TRY(keyframes_assemble_into(kf, ctx, &id, 1, &n->roll_poses, &n->roll_frame, &n_out));
+  if (n_out == 0) return LGS_OK;
+  const float leaf[3] = {n->resolution, n->resolution, n->resolution};
+  SortedVoxels sv;
+  LGS_TRY(build_sorted_voxels(ctx, n->roll_frame.as<float4>(), n_out, leaf, -1.0, nullptr, nullptr, nullptr, &sv));
+  if (sv.status == LGS_VG_REFUSED_OVERFLOW) {
+    set_error("key frame %d alone exceeds the voxel index range at resolution %g", id, n->resolution);
+    return LGS_ERR_INVALID;
+  }
+  if (sv.n_kept == 0) return LGS_OK;
+  const int V = sv.n_seg;
+  for (int a = 0; a < 3; a++) {
+    f->min_b[a] = sv.min_b[a];
+    f->max_b[a] = sv.max_b[a];
+    f->div_b[a] = sv.div_b[a];
+  }
+  LGS_TRY(f->keys.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(f->cnt.reserve(static_cast<size_t>(V) * 4));
+  LGS_TRY(f->sums.reserve(static_cast<size_t>(V) * kSumsPerVoxel * sizeof(double)));
+  voxel_sums_kernel<<<grid_for(static_cast<int64_t>(V) * 32, 256), 256, 0, st>>>(n->roll_frame.as<float4>(), sv.vals, sv.seg_start, V, sv.n_kept, f->sums.as<double>());
+  frame_pack_kernel<<<grid_for(V, 256), 256, 0, st>>>(sv.keys, sv.seg_start, V, sv.n_kept, f->keys.as<unsigned>(), f->cnt.as<int>());
+  ctx->launches += 2;
   LGS_CUDA(cudaGetLastError());
-  LGS_TRY(ctx->pin.reserve(256));
-  int* h = ctx->pin.as<int>();
-  LGS_CUDA(cudaMemcpyAsync(h, n->small.p, 4, cudaMemcpyDeviceToHost, st));
-  LGS_CUDA(cudaStreamSynchronize(st));
-  n->n_valid = h[0];
-  n->grid_ready = true;
+  f->n_vox = V;
+  return LGS_OK;
+}
+
+// (Re)builds the voxel structure from the key frames of n->roll_ids: cached partial sums for the frames seen before (same
+// pose, same resolution), a fresh voxelisation for the others, then one merge.  Equals the full build on the concatenated
+// cloud up to the f64 rounding of adding per-frame partial sums instead of one running sum (~1e-16 relative).
+int build_grid_from_frames(lgs_ndt* n) {
+  lgs_ctx* ctx = n->ctx;
+  cudaStream_t st = ctx->stream;
+  const lgs_keyframes* kf = n->roll_kf;
+  n->grid_ready = false;
+  n->refused = false;
+  n->n_voxels = n->n_valid = 0;
+  n->roll_epoch++;
+  n->roll_frames_voxelised = 0;
+  std::vector<lgs_ndt::FrameVox*> use;
+  for (int32_t id : n->roll_ids) {
+    lgs_ndt::FrameVox* f = nullptr;
+    for (auto* c : n->frame_cache)
+      if (c->id == id) f = c;
+    const bool valid = f && f->res == n->resolution && f->n_points == keyframes_points(kf, id) && memcmp(f->pose, keyframes_pose(kf, id), sizeof(f->pose)) == 0;
+    if (!valid) {
+      if (!f) {
+        f = new lgs_ndt::FrameVox;
+        n->frame_cache.push_back(f);
+      }
+      LGS_TRY(voxelise_frame(n, kf, id, f));
+      n->roll_frames_voxelised++;
+    }
+    f->last_used = n->roll_epoch;
+    use.push_back(f);
+  }
+  // evict the frames that left the window
+  for (size_t i = 0; i < n->frame_cache.size();) {
+    if (n->frame_cache[i]->last_used != n->roll_epoch) {
+      lgs_ndt::FrameVox* f = n->frame_cache[i];
+      LGS_CUDA(cudaStreamSynchronize(st));
+      f->keys.release();
+      f->cnt.release();
+      f->sums.release();
+      delete f;
+      n->frame_cache.erase(n->frame_cache.begin() + i);
+    } else {
+      i++;
+    }
+  }
+  int64_t M = 0;
+  bool any = false;
+  int gmin[3] = {0, 0, 0}, gmax[3] = {0, 0, 0};
+  for (auto* f : use) {
+    if (f->n_vox == 0) continue;
+    M += f->n_vox;
+    for (int a = 0; a < 3; a++) {
+      gmin[a] = any ? std::min(gmin[a], f->min_b[a]) : f->min_b[a];
+      gmax[a] = any ? std::max(gmax[a], f->max_b[a]) : f->max_b[a];
+    }
+    any = true;
+  }
+  int64_t d[3];
+  for (int a = 0; a < 3; a++) d[a] = static_cast<int64_t>(gmax[a]) - gmin[a] + 1;
+  if (!any || d[0] * d[1] * d[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max()) || M >= (int64_t(1) << 31)) {  // VGC:79-84
+    n->refused = true;
+    n->grid_ready = true;
+    return LGS_OK;
+  }
+  for (int a = 0; a < 3; a++) {
+    n->min_b[a] = gmin[a];
+    n->max_b[a] = gmax[a];
+    n->div_b[a] = static_cast<int>(d[a]);
+  }
+  const uint64_t total_cells = static_cast<uint64_t>(d[0]) * d[1] * d[2];
+  LGS_TRY(n->roll_gkeys.reserve(static_cast<size_t>(M) * 4));
+  LGS_TRY(n->roll_gvals.reserve(static_cast<size_t>(M) * 4));
+  LGS_TRY(n->roll_gkeys_alt.reserve(static_cast<size_t>(M) * 4));
+  LGS_TRY(n->roll_gvals_alt.reserve(static_cast<size_t>(M) * 4));
+  LGS_TRY(n->roll_ccnt.reserve(static_cast<size_t>(M) * 4));
+  LGS_TRY(n->roll_csum.reserve(static_cast<size_t>(M) * kSumsPerVoxel * sizeof(double)));
+  int64_t out0 = 0;
+  for (size_t s0 = 0; s0 < use.size(); s0 += kMergeFrames) {
+    MergeSegments S;
+    S.count = 0;
+    int acc = 0;
+    for (size_t s = s0; s < std::min(use.size(), s0 + kMergeFrames); s++) {
+      const lgs_ndt::FrameVox* f = use[s];
+      if (f->n_vox == 0) continue;
+      const int k = S.count++;
+      S.keys[k] = f->keys.as<unsigned>();
+      S.cnt[k] = f->cnt.as<int>();
+      S.sums[k] = f->sums.as<double>();
+      S.begin[k] = acc;
+      acc += f->n_vox;
+      for (int a = 0; a < 3; a++) S.fmin[k][a] = f->min_b[a] - gmin[a];
+      S.fdx[k] = f->div_b[0];
+      S.fdxy[k] = f->div_b[0] * f->div_b[1];
+    }
+    S.begin[S.count] = acc;
+    S.gmul[0] = 1;
+    S.gmul[1] = static_cast<int>(d[0]);
+    S.gmul[2] = static_cast<int>(d[0] * d[1]);
+    if (acc > 0) {
+      frame_gather_kernel<<<std::max(1, std::min(grid_for(acc, 256), kNumSMs * 8)), 256, 0, st>>>(S, static_cast<int>(out0), n->roll_gkeys.as<unsigned>(),
+                                                                                              n->roll_gvals.as<unsigned>(), n->roll_ccnt.as<int>(),
+                                                                                              n->roll_csum.as<double>());
+      ctx->launches++;
+    }
+    out0 += acc;
+  }
+  LGS_CUDA(cudaGetLastError());
+  unsigned *skeys, *svals;
+  LGS_TRY(radix_sort_pairs(ctx, n->roll_gkeys.as<unsigned>(), n->roll_gvals.as<unsigned>(), n->roll_gkeys_alt.as<unsigned>(), n->roll_gvals_alt.as<unsigned>(), M,
+                           bits_for_cells(total_cells), &skeys, &svals));
+  LGS_TRY(n->roll_seg.reserve(static_cast<size_t>(M) * 4 + 64));
+  LGS_TRY(n->roll_small.reserve(64));
+  Mailbox mb;
+  LGS_TRY(mailbox_next(ctx, &mb));
+  LGS_TRY(scan_select(ctx, MergeHeads{skeys, n->roll_seg.as<int>()}, M, n->roll_small.as<int>(), &mb));
+  double nseg = 0;
+  LGS_TRY(mailbox_wait(ctx, mb, 1, &nseg));
+  const int V = static_cast<int>(nseg);
+  LGS_TRY(n->roll_msum.reserve(static_cast<size_t>(V) * kSumsPerVoxel * sizeof(double)));
+  LGS_TRY(n->roll_mcnt.reserve(static_cast<size_t>(V) * 4));
+  frame_merge_kernel<<<grid_for(static_cast<int64_t>(V) * (kSumsPerVoxel + 1), 256), 256, 0, st>>>(svals, n->roll_seg.as<int>(), V, static_cast<int>(M), n->roll_ccnt.as<int>(),
+                                                                                                 n->roll_csum.as<double>(), n->roll_msum.as<double>(),
+                                                                                                 n->roll_mcnt.as<int>());
+  ctx->launches++;
+  return finish_grid(n, V, total_cells, skeys, n->roll_seg.as<int>(), M, n->roll_msum.as<double>(), n->roll_mcnt.as<int>());
+}
+
+// getFitnessScore needs the target as a cloud: assembled from the key frames on first use
+int ensure_target_cloud(lgs_ndt* n) {
+  if (!n->target_from_frames || !n->target_cloud_stale) return LGS_OK;
+  int64_t total = 0;
+  LGS_TRY(keyframes_assemble_into(n->roll_kf, n->ctx, n->roll_ids.data(), static_cast<int32_t>(n->roll_ids.size()), &n->roll_poses, &n->target, &total));
+  n->n_target = total;
+  n->target_cloud_stale = false;
+  n->nn_ready = false;
   return LGS_OK;
 }
 
@@ -823,6 +1120,15 @@ void lgs_ndt_destroy(lgs_ndt* n) {
   cudaSetDevice(n->ctx->device);
   cudaStreamSynchronize(n->ctx->stream);
   n->align_dev.release();
+  for (auto* f : n->frame_cache) {
+    f->keys.release();
+    f->cnt.release();
+    f->sums.release();
+    delete f;
+  }
+  for (DevBuf* b : {&n->roll_frame, &n->roll_gkeys, &n->roll_gvals, &n->roll_gkeys_alt, &n->roll_gvals_alt, &n->roll_ccnt, &n->roll_csum, &n->roll_msum,
+                    &n->roll_mcnt, &n->roll_seg, &n->roll_small, &n->roll_poses})
+    b->release();
   for (DevBuf* b : {&n->target, &n->source, &n->out_cloud, &n->table, &n->hkeys, &n->recs, &n->ex_idx, &n->ex_n, &n->ex_mean, &n->ex_cov, &n->ex_icov,
                     &n->small, &n->partials, &n->result, &n->vsums})
     b->release();
@@ -856,6 +1162,7 @@ int lgs_ndt_set_search_method(lgs_ndt* n, int32_t m) {
 static int after_target(lgs_ndt* n) {
   n->have_target = true;
   n->nn_ready = false;
+  n->target_from_frames = false;
   return build_grid(n);
 }
 
@@ -875,6 +1182,28 @@ int lgs_ndt_set_target_dev(lgs_ndt* n, const float* pts_dev, int64_t cnt) {
   n->n_target = cnt;
   return after_target(n);
 }
+int lgs_ndt_set_target_keyframes(lgs_ndt* n, lgs_keyframes* kf, const int32_t* ids, int32_t n_ids, int32_t* frames_voxelised) {
+  LGS_NVTX("lgs_ndt_set_target_keyframes");
+  LGS_REQUIRE(n && kf && (ids || n_ids == 0) && n_ids >= 0, "bad argument");
+  LGS_REQUIRE(keyframes_device(kf) == n->ctx->device, "the key-frame array lives on another device");
+  const int64_t count = keyframes_count(kf);
+  for (int32_t i = 0; i < n_ids; i++) LGS_REQUIRE(ids[i] >= 0 && ids[i] < count, "key frame id out of range");
+  LGS_TRY(use_device(n->ctx));
+  LGS_TRY(keyframes_wait_resident(kf));
+  if (n->roll_kf != kf) {  // another array: nothing cached applies
+    for (auto* f : n->frame_cache) f->id = -1;
+  }
+  n->roll_kf = kf;
+  n->roll_ids.assign(ids, ids + n_ids);
+  n->target_from_frames = true;
+  n->target_cloud_stale = true;
+  n->have_target = true;
+  n->nn_ready = false;
+  const int rc = build_grid_from_frames(n);
+  if (frames_voxelised) *frames_voxelised = n->roll_frames_voxelised;
+  return rc;
+}
+
 int lgs_ndt_set_source(lgs_ndt* n, const void* pts, int64_t cnt, int32_t stride) {
   LGS_REQUIRE(n, "null");
   LGS_TRY(use_device(n->ctx));
@@ -952,6 +1281,7 @@ int lgs_ndt_fitness(lgs_ndt* n, double max_range, double* fitness) {
     return LGS_ERR_STATE;
   }
   LGS_TRY(use_device(n->ctx));
+  LGS_TRY(ensure_target_cloud(n));
   if (!n->nn_ready) {
     LGS_TRY(n->nn.build(n->ctx, n->target.as<float4>(), n->n_target));
     n->nn_ready = true;

@@ -277,6 +277,83 @@ def test_ndt_device_resident_align_equals_host_stepped(api, velodyne_pair, oracl
     assert all(l == 1 for l in launches), launches  # one kernel launch per align
 
 
+def test_ndt_rolling_map_incremental_target(api, oracle):
+    """SURVEY section 8f-2 / LSM:187-212: the scan matcher's rolling local map as a list of resident key frames, maintained
+    incrementally (lgs_ndt_set_target_keyframes).  Sliding the window voxelises only the key frame that entered it; the voxel
+    table equals setInputTarget(assembled cloud) - occupancy, counts, validity flags identical, means / covariances to 1e-12 -
+    and the oracle's on the same cloud; aligns take the same iterations to the same pose; a moved key frame is re-voxelised."""
+    from lidar_graph_slam_b200 import synth
+    n_kf, window = 14, 8
+    d = synth.loop_keyframes(n_pairs=1, n_keyframes=n_kf, n_azimuth=900, n_unique=1)
+    kf = api.KeyFrameArray()
+    for c, P in zip(d["clouds"][:n_kf], d["poses"][:n_kf]):
+        kf.push(c, P)
+    inc = api.NormalDistributionsTransform()
+    full = api.NormalDistributionsTransform()
+    for x in (inc, full):
+        x.setResolution(1.0)
+        x.setTransformationEpsilon(0.01)
+        x.setMaximumIterations(64)
+
+    def check_same(ids, src, guess, with_oracle=False):
+        cloud = kf.assemble(ids)
+        full.setInputTarget(cloud)
+        vi, vf = inc.export_voxels(), full.export_voxels()
+        assert np.array_equal(vi["idx"], vf["idx"]) and np.array_equal(vi["n"], vf["n"]) and vi["n_valid"] == vf["n_valid"]
+        assert list(vi["min_b"]) == list(vf["min_b"]) and list(vi["div_b"]) == list(vf["div_b"])
+        valid = vf["n"] >= 6
+        np.testing.assert_allclose(vi["mean"], vf["mean"], rtol=1e-12, atol=1e-12)
+        # the single-pass covariance (VGC:329) cancels sums of ~x^2 n against each other: a 1e-16 relative difference of the
+        # sums (per-frame partial sums instead of one running sum) is ~1e-13 absolute at 50 m
+        np.testing.assert_allclose(vi["cov"][valid], vf["cov"][valid], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(vi["icov"][valid], vf["icov"][valid], rtol=1e-6, atol=1e-6 * np.abs(vf["icov"][valid]).max())
+        for x in (inc, full):
+            x.setInputSource(src)
+            x.align(guess)
+        assert (inc.result.iterations, inc.result.converged, inc.result.evaluations) == (full.result.iterations, full.result.converged, full.result.evaluations)
+        t_err, r_err = pose_error(full.getFinalTransformation(), inc.getFinalTransformation())
+        assert t_err < 1e-6 and r_err < 1e-6
+        assert inc.getFitnessScore() == pytest.approx(full.getFitnessScore(), rel=1e-12)  # the cloud is assembled on first use
+        if with_oracle:
+            o = oracle.NDT()
+            o.setResolution(1.0)
+            o.setTransformationEpsilon(0.01)
+            o.setMaximumIterations(64)
+            o.setInputTarget(cloud.cpu().numpy())
+            o.setInputSource(src)
+            vo = o.export_voxels()
+            assert np.array_equal(vi["idx"], vo["idx"]) and np.array_equal(vi["n"], vo["n"])
+            np.testing.assert_allclose(vi["mean"], vo["mean"], rtol=1e-9, atol=1e-12)
+            o.align(guess)
+            t_err, r_err = pose_error(o.final_transformation, inc.getFinalTransformation())
+            assert t_err < T_TOL_M and r_err < R_TOL_RAD and inc.result.iterations == o.nr_iterations
+
+    for step in range(n_kf - window + 1):
+        ids = list(range(step + window - 1, step - 1, -1))  # newest first, as LSM:199-212 walks the array
+        voxelised = inc.setInputTargetKeyFrames(kf, ids)
+        assert voxelised == (window if step == 0 else 1), (step, voxelised)
+        k = ids[0]
+        guess = d["poses"][k].copy()
+        guess[:3, 3] += np.array([0.2, -0.15, 0.02], np.float32)
+        check_same(ids, d["clouds"][k], guess, with_oracle=step in (0, 3))
+    # a pose-graph update moves one key frame of the window: only that frame is voxelised again
+    P = d["poses"][ids[3]].copy()
+    P[:3, 3] += np.array([0.07, -0.04, 0.01], np.float32)
+    kf.set_pose(ids[3], P)
+    assert inc.setInputTargetKeyFrames(kf, ids) == 1
+    check_same(ids, d["clouds"][ids[0]], guess)
+    # a coarser resolution invalidates every cached frame; the same list again costs nothing
+    for x in (inc, full):
+        x.setResolution(2.0)
+    assert inc.setInputTargetKeyFrames(kf, ids) in (0, window)   # setResolution already re-initialised the grid from the frames
+    assert inc.setInputTargetKeyFrames(kf, ids) == 0
+    check_same(ids, d["clouds"][ids[0]], guess)
+    # back to a plain cloud target
+    inc.setInputTarget(kf.assemble(ids[:2]))
+    full.setInputTarget(kf.assemble(ids[:2]))
+    assert np.array_equal(inc.export_voxels()["idx"], full.export_voxels()["idx"])
+
+
 def test_ndt_cfg0_synthetic_scan_to_map(api, oracle):
     """BASELINE configs[0]: 120 000-point 64-beam sweep against a 1 000 000-point local map, DIRECT7, 1.0 m."""
     from lidar_graph_slam_b200 import synth

@@ -169,6 +169,25 @@ def main():
         api.check(kf._L.lgs_keyframes_assemble(kf._h, idarr.ctypes.data_as(C.c_void_p), len(ids), float(leaf), C.byref(out_p), C.byref(out_n)))
     med, mn = timed(lambda: assemble(0.0))
     emit("sub-map assembly: 20 key frames x 50 000 points (transform + concatenate, device resident)", med, mn, 32 * 20 * 50000, n=20 * 50000)
+    # rolling map: a key-frame change as full rebuild (assemble + setInputTarget) and as incremental update
+    nd_full, nd_inc = api.NormalDistributionsTransform(ctx), api.NormalDistributionsTransform(ctx)
+    for x in (nd_full, nd_inc):
+        x.setResolution(1.0)
+    state = {"k": 0}
+
+    def window():
+        state["k"] = (state["k"] + 1) % 4
+        return np.asarray([23 - state["k"] - j for j in range(20)], np.int32)
+
+    def full_rebuild():
+        w = window()
+        api.check(kf._L.lgs_keyframes_assemble(kf._h, w.ctypes.data_as(C.c_void_p), len(w), 0.0, C.byref(out_p), C.byref(out_n)))
+        api.check(nd_full._L.lgs_ndt_set_target_dev(nd_full._h, out_p, out_n.value))
+    med, mn = timed(full_rebuild)
+    emit("rolling map, key-frame change: assemble 20 x 50 000 points + NDT target build (full rebuild)", med, mn, 32 * 20 * 50000 + 16 * 20 * 50000, n=20 * 50000)
+    med, mn = timed(lambda: nd_inc.setInputTargetKeyFrames(kf, window()))
+    emit("rolling map, key-frame change: lgs_ndt_set_target_keyframes (1 of 20 key frames voxelised, cached partial sums merged)", med, mn,
+         32 * 50000 + 16 * 50000 + 88 * int(nd_inc.grid_info().n_voxels) * 4, n=20 * 50000)
     med, mn = timed(lambda: assemble(0.5))
     emit("sub-map assembly + VoxelGrid 0.5 m (GBS:297-313)", med, mn, 32 * 20 * 50000 + (16 + 8) * 20 * 50000 + 16 * int(out_n.value), n=20 * 50000, voxels=int(out_n.value))
 
