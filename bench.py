@@ -221,7 +221,7 @@ def loop_closure_bench(rank, world, device, n_total, n_host_pairs):
         kf.push(c, P)
     comm = api.Comm.from_torch_distributed(device)
     # concurrent pairs per GPU, each a host thread on its own stream; never more than the host cores per rank
-    n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", max(1, min(4, host_threads() // max(world, 1))))
+    n_workers = _env_int("LGS_BENCH_LOOP_WORKERS", 8 if host_threads() // max(world, 1) >= 4 else 4)
     kw = dict(search_key_frame_num=20, method=api.METHOD_GICP, n_workers=n_workers)
     kf.batch_align_dist(comm, d["scan_ids"][:4 * n_workers * world], d["center_ids"][:4 * n_workers * world], **kw)  # warm-up: every worker's device state
 

@@ -236,6 +236,7 @@ void worker(BatchShared* S) {
   int rc = LGS_OK;
   const lgs_batch_params& bp = *S->bp;
   if (!w->ctx) rc = lgs_ctx_create(S->device, nullptr, &w->ctx);
+  if (rc == LGS_OK) w->ctx->polite_wait = true;
   if (rc == LGS_OK) rc = use_device(w->ctx);
   if (rc == LGS_OK) {
     if (bp.method == LGS_METHOD_GICP) {
@@ -370,7 +371,7 @@ static int run_batch(BatchShared& S) {
     set_error("no CUDA device available; this library has no CPU fallback");
     return LGS_ERR_CUDA;
   }
-  int W = params->n_workers > 0 ? params->n_workers : 4;
+  int W = params->n_workers > 0 ? params->n_workers : 8;  // measured on one B200: 2 276 / 2 726 / 2 609 pairs/s at 4 / 8 / 12 workers
   if (W > n_pairs) W = static_cast<int>(std::max<int64_t>(n_pairs, 1));
   if (W > 32) W = 32;
   std::vector<std::thread> threads;

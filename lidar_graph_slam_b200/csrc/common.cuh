@@ -144,6 +144,7 @@ struct lgs_ctx {
   lgs::DevBuf vg_in, vg_out, vg_vidx, vg_rank;  // host-facing voxel-grid call: staged cloud + device-side outputs
   lgs::MailboxHost* mbox = nullptr;             // result mailbox (mapped pinned host memory)
   unsigned long long mbox_token = 0;
+  bool polite_wait = false;  // batch workers: yield the core while waiting for a mailbox (several workers may share one)
   // One-shot record sink of the loop-closure batch (batch.cu, dist.cu): when set, the next getFitnessScore kernel on this
   // context - the last kernel of a candidate pair - completes rec_out_proto with the fitness it has just reduced and
   // stores the 96-byte record at rec_out_dev (a slot of the NCCL send buffer): no staging copy precedes the gather.

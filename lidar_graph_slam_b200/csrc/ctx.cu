@@ -2,6 +2,7 @@
 #include <atomic>
 
 #include <cstdlib>
+#include <sched.h>
 
 #include "persist.cuh"
 
@@ -121,6 +122,7 @@ int mailbox_wait(lgs_ctx* ctx, const Mailbox& mb, int k, double* out) {
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
+      if (ctx->polite_wait && (spins & 0x3fu) == 0x3fu) sched_yield();
       if ((++spins & 0x3fffu) == 0) {
         // a failed or finished-without-publishing launch must not hang the caller
         cudaError_t e = cudaStreamQuery(ctx->stream);

@@ -2,7 +2,7 @@
 """Development loop for the loop-closure batch (cfg 4 in miniature, run on the GPU box): wall time per pair against
 the number of host workers, and the per-stage split of one pair.
 
-    python tools/dev_batch.py [--pairs 8] [--workers 1,2,4,8]
+    python tools/dev/dev_batch.py [--pairs 8] [--workers 1,2,4,8]
 """
 import argparse
 import os
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

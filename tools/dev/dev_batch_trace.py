@@ -5,7 +5,7 @@ import os
 import sys
 
 os.environ["LGS_BATCH_TRACE"] = "1"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lidar_graph_slam_b200 import api, synth  # noqa: E402
 
