@@ -335,7 +335,8 @@ def gicp_odometry_bench(device, stream, ctx, n_sweeps):
             passes += g.result.evaluations + g.result.line_search_trials
             E = np.linalg.inv(np.linalg.inv(poses[k - 1]) @ poses[k]) @ T.astype(np.float64)
             worst = max(worst, float(np.linalg.norm(E[:3, 3])))
-            worst_rot = max(worst_rot, float(np.degrees(np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)))))
+            skew = 0.5 * np.sqrt((E[2, 1] - E[1, 2]) ** 2 + (E[0, 2] - E[2, 0]) ** 2 + (E[1, 0] - E[0, 1]) ** 2)
+            worst_rot = max(worst_rot, float(np.degrees(np.arctan2(skew, (np.trace(E[:3, :3]) - 1) / 2))))
             X = X @ T.astype(np.float64)
     ms = np.array(ms)
     D = np.linalg.inv(np.linalg.inv(poses[0]) @ poses[-1]) @ X

@@ -900,7 +900,7 @@ void fill_eval_constants(lgs_ndt* n) {
 
 int ensure_reduction_buffers(lgs_ndt* n, int grid) {
   cudaStream_t st = n->ctx->stream;
-  LGS_TRY(n->partials.reserve(static_cast<size_t>(std::max(grid, kNumSMs)) * kNumAcc * sizeof(double)));
+  LGS_TRY(n->partials.reserve(static_cast<size_t>(std::max(grid, kNumSMs)) * (kRow + 8) * sizeof(double)));  // rows + LGS_DERIV_TRACE words
   if (!n->result.p) {
     LGS_TRY(n->result.reserve(kNumAcc * sizeof(double) + 64));
     LGS_CUDA(cudaMemsetAsync(n->result.p, 0, kNumAcc * sizeof(double) + 64, st));
@@ -909,14 +909,14 @@ int ensure_reduction_buffers(lgs_ndt* n, int grid) {
 }
 
 // one computeDerivatives / computeHessian evaluation as one kernel launch, with the transform and the angular tables
-// already in n->P.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian.  sums: the kernel's packed result (29 / 8 /
+// already in n->P.  mode 0: score+g+H (f32 terms), 1: score+g, 2: f64 Hessian.  sums[kRow]: the kernel's packed result (44 / 8 /
 // 22 doubles, zeros when there is nothing to evaluate).
 int evaluate_launch(lgs_ndt* n, int mode, double* sums) {
   lgs_ctx* ctx = n->ctx;
   cudaStream_t st = ctx->stream;
   fill_eval_constants(n);
-  const int K = mode == 0 ? 29 : (mode == 1 ? 8 : 22);
-  std::fill(sums, sums + 32, 0.0);
+  const int K = mode == 0 ? kSumsHess : (mode == 1 ? kSumsGrad : kSumsF64);
+  std::fill(sums, sums + kRow, 0.0);
   if (mode == 2) n->hess_recomputes++; else n->evals++;
   if (n->n_source == 0 || n->refused || n->n_valid == 0) return LGS_OK;
   const DeviceCaps* caps = nullptr;
@@ -969,7 +969,7 @@ int evaluate_launch(lgs_ndt* n, int mode, double* sums) {
 int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* score, double* g, double* H) {
   memcpy(n->P.T, T, sizeof(float) * 16);
   if (p) angle_derivatives(p, &n->P);
-  double sums[32];
+  double sums[kRow];
   LGS_TRY(evaluate_launch(n, mode, sums));
   if (mode == 2) {
     for (int i = 0; i < 6; i++)
@@ -980,9 +980,9 @@ int evaluate(lgs_ndt* n, const float* T, const double p[6], int mode, double* sc
   if (g) memcpy(g, sums + 1, 6 * sizeof(double));
   if (H) {
     std::fill(H, H + 36, 0.0);
-    if (mode == 0)
+    if (mode == 0)  // all 36 entries, as the reference forms them (its two triangles differ in f32 rounding)
       for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = sums[7 + tri(i, j)];
+        for (int j = 0; j < 6; j++) H[i * 6 + j] = sums[hidx(i, j)];
   }
   return LGS_OK;
 }
@@ -1010,8 +1010,18 @@ int align_host_stepped(lgs_ndt* n, const double p0[6], const float T0[16], Align
   n->evals = n->hess_recomputes = 0;
   while (true) {
     command_to_params(c, &n->P);
-    double sums[32];
+    double sums[kRow];
     LGS_TRY(evaluate_launch(n, c.mode, sums));
+    static const bool eval_trace = getenv("LGS_NDT_EVAL_TRACE") != nullptr;  // tests/diag_ndt_eval_diff.py
+    if (eval_trace) {
+      fprintf(stderr, "EV mode %d P", c.mode);
+      for (int i = 0; i < 6; i++) fprintf(stderr, " %a", m.pending == 0 ? m.p[i] : m.x_t[i]);
+      fprintf(stderr, " T");
+      for (int i = 0; i < 12; i++) fprintf(stderr, " %a", static_cast<double>(n->P.T[i]));
+      fprintf(stderr, " | S");
+      for (int i = 0; i < 28; i++) fprintf(stderr, " %a", sums[i]);  // score, g, upper triangle
+      fprintf(stderr, "\n");
+    }
     if (!m.advance(sums, &c)) break;
   }
   memcpy(out->T, m.final_T, sizeof(out->T));

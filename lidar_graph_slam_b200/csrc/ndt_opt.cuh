@@ -12,6 +12,7 @@
 // All state is f64 and every expression keeps the reference's operation order (no FMA contraction: -fmad=false), so both
 // drivers walk the same path.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 
 #include "math.cuh"
@@ -307,70 +308,93 @@ LGS_HD double trial_value(double a_l, double f_l, double g_l, double a_u, double
 }
 
 // ---- Newton step ------------------------------------------------------------------------------------------------------
-// delta = -H^-1 g (NDT:127-129).  The reference goes through Eigen's two-sided JacobiSVD: ~80 dependent plane rotations,
-// each a chain of f64 divisions and square roots - 5 us on a CPU core, 30-40 us on a GPU thread, more than the derivative
-// evaluation it sits between; Gaussian elimination still chains six reciprocals (measured: 5.8k SM cycles).  The solution
-// only enters the align through p -> (f32 transform, f32 tables), so the machine solves the regular case by block
-// elimination on the symmetric H = [A B; B^T D] (A: translations, D: rotations): A^-1 and the inverse of the Schur
-// complement S = D - B^T A^-1 B in closed form (adjugate / determinant) - two reciprocals in the whole dependency chain.
-// It agrees with the SVD solution to ~cond * 1e-16 relative, orders below the f32 quantisation of the transform.  Whenever
-// a determinant is small against the products it is summed from (cancellation = ill-conditioning), or anything is not
-// finite, the machine falls back to the JacobiSVD with Eigen's rank threshold, whose minimum-norm semantics then matter.
-// Both drivers use this rule.  Ht: upper triangle of H, row by row (21 values); b: right-hand side; x: solution.
-LGS_HD int tri6(int i, int j) { return i <= j ? i * 6 - (i * (i - 1)) / 2 + (j - i) : j * 6 - (j * (j - 1)) / 2 + (i - j); }
+// delta = -H^-1 g (NDT:127-129).  H is the FULL 6x6 of the reference: its f32 terms are not symmetric - entry (i,j) is
+// e * ((-d2 * g_i) * g_j + ... + JCJ(j,i)), entry (j,i) rounds the same products in the other order (NDT:521-531) - so the
+// two triangles differ by ~1e-8 relative, and the JacobiSVD of the reference sees both.  (Mirroring one triangle moves the
+// Newton step by that much: enough to flip the f32 rounding of an entry of the next transform every few evaluations, after
+// which the two optimisers walk different paths.)
+// The reference goes through Eigen's two-sided JacobiSVD: ~80 dependent plane rotations, each a chain of f64 divisions and
+// square roots - 5 us on a CPU core, 30-40 us on a GPU thread, more than the derivative evaluation it sits between;
+// Gaussian elimination still chains six reciprocals (measured: 5.8k SM cycles).  The solution only enters the align
+// through p -> (f32 transform, f32 tables), so the machine solves the regular case by block elimination on
+// H = [A B; C D] (A: translations, D: rotations): A^-1 and the inverse of the Schur complement S = D - C A^-1 B in closed
+// form (adjugate / determinant) - two reciprocals in the whole dependency chain.  It agrees with the SVD solution to
+// ~cond * 1e-16 relative, orders below the f32 quantisation of the transform.  Whenever a determinant is small against the
+// products it is summed from (cancellation = ill-conditioning), or anything is not finite, the machine falls back to the
+// JacobiSVD with Eigen's rank threshold, whose minimum-norm semantics then matter.  Both drivers use this rule.
+// H: row-major 6x6; b: right-hand side; x: solution.
 
-// adjugate and determinant of a symmetric 3x3 (a00 a01 a02 a11 a12 a22); false when the determinant cancels
-LGS_HD bool sym3_adjugate(const double* a, double* adj, double* det) {
-  const double a00 = a[0], a01 = a[1], a02 = a[2], a11 = a[3], a12 = a[4], a22 = a[5];
-  adj[0] = a11 * a22 - a12 * a12;
-  adj[1] = a02 * a12 - a01 * a22;
-  adj[2] = a01 * a12 - a02 * a11;
-  adj[3] = a00 * a22 - a02 * a02;
-  adj[4] = a01 * a02 - a00 * a12;
-  adj[5] = a00 * a11 - a01 * a01;
-  const double t0 = a00 * adj[0], t1 = a01 * adj[1], t2 = a02 * adj[2];
+// adjugate (row-major) and determinant of a 3x3; false when the determinant cancels
+LGS_HD bool mat3_adjugate(const double* a, double* adj, double* det) {
+  adj[0] = a[4] * a[8] - a[5] * a[7];
+  adj[1] = a[2] * a[7] - a[1] * a[8];
+  adj[2] = a[1] * a[5] - a[2] * a[4];
+  adj[3] = a[5] * a[6] - a[3] * a[8];
+  adj[4] = a[0] * a[8] - a[2] * a[6];
+  adj[5] = a[2] * a[3] - a[0] * a[5];
+  adj[6] = a[3] * a[7] - a[4] * a[6];
+  adj[7] = a[1] * a[6] - a[0] * a[7];
+  adj[8] = a[0] * a[4] - a[1] * a[3];
+  const double t0 = a[0] * adj[0], t1 = a[1] * adj[3], t2 = a[2] * adj[6];
   *det = (t0 + t1) + t2;
   const double mag = (fabs(t0) + fabs(t1)) + fabs(t2);
   return fabs(*det) > 1e-10 * mag && mag < 1.7976931348623157e308;  // NaN fails the first comparison
 }
-LGS_HD void sym3_mul_vec(const double* m, const double* v, double* out) {  // m packed as above
+LGS_HD void mat3_mul_vec(const double* m, const double* v, double* out) {
   out[0] = (m[0] * v[0] + m[1] * v[1]) + m[2] * v[2];
-  out[1] = (m[1] * v[0] + m[3] * v[1]) + m[4] * v[2];
-  out[2] = (m[2] * v[0] + m[4] * v[1]) + m[5] * v[2];
+  out[1] = (m[3] * v[0] + m[4] * v[1]) + m[5] * v[2];
+  out[2] = (m[6] * v[0] + m[7] * v[1]) + m[8] * v[2];
 }
-LGS_HD bool schur_solve6(const double* Ht, const double* b, double* x) {
-  const double A[6] = {Ht[tri6(0, 0)], Ht[tri6(0, 1)], Ht[tri6(0, 2)], Ht[tri6(1, 1)], Ht[tri6(1, 2)], Ht[tri6(2, 2)]};
-  double adjA[6], detA;
-  if (!sym3_adjugate(A, adjA, &detA)) return false;
+struct Schur6 {
+  double Ai[9], W[3][3], Si[9];  // A^-1, A^-1 B, S^-1
+};
+LGS_HD bool schur_factor6(const double* H, Schur6* f) {
+  const double A[9] = {H[0], H[1], H[2], H[6], H[7], H[8], H[12], H[13], H[14]};
+  double adjA[9], detA;
+  if (!mat3_adjugate(A, adjA, &detA)) return false;
   const double rA = 1.0 / detA;
-  double Ai[6];
-  for (int k = 0; k < 6; k++) Ai[k] = adjA[k] * rA;
-  // W = A^-1 B (3x3, column c of B = H[0..2][3 + c]); u = A^-1 b1
-  double W[3][3], u[3];
-  for (int c = 0; c < 3; c++) {
-    const double col[3] = {Ht[tri6(0, 3 + c)], Ht[tri6(1, 3 + c)], Ht[tri6(2, 3 + c)]};
+  for (int k = 0; k < 9; k++) f->Ai[k] = adjA[k] * rA;
+  for (int c = 0; c < 3; c++) {  // column c of B = H[0..2][3 + c]
+    const double col[3] = {H[3 + c], H[6 + 3 + c], H[12 + 3 + c]};
     double w[3];
-    sym3_mul_vec(Ai, col, w);
-    W[0][c] = w[0];
-    W[1][c] = w[1];
-    W[2][c] = w[2];
+    mat3_mul_vec(f->Ai, col, w);
+    f->W[0][c] = w[0];
+    f->W[1][c] = w[1];
+    f->W[2][c] = w[2];
   }
-  sym3_mul_vec(Ai, b, u);
-  // S = D - B^T W (symmetric: the upper triangle is formed), r = b2 - B^T u
-  double S[6], r[3];
-  int k = 0;
+  double S[9];  // D - C W   (C = H[3..5][0..2])
   for (int i = 0; i < 3; i++) {
-    const double bi[3] = {Ht[tri6(0, 3 + i)], Ht[tri6(1, 3 + i)], Ht[tri6(2, 3 + i)]};  // column i of B = row i of B^T
-    for (int j = i; j < 3; j++) S[k++] = Ht[tri6(3 + i, 3 + j)] - ((bi[0] * W[0][j] + bi[1] * W[1][j]) + bi[2] * W[2][j]);
-    r[i] = b[3 + i] - ((bi[0] * u[0] + bi[1] * u[1]) + bi[2] * u[2]);
+    const double* ci = H + (3 + i) * 6;
+    for (int j = 0; j < 3; j++) S[i * 3 + j] = ci[3 + j] - ((ci[0] * f->W[0][j] + ci[1] * f->W[1][j]) + ci[2] * f->W[2][j]);
   }
-  double adjS[6], detS;
-  if (!sym3_adjugate(S, adjS, &detS)) return false;
+  double adjS[9], detS;
+  if (!mat3_adjugate(S, adjS, &detS)) return false;
   const double rS = 1.0 / detS;
-  double y[3];
-  sym3_mul_vec(adjS, r, y);
-  for (int i = 0; i < 3; i++) x[3 + i] = y[i] * rS;
-  for (int i = 0; i < 3; i++) x[i] = u[i] - ((W[i][0] * x[3] + W[i][1] * x[4]) + W[i][2] * x[5]);
+  for (int k = 0; k < 9; k++) f->Si[k] = adjS[k] * rS;
+  return true;
+}
+LGS_HD void schur_apply6(const double* H, const Schur6& f, const double* b, double* x) {
+  double u[3], r[3];
+  mat3_mul_vec(f.Ai, b, u);
+  for (int i = 0; i < 3; i++) {
+    const double* ci = H + (3 + i) * 6;
+    r[i] = b[3 + i] - ((ci[0] * u[0] + ci[1] * u[1]) + ci[2] * u[2]);
+  }
+  mat3_mul_vec(f.Si, r, x + 3);
+  for (int i = 0; i < 3; i++) x[i] = u[i] - ((f.W[i][0] * x[3] + f.W[i][1] * x[4]) + f.W[i][2] * x[5]);
+}
+// Elimination without pivoting loses the digits the determinants cancel (at most ten under mat3_adjugate's rule): one step of iterative refinement on the f64 residual brings the solution back to ~cond * 1e-16.
+LGS_HD bool schur_solve6(const double* H, const double* b, double* x) {
+  Schur6 f;
+  if (!schur_factor6(H, &f)) return false;
+  schur_apply6(H, f, b, x);
+  double res[6], dx[6];
+  for (int i = 0; i < 6; i++) {
+    const double* h = H + i * 6;
+    res[i] = b[i] - (((h[0] * x[0] + h[1] * x[1]) + (h[2] * x[2] + h[3] * x[3])) + (h[4] * x[4] + h[5] * x[5]));
+  }
+  schur_apply6(H, f, res, dx);
+  for (int i = 0; i < 6; i++) x[i] += dx[i];
   for (int i = 0; i < 6; i++)
     if (!(fabs(x[i]) < 1.7976931348623157e308)) return false;
   return true;
@@ -382,12 +406,13 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-void svd_fallback(const double* Ht, const double* b, double* x) {
-  double H[36];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < 6; j++) H[i * 6 + j] = Ht[tri6(i, j)];
+void svd_fallback(const double* H, const double* b, double* x) {
   m::svd_solve<6>(H, b, x);
 }
+
+// where the evaluation kernels leave entry (i,j) of the Hessian in their row of sums (mode 0): the upper triangle row by
+// row from 7, the strict lower triangle row by row from 28
+LGS_HD int hess_sum_index(int i, int j) { return i <= j ? 7 + i * 6 - (i * (i - 1)) / 2 + (j - i) : 28 + (i * (i - 1)) / 2 + j; }
 
 // ---- the machine ------------------------------------------------------------------------------------------------------
 struct Command {       // the evaluation to run next
@@ -406,7 +431,7 @@ struct Machine {
   double step_size, trans_eps, n_in;
   int max_iter;
   // optimiser state (NDT:103-171)
-  double p[6], score, g[6], Ht[21];  // Ht: upper triangle of H, row by row
+  double p[6], score, g[6], H[36];  // H: row-major, both triangles (see "Newton step")
   int nr_iterations, converged, early_exit;
   double trans_probability;
   int evals, trials, hess_recomputes;
@@ -434,7 +459,7 @@ struct Machine {
     for (int i = 0; i < 16; i++) final_T[i] = T0[i];
     score = 0;
     for (int i = 0; i < 6; i++) g[i] = 0;
-    for (int i = 0; i < 21; i++) Ht[i] = 0;
+    for (int i = 0; i < 36; i++) H[i] = 0;
     nr_iterations = converged = early_exit = 0;
     trans_probability = 0;
     evals = 1;
@@ -448,24 +473,35 @@ struct Machine {
   }
 
   LGS_HD void take_sums(const double* s, int mode) {
-    // mode 0: score, g[6], upper triangle of H (21); mode 1: score, g[6]; mode 2: upper triangle of H.  (The reference
+    // mode 0: score, g[6], upper triangle of H (21), strict lower triangle (15); mode 1: score, g[6]; mode 2: upper
+    // triangle of the f64 Hessian (computeHessian's two triangles differ by f64 rounding only: mirrored).  (The reference
     // zeroes H in a gradient-only evaluation, NDT:201; computeHessian always overwrites it before its next use, NDT:927.)
     if (mode == 2) {
-      for (int k = 0; k < 21; k++) Ht[k] = s[k];
+      int k = 0;
+      for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) H[i * 6 + j] = H[j * 6 + i] = s[k++];
       return;
     }
     score = s[0];
     for (int i = 0; i < 6; i++) g[i] = s[1 + i];
     if (mode == 0)
-      for (int k = 0; k < 21; k++) Ht[k] = s[7 + k];
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) H[i * 6 + j] = s[hess_sum_index(i, j)];
   }
 
   // NDT:127-129
   LGS_HD void solve() {
     double neg_g[6];
     for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
-    if (schur_solve6(Ht, neg_g, delta_p)) return;
-    svd_fallback(Ht, neg_g, delta_p);
+#if !defined(__CUDA_ARCH__)
+    static const bool force_svd = getenv("LGS_NDT_FORCE_SVD") != nullptr;  // development aid (host-stepped driver only)
+    if (force_svd) {
+      svd_fallback(H, neg_g, delta_p);
+      return;
+    }
+#endif
+    if (schur_solve6(H, neg_g, delta_p)) return;
+    svd_fallback(H, neg_g, delta_p);
   }
   LGS_HD int request_pose(int mode) {
     for (int i = 0; i < 6; i++) x_t[i] = p[i] + dir[i] * a_t;

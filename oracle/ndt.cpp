@@ -1,6 +1,8 @@
 // ORACLE (test infrastructure).  pclomp::NormalDistributionsTransform restated from NDT / NDT.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #ifdef _OPENMP
 #include <omp.h>
@@ -269,6 +271,19 @@ double NDT::computeDerivatives(double g[6], double H[36], const std::vector<P4>&
     score += scores[i];
     for (int k = 0; k < 6; k++) g[k] += grads[i * 6 + k];
     for (int k = 0; k < 36; k++) H[k] += hess[i * 36 + k];
+  }
+  static const bool eval_trace = getenv("LGS_NDT_EVAL_TRACE") != nullptr;  // tests/diag_ndt_eval_diff.py: pose, transform, sums
+  if (eval_trace) {
+    fprintf(stderr, "EV mode %d P", compute_hessian ? 0 : 1);
+    for (int i = 0; i < 6; i++) fprintf(stderr, " %a", p[i]);
+    fprintf(stderr, " T");
+    for (int i = 0; i < 12; i++) fprintf(stderr, " %a", static_cast<double>(final_transformation[i]));
+    fprintf(stderr, " | S %a", score);
+    for (int k = 0; k < 6; k++) fprintf(stderr, " %a", g[k]);
+    if (compute_hessian)
+      for (int r = 0; r < 6; r++)
+        for (int c = r; c < 6; c++) fprintf(stderr, " %a", H[r * 6 + c]);
+    fprintf(stderr, "\n");
   }
   return score;
 }

@@ -36,5 +36,9 @@ def api():
 
 
 def pose_error(T_ref, T):
+    """Translation (m) and rotation (rad) between two poses.  The angle comes from the skew part of the relative rotation
+    (atan2 of sine and cosine): acos of the trace alone cannot resolve less than sqrt(2 ulp) = 3.4e-4 rad of an f32 matrix."""
     d = np.linalg.inv(np.asarray(T_ref, np.float64)) @ np.asarray(T, np.float64)
-    return float(np.linalg.norm(d[:3, 3])), float(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1)))
+    R = d[:3, :3]
+    sin_a = 0.5 * np.sqrt((R[2, 1] - R[1, 2]) ** 2 + (R[0, 2] - R[2, 0]) ** 2 + (R[1, 0] - R[0, 1]) ** 2)
+    return float(np.linalg.norm(d[:3, 3])), float(np.arctan2(sin_a, (np.trace(R) - 1) / 2))

@@ -18,7 +18,7 @@ using namespace lgs::ndtopt;
 int main() {
   std::mt19937_64 rng(12345);
   std::uniform_real_distribution<double> ang(-3.2, 3.2), small(-2e-4, 2e-4), u(-1.0, 1.0);
-  long failures = 0, refused = 0;
+  long failures = 0, refused = 0, loose = 0;
   for (int it = 0; it < 20000; it++) {
     double x[6] = {u(rng) * 50, u(rng) * 50, u(rng) * 5, ang(rng), ang(rng), ang(rng)};
     if (it % 3 == 0) x[3 + it % 3] = small(rng);
@@ -51,10 +51,11 @@ int main() {
       failures++;
     }
   }
-  // block elimination vs JacobiSVD on symmetric systems conditioned like an NDT Hessian (rotations ~1e3 times stiffer),
-  // positive and negative definite and indefinite
+  // block elimination vs JacobiSVD on systems conditioned like an NDT Hessian (rotations ~1e3 times stiffer), positive and
+  // negative definite and indefinite, symmetric up to the f32 rounding of the reference's terms (the two triangles of its
+  // Hessian differ by ~1e-8 relative)
   for (int it = 0; it < 3000; it++) {
-    double A[36], H[36], Ht[21], g[6];
+    double A[36], H[36], g[6];
     for (double& v : A) v = u(rng);
     for (int i = 0; i < 6; i++)
       for (int j = 0; j < 6; j++) {
@@ -64,12 +65,12 @@ int main() {
       }
     for (int i = 0; i < 6; i++) H[i * 6 + i] += (it % 3 == 1 ? -0.05 : 0.05);
     for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) Ht[tri6(i, j)] = H[i * 6 + j];
+      for (int j = 0; j < i; j++) H[i * 6 + j] *= 1.0 + 3e-8 * u(rng);
     for (double& v : g) v = u(rng) * 100;
     double neg_g[6], xs[6], xb[6];
     for (int i = 0; i < 6; i++) neg_g[i] = -g[i];
     lgs::m::svd_solve<6>(H, neg_g, xs);
-    if (!schur_solve6(Ht, neg_g, xb)) {
+    if (!schur_solve6(H, neg_g, xb)) {
       refused++;
       continue;
     }
@@ -78,24 +79,45 @@ int main() {
       nrm += xs[i] * xs[i];
       err += (xs[i] - xb[i]) * (xs[i] - xb[i]);
     }
-    if (!(std::sqrt(err) <= 1e-8 * std::sqrt(nrm))) {
-      if (failures < 5) printf("system %d: relative difference %.3e\n", it, std::sqrt(err / nrm));
+    // both solutions carry ~cond * 1e-16 of error: the bar is on the residual of the elimination, and on the difference
+    // wherever the SVD's own residual says the system is well conditioned
+    auto residual = [&](const double* x) {
+      double r2 = 0, h2 = 0, x2 = 0;
+      for (int i = 0; i < 6; i++) {
+        double r = -neg_g[i];
+        for (int j = 0; j < 6; j++) r += H[i * 6 + j] * x[j], h2 += H[i * 6 + j] * H[i * 6 + j];
+        r2 += r * r;
+        x2 += x[i] * x[i];
+      }
+      return std::sqrt(r2) / (std::sqrt(h2) * std::sqrt(x2));
+    };
+    if (!(residual(xb) <= 1e-15) || !(std::sqrt(err) <= 1e-9 * std::sqrt(nrm))) {
+      if (failures < 5) printf("system %d: relative difference %.3e, residuals %.3e (elimination) %.3e (SVD)\n", it, std::sqrt(err / nrm), residual(xb), residual(xs));
       failures++;
     }
+    if (std::sqrt(err) > 1e-11 * std::sqrt(nrm)) loose++;
   }
+  if (loose > 5) failures++, printf("%ld of 3000 solutions further than 1e-11 from the SVD's\n", loose);
   if (refused > 300) failures++, printf("block elimination refused %ld of 3000 regular systems\n", refused);
   {  // singular and non-finite systems are handed to the SVD
-    double Ht[21] = {0}, b[6] = {1, 2, 3, 4, 5, 6}, x[6];
-    if (schur_solve6(Ht, b, x)) failures++, printf("zero system accepted\n");
+    double H[36] = {0}, b[6] = {1, 2, 3, 4, 5, 6}, x[6];
+    if (schur_solve6(H, b, x)) failures++, printf("zero system accepted\n");
     for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) Ht[tri6(i, j)] = (i + 1.0) * (j + 1.0);  // rank 1
-    if (schur_solve6(Ht, b, x)) failures++, printf("rank-1 system accepted\n");
+      for (int j = 0; j < 6; j++) H[i * 6 + j] = (i + 1.0) * (j + 1.0);  // rank 1
+    if (schur_solve6(H, b, x)) failures++, printf("rank-1 system accepted\n");
     for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) Ht[tri6(i, j)] = (i == j) ? 2.0 : 0.1;
-    Ht[tri6(4, 5)] = NAN;
-    if (schur_solve6(Ht, b, x)) failures++, printf("NaN system accepted\n");
-    Ht[tri6(4, 5)] = 0.1;
-    if (!schur_solve6(Ht, b, x)) failures++, printf("regular system refused\n");
+      for (int j = 0; j < 6; j++) H[i * 6 + j] = (i == j) ? 2.0 : 0.1;
+    H[4 * 6 + 5] = NAN;
+    if (schur_solve6(H, b, x)) failures++, printf("NaN system accepted\n");
+    H[4 * 6 + 5] = 0.1;
+    if (!schur_solve6(H, b, x)) failures++, printf("regular system refused\n");
+    // a visibly non-symmetric system: the solution is that of the full matrix, not of a mirrored triangle
+    H[3 * 6 + 1] = 0.7;
+    double xs[6];
+    lgs::m::svd_solve<6>(H, b, xs);
+    if (!schur_solve6(H, b, x)) failures++, printf("non-symmetric system refused\n");
+    for (int i = 0; i < 6; i++)
+      if (!(std::fabs(x[i] - xs[i]) <= 1e-12 * (1.0 + std::fabs(xs[i])))) failures++, printf("non-symmetric system: x[%d] %.17g vs %.17g\n", i, x[i], xs[i]);
   }
   printf("%ld failures\n", failures);
   return failures ? 1 : 0;

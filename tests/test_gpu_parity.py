@@ -4,11 +4,12 @@ Bars (BASELINE.json north_star / SURVEY.md section 8d): voxel indices, occupancy
 bit-exact; voxel mean / inverse covariance rel 1e-9; final transforms within 1e-4 m / 1e-4 rad; fitness and
 transformation probability within 1e-5 relative; identical iteration counts and convergence flags."""
 import os
+import json
 
 import numpy as np
 import pytest
 
-from conftest import pose_error
+from conftest import ROOT, pose_error
 
 pytestmark = pytest.mark.gpu
 
@@ -160,11 +161,10 @@ def test_ndt_velodyne_voxels_and_derivatives(api, oracle, velodyne_pair):
                     np.testing.assert_allclose(Hg, Ho, rtol=1e-9, atol=1e-11 * scale)
                     assert np.array_equal(Hg, Hg.T)
                 if mode == 0:
-                    # the kernel forms the upper triangle exactly as the reference does and mirrors it; the reference's
-                    # own (j,i) entry differs from its (i,j) entry by f32 rounding of the terms only
-                    np.testing.assert_allclose(np.triu(Hg), np.triu(Ho), rtol=1e-9, atol=1e-11 * scale)
-                    np.testing.assert_allclose(Hg, Ho, rtol=1e-6, atol=1e-7 * scale)
-                    assert np.array_equal(Hg, Hg.T)
+                    # all 36 entries exactly as the reference forms them: its (j,i) entry is NOT its (i,j) entry (the f32
+                    # products of a term round in the other order, NDT:521-531), and the Newton step sees both triangles
+                    np.testing.assert_allclose(Hg, Ho, rtol=1e-12, atol=1e-13 * scale)
+                    assert not np.array_equal(Ho, Ho.T) and np.array_equal(Hg == Hg.T, Ho == Ho.T)
 
 
 def test_ndt_velodyne_align_parity(api, oracle, velodyne_pair):
@@ -275,6 +275,82 @@ def test_ndt_device_resident_align_equals_host_stepped(api, velodyne_pair, oracl
             assert ra.trans_probability == pytest.approx(rb.trans_probability, rel=1e-9)
         b.profile(0)
     assert all(l == 1 for l in launches), launches  # one kernel launch per align
+
+
+def test_ndt_parity_over_many_random_guesses(api, oracle, velodyne_pair):
+    """How robust is "same iteration count"?  48 seeded random guesses (up to 0.6 m / 4 deg off the ground truth, every eighth
+    four times as far) on the bundled pair at two resolutions: for EVERY one the device-resident align takes the oracle's
+    iterations, derivative evaluations, line-search trials and computeHessian calls, and ends on the oracle's transform to
+    1e-6 m / 1e-6 rad (in practice the same 16 floats).  The Newton step is a block elimination on the device and a JacobiSVD
+    in the oracle, the sines and cosines come from a restatement of the C library's, the sums are added in another order:
+    none of these matters.  What does: this test found that the reference's f32-term Hessian is not symmetric (its (i,j) and
+    (j,i) entries round their products in different orders, ~1e-8 apart) and that a solver fed one mirrored triangle leaves
+    the reference's path on a quarter of these guesses (3 with other iteration counts, 9 more ending up to 2 mm away).  The
+    evaluation kernels form all 36 entries since."""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    rel = velodyne_pair["relative"].astype(np.float64)
+    rng = np.random.default_rng(20261018)
+    rows = []
+    for res in (1.0, 2.0):
+        g, o = _ndt_pair(api, oracle, td, sd, res=res, eps=0.01, it=64)
+        for k in range(24):
+            scale = 4.0 if k % 8 == 7 else 1.0  # every eighth guess is far off
+            d = np.eye(4)
+            ang = rng.uniform(-1, 1, 3) * np.radians([1.0, 1.0, 4.0]) * scale
+            cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+            Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+            Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+            Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+            d[:3, :3] = Rx @ Ry @ Rz
+            d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([0.6, 0.6, 0.1]) * scale
+            guess = (d @ rel).astype(np.float32)
+            g.align(guess)
+            o.align(guess)
+            r = g.result
+            t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+            same = (r.iterations, bool(r.converged), r.evaluations, r.line_search_trials, r.hessian_recomputes) == \
+                (o.nr_iterations, o.converged, o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"])
+            fit = abs(g.getTransformationProbability() - o.trans_probability) / abs(o.trans_probability)
+            rows.append(dict(res=res, k=k, same=same, it=(r.iterations, o.nr_iterations), conv=(bool(r.converged), bool(o.converged)),
+                             t_err=float(t_err), r_err=float(r_err), fit=float(fit)))
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "ndt_random_guesses.json"), "w") as f:
+            json.dump(rows, f, indent=1)
+    assert len(rows) == 48
+    for x in rows:
+        assert x["same"] and x["t_err"] < 1e-6 and x["r_err"] < 1e-6 and x["fit"] < 1e-9, x
+    assert len({x["it"][0] for x in rows}) > 10  # the guesses do exercise different paths (2 to 39 iterations)
+
+
+def test_gicp_parity_over_many_random_guesses(api, oracle, velodyne_pair):
+    """The same for FastGICP (target three times the source, so the lazy target covariances are exercised): 24 random guesses,
+    identical nr_iterations / linearisations / error evaluations, poses within 1e-4, fitness within 1e-5."""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.1)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.3)["points"]
+    assert len(td) > 2 * len(sd)
+    rel = velodyne_pair["relative"].astype(np.float64)
+    rng = np.random.default_rng(4242)
+    g, o = api.FastGICP(), oracle.FastGICP()
+    for x in (g, o):
+        x.setMaxCorrespondenceDistance(2.0)
+        x.setMaximumIterations(100)
+        x.setTransformationEpsilon(0.01)
+        x.setInputTarget(td)
+        x.setInputSource(sd)
+    for k in range(24):
+        d = np.eye(4)
+        yaw = rng.uniform(-1, 1) * np.radians(5.0)
+        d[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+        d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([1.0, 1.0, 0.1])
+        guess = (d @ rel).astype(np.float32)
+        g.align(guess)
+        o.align(guess)
+        assert (g.result.iterations, bool(g.result.converged), g.result.evaluations, g.result.line_search_trials) == \
+            (o.nr_iterations, o.converged, o.stats["linearize_calls"], o.stats["error_calls"]), k
+        t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+        assert t_err < T_TOL_M and r_err < R_TOL_RAD, (k, t_err, r_err)
+        assert g.getFitnessScore() == pytest.approx(o.getFitnessScore(), rel=FIT_RTOL)
 
 
 def test_ndt_rolling_map_incremental_target(api, oracle):
