@@ -839,6 +839,57 @@ def _gicp_omp_pair(api, oracle, target, source, **kw):
     return g, o
 
 
+def _random_guesses(rel, seed, count, yaw_deg=4.0, xy=0.6):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        d = np.eye(4)
+        yaw = rng.uniform(-1, 1) * np.radians(yaw_deg)
+        d[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+        d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([xy, xy, 0.1])
+        out.append((d @ rel.astype(np.float64)).astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize("method", [1, 3])  # DIRECT26, DIRECT1 (DIRECT7 has its own test; KDTREE is refused)
+def test_ndt_search_methods_over_random_guesses(api, oracle, velodyne_pair, method):
+    """The other neighbourhood searches of pclomp NDT (ndt_omp.h:52-57) over 12 random guesses each: identical counts, the
+    oracle's transform.  (DIRECT26: 27 cells; DIRECT1: the point's own cell.)"""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.3)["points"]
+    g, o = _ndt_pair(api, oracle, td, sd, res=1.0, eps=0.01, it=40, method=method)
+    for k, guess in enumerate(_random_guesses(velodyne_pair["relative"], 77 + method, 12)):
+        g.align(guess)
+        o.align(guess)
+        r = g.result
+        assert (r.iterations, bool(r.converged), r.evaluations, r.line_search_trials, r.hessian_recomputes) == \
+            (o.nr_iterations, o.converged, o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"]), (method, k)
+        t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+        assert t_err < 1e-6 and r_err < 1e-6, (method, k, t_err, r_err)
+        assert g.getTransformationProbability() == pytest.approx(o.trans_probability, rel=1e-9)
+
+
+def test_gicp_omp_parity_over_random_guesses(api, oracle, velodyne_pair):
+    """pclomp GICP (BFGS) over 12 random guesses: identical outer iterations, functor / gradient evaluation counts and inner
+    iterations (the exact fixed-point sums make every evaluation bit-identical), poses within 1e-4."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.25)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.25)["points"]
+    g, o = _gicp_omp_pair(api, oracle, t2, s2, max_corr=2.0, eps=0.01, max_iter=30, max_inner=10)
+    for guess in _random_guesses(velodyne_pair["relative"], 99, 12):
+        _compare_gicp_omp_align(g, o, guess)
+
+
+def test_icp_parity_over_random_guesses(api, oracle, velodyne_pair):
+    """pcl::IterativeClosestPoint with the loop-closure parameters (GBS:145-149) over 12 random guesses on the same pair of
+    objects (PCL's convergence criteria carry state from align to align, reproduced): identical iteration counts and
+    convergence states, poses within 1e-4."""
+    t2 = oracle.voxel_grid(velodyne_pair["target"], 0.25)["points"]
+    s2 = oracle.voxel_grid(velodyne_pair["source"], 0.25)["points"]
+    g, o = _icp_pair(api, oracle, t2, s2)
+    for guess in _random_guesses(velodyne_pair["relative"], 123, 12):
+        _compare_icp_align(g, o, guess)
+
+
 def test_gicp_omp_covariances_and_functor(api, oracle, velodyne_pair):
     """pclomp::GeneralizedIterativeClosestPoint pieces: computeCovariances (GO:48-122), the correspondence / Mahalanobis
     set-up of one outer iteration (GO:404-474) and the three BFGS functor evaluations (GO:245-367)."""
