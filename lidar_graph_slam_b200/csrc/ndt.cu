@@ -1019,7 +1019,7 @@ int align_host_stepped(lgs_ndt* n, const double p0[6], const float T0[16], Align
       fprintf(stderr, " T");
       for (int i = 0; i < 12; i++) fprintf(stderr, " %a", static_cast<double>(n->P.T[i]));
       fprintf(stderr, " | S");
-      for (int i = 0; i < 28; i++) fprintf(stderr, " %a", sums[i]);  // score, g, upper triangle
+      for (int i = 0; i < (c.mode == 0 ? 43 : 28); i++) fprintf(stderr, " %a", sums[i]);  // score, g, upper triangle, strict lower triangle
       fprintf(stderr, "\n");
     }
     if (!m.advance(sums, &c)) break;

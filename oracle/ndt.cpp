@@ -280,9 +280,12 @@ double NDT::computeDerivatives(double g[6], double H[36], const std::vector<P4>&
     for (int i = 0; i < 12; i++) fprintf(stderr, " %a", static_cast<double>(final_transformation[i]));
     fprintf(stderr, " | S %a", score);
     for (int k = 0; k < 6; k++) fprintf(stderr, " %a", g[k]);
-    if (compute_hessian)
+    if (compute_hessian) {
       for (int r = 0; r < 6; r++)
         for (int c = r; c < 6; c++) fprintf(stderr, " %a", H[r * 6 + c]);
+      for (int r = 1; r < 6; r++)
+        for (int c = 0; c < r; c++) fprintf(stderr, " %a", H[r * 6 + c]);
+    }
     fprintf(stderr, "\n");
   }
   return score;

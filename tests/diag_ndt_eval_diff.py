@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Development aid (GPU box): first evaluation at which the host-stepped NDT align and the oracle part ways for one random guess.
 Both sides print every evaluation (transform, sums) as hex floats when LGS_NDT_EVAL_TRACE is set; this script runs them one after
-the other with stderr redirected and compares the lines.   usage: diag_ndt_eval_diff.py RES GUESS_INDEX"""
+the other with stderr redirected and compares the lines.\n   usage: diag_ndt_eval_diff.py RES GUESS_INDEX (a guess of test_ndt_parity_over_many_random_guesses) | --case FILE.npz (saved by diag_fuzz.py)"""
 import os
 import sys
 
@@ -13,27 +13,34 @@ os.environ["LGS_NDT_EVAL_TRACE"] = "1"
 from lidar_graph_slam_b200 import api  # noqa: E402
 from oracle import pyoracle as O  # noqa: E402
 
-want_res, want_k = float(sys.argv[1]), int(sys.argv[2])
-z = np.load(os.path.join(ROOT, "tests", "golden", "velodyne_pair.npz"))
-td, sd = O.voxel_grid(z["target"], 0.2)["points"], O.voxel_grid(z["source"], 0.2)["points"]
-rel = z["relative"].astype(np.float64)
-rng = np.random.default_rng(20261018)
-guess = None
-for res in (1.0, 2.0):
-    for k in range(24):
-        scale = 4.0 if k % 8 == 7 else 1.0
-        d = np.eye(4)
-        ang = rng.uniform(-1, 1, 3) * np.radians([1.0, 1.0, 4.0]) * scale
-        cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
-        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]); Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
-        d[:3, :3] = Rx @ Ry @ Rz
-        d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([0.6, 0.6, 0.1]) * scale
-        if (res, k) == (want_res, want_k):
-            guess = (d @ rel).astype(np.float32)
+if sys.argv[1] == "--case":  # a case saved by tests/diag_fuzz.py
+    z = np.load(sys.argv[2])
+    td, sd, guess = z["target"], z["source"], z["guess"]
+    want_res, eps, it, step, method = float(z["res"]), float(z["eps"]), int(z["it"]), float(z["step"]), int(z["method"])
+else:
+    want_res, want_k = float(sys.argv[1]), int(sys.argv[2])
+    eps, it, step, method = 0.01, 64, 0.1, 2
+    z = np.load(os.path.join(ROOT, "tests", "golden", "velodyne_pair.npz"))
+    td, sd = O.voxel_grid(z["target"], 0.2)["points"], O.voxel_grid(z["source"], 0.2)["points"]
+    rel = z["relative"].astype(np.float64)
+    rng = np.random.default_rng(20261018)
+    guess = None
+    for res in (1.0, 2.0):
+        for k in range(24):
+            scale = 4.0 if k % 8 == 7 else 1.0
+            d = np.eye(4)
+            ang = rng.uniform(-1, 1, 3) * np.radians([1.0, 1.0, 4.0]) * scale
+            cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+            Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]); Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+            d[:3, :3] = Rx @ Ry @ Rz
+            d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([0.6, 0.6, 0.1]) * scale
+            if (res, k) == (want_res, want_k):
+                guess = (d @ rel).astype(np.float32)
 objs = []
 for kind in ("stepped", "oracle"):
     n = O.NDT() if kind == "oracle" else api.NormalDistributionsTransform()
-    n.setResolution(want_res); n.setTransformationEpsilon(0.01); n.setMaximumIterations(64); n.setStepSize(0.1)
+    n.setResolution(want_res); n.setTransformationEpsilon(eps); n.setMaximumIterations(it); n.setStepSize(step)
+    n.setNeighborhoodSearchMethod(method)
     n.setInputTarget(td); n.setInputSource(sd)
     if kind == "stepped":
         n.profile(1)
@@ -63,7 +70,7 @@ A = [a for a in A if a[2] != "2"]
 for i, (a, b) in enumerate(zip(A, B)):
     Pa, Pb = a[4:10], b[4:10]
     Ta, Tb = a[11:23], b[11:23]
-    ns = 7 if a[2] == "1" else 28
+    ns = 7 if a[2] == "1" else 43
     Sa, Sb = [float.fromhex(v) for v in a[25:25 + ns]], [float.fromhex(v) for v in b[25:25 + ns]]
     same_T = Ta == Tb
     print("   pose", " ".join("%.3e" % (float.fromhex(x) - float.fromhex(y)) for x, y in zip(Pa, Pb)))
@@ -73,4 +80,9 @@ for i, (a, b) in enumerate(zip(A, B)):
         for x, y in zip(Ta, Tb):
             if x != y:
                 print("    T entry", x, y, float.fromhex(x) - float.fromhex(y))
+        break
+    if rel > 1e-9:
+        for k, (x, y) in enumerate(zip(Sa, Sb)):
+            if abs(x - y) > 1e-9 * max(abs(y), 1e-300):
+                print("    sum %d: %.17g vs %.17g" % (k, x, y))
         break
