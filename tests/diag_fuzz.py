@@ -92,15 +92,15 @@ def fuzz_voxelgrid(case):
         return report(case, tag, "centroids differ in %d entries, max %g" % ((out != ref["points"]).sum(), np.abs(out - ref["points"]).max()))
 
 
-def fuzz_ndt(case):
+def fuzz_ndt(case, large=False):
     kind = KINDS[rng.integers(0, 5)]  # not "far": the NDT cell table refuses absurd extents by design, tested elsewhere
-    nt = int(rng.integers(200, 60000))
+    nt = int(rng.integers(200, 60000)) if not large else int(rng.integers(160000, 400000))
     tgt = cloud(nt, kind)
     # the source: the target moved by a small rigid motion, subsampled, plus noise
     ang = rng.uniform(-1, 1, 3) * np.radians([1, 1, 3])
     cz, sz = np.cos(ang[2]), np.sin(ang[2])
     Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
-    ns = int(rng.integers(50, min(nt, 20000) + 1))
+    ns = int(rng.integers(50, min(nt, 20000) + 1)) if not large else int(rng.integers(155000, nt))  # large: several tiles per CTA
     pick = rng.choice(nt, ns, replace=False)
     src = tgt[pick].copy()
     src[:, :3] = (src[:, :3] - rng.uniform(-0.4, 0.4, 3)) @ Rz + rng.normal(0, 0.02, (ns, 3))
@@ -190,11 +190,78 @@ def fuzz_gicp(case):
         report(case, tag, "align %s vs %s  pose diff %.3e m %.3e rad" % (a, b, t_err, r_err))
 
 
+def fuzz_ndt_large(case):
+    if case % 20 == 7:
+        fuzz_ndt(case, large=True)
+
+
+def _pair_for_icp():
+    kind = KINDS[rng.integers(0, 3)]
+    nt = int(rng.integers(300, 20000))
+    tgt = cloud(nt, kind)
+    ns = int(rng.integers(100, min(nt, 8000) + 1))
+    src = tgt[rng.choice(nt, ns, replace=False)].copy()
+    yaw = rng.uniform(-1, 1) * np.radians(3)
+    cz, sz = np.cos(yaw), np.sin(yaw)
+    src[:, :3] = (src[:, :3] - rng.uniform(-0.3, 0.3, 3)) @ np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) + rng.normal(0, 0.02, (ns, 3))
+    return kind, tgt, src.astype(np.float32)
+
+
+def fuzz_icp(case):
+    if case % 3:
+        return
+    kind, tgt, src = _pair_for_icp()
+    corr = float(rng.choice([1.0, 2.0, 30.0]))
+    g, o = api.IterativeClosestPoint(), O.IterativeClosestPoint()
+    for x in (g, o):
+        x.setMaxCorrespondenceDistance(corr)
+        x.setMaximumIterations(100)
+        x.setTransformationEpsilon(1e-8)
+        x.setEuclideanFitnessEpsilon(1e-6)
+        x.setInputTarget(tgt)
+        x.setInputSource(src)
+    tag = "icp %s nt=%d ns=%d corr=%g" % (kind, len(tgt), len(src), corr)
+    for _ in range(2):  # twice: PCL's convergence criteria keep state between aligns
+        g.align()
+        o.align()
+        a = (g.result.iterations, bool(g.result.converged), g.result.line_search_trials)
+        b = (o.nr_iterations, bool(o.converged), o.stats["convergence_state"])
+        t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+        if a != b or not (t_err < 1e-4 and r_err < 1e-4):
+            report(case, tag, "align %s vs %s  pose diff %.3e m %.3e rad" % (a, b, t_err, r_err))
+
+
+def fuzz_gicp_omp(case):
+    if case % 3 != 1:
+        return
+    kind, tgt, src = _pair_for_icp()
+    corr = float(rng.choice([1.0, 2.0]))
+    g, o = api.GeneralizedIterativeClosestPoint(), O.GeneralizedIterativeClosestPoint()
+    for x in (g, o):
+        x.setMaxCorrespondenceDistance(corr)
+        x.setTransformationEpsilon(0.01)
+        x.setMaximumIterations(30)
+        x.setMaximumOptimizerIterations(10)
+        x.setInputTarget(tgt)
+        x.setInputSource(src)
+    tag = "gicp_omp %s nt=%d ns=%d corr=%g" % (kind, len(tgt), len(src), corr)
+    g.align()
+    o.align()
+    a = (g.result.iterations, bool(g.result.converged), g.result.line_search_trials, g.result.evaluations, g.result.hessian_recomputes)
+    b = (o.nr_iterations, bool(o.converged), o.stats["f_calls"], o.stats["df_calls"] + o.stats["fdf_calls"], o.stats["inner_iterations"])
+    t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
+    if a != b or not (t_err < 1e-4 and r_err < 1e-4):
+        report(case, tag, "align %s vs %s  pose diff %.3e m %.3e rad" % (a, b, t_err, r_err))
+
+
+FUZZERS = (fuzz_voxelgrid, fuzz_ndt, fuzz_gicp)
+if os.environ.get("LGS_FUZZ_MORE"):  # the slower fuzzers: multi-tile NDT sources, ICP, pclomp GICP
+    FUZZERS = FUZZERS + (fuzz_ndt_large, fuzz_icp, fuzz_gicp_omp)
 for case in range(n_cases):
-    for fn in (fuzz_voxelgrid, fuzz_ndt, fuzz_gicp):
+    for fn in FUZZERS:
         try:
             fn(case)
         except Exception as e:  # a refusal on one side only is a disagreement too
             report(case, fn.__name__, "exception %r\n%s" % (e, traceback.format_exc(limit=3)))
-print("%d cases x 3 fuzzers, %d disagreements" % (n_cases, len(bad)))
+print("%d cases x %d fuzzers, %d disagreements" % (n_cases, len(FUZZERS), len(bad)))
 sys.exit(1 if bad else 0)
