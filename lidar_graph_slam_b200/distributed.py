@@ -37,12 +37,13 @@ def gather_records(local_records, n_total, pair_ids, rank, world):
 
 
 def records_to_array(records):
-    """lgs_align_result ctypes records -> (n, 26) float32 array [T(16), fitness, trans_prob, iters, conv, evals, trials, hess, pair_id, 0, 0]."""
-    out = np.zeros((len(records), 26), np.float32)
+    """lgs_align_result ctypes records -> (n, 24) float64 array
+    [T(16), fitness, trans_prob, iterations, converged, evaluations, line_search_trials, hessian_recomputes, pair_id]
+    (float64: a fitness of DBL_MAX - no correspondence within range - stays finite, pair ids stay exact)."""
+    out = np.zeros((len(records), 24), np.float64)
     for i, r in enumerate(records):
-        out[i, :16] = np.array(r.T, np.float32)
+        out[i, :16] = np.array(r.T, np.float64)
         out[i, 16] = r.fitness
         out[i, 17] = r.trans_probability
         out[i, 18:24] = [r.iterations, r.converged, r.evaluations, r.line_search_trials, r.hessian_recomputes, r.pair_id]
-        out[i, 25] = r.pair_id
     return out
