@@ -501,6 +501,43 @@ def test_ndt_convert_transform_host_function(oracle):
     assert np.array_equal(api.NormalDistributionsTransform.convertTransform(np.zeros(6)), np.eye(4, dtype=np.float32))
 
 
+def test_ndt_hessian_has_two_triangles_and_counts_do_not_depend_on_the_summation_order(oracle, velodyne_pair):
+    """Two properties of the reference's NDT that the product's parity bars rest on.  (1) The Hessian of computeDerivatives is
+    formed entry by entry from f32 terms (NDT:521-531) and is NOT symmetric: (i,j) and (j,i) round their products in different
+    orders, ~1e-8 apart; the JacobiSVD Newton step sees both triangles, so a restatement must form all 36.  (2) The align is
+    insensitive to the order in which the per-point results are added (NDT:277-282 adds them serially): with the source
+    reversed, every iteration / evaluation / trial / computeHessian count and the final 16 floats stay the same - so "same
+    iteration count as the reference" is a well-defined bar for an implementation that adds in yet another order."""
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.2)["points"]
+    a, b = oracle.NDT(), oracle.NDT()
+    for n, src in ((a, sd), (b, np.ascontiguousarray(sd[::-1]))):
+        n.setResolution(1.0)
+        n.setTransformationEpsilon(0.01)
+        n.setMaximumIterations(64)
+        n.setStepSize(0.1)
+        n.setInputTarget(td)
+        n.setInputSource(src)
+    p = np.array([0.45, 0.12, -0.02, 0.004, -0.008, 0.011])
+    _, _, H = a.derivatives(oracle.ndt_convert_transform(p), p, 0)
+    asym = np.abs(H - H.T) / np.abs(H).max()
+    assert not np.array_equal(H, H.T) and 1e-12 < asym.max() < 1e-6
+    _, _, H64 = a.derivatives(oracle.ndt_convert_transform(p), p, 2)  # computeHessian, f64 terms: symmetric to rounding
+    assert np.abs(H64 - H64.T).max() <= 1e-12 * np.abs(H64).max()
+    rel = velodyne_pair["relative"].astype(np.float64)
+    rng = np.random.default_rng(5)
+    for _ in range(8):
+        d = np.eye(4)
+        yaw = rng.uniform(-1, 1) * np.radians(4.0)
+        d[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+        d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([0.6, 0.6, 0.1])
+        guess = (d @ rel).astype(np.float32)
+        a.align(guess)
+        b.align(guess)
+        assert (a.nr_iterations, a.converged, a.stats) == (b.nr_iterations, b.converged, b.stats)
+        assert np.array_equal(a.final_transformation, b.final_transformation)
+
+
 def test_c_abi_exports_every_declared_symbol():
     """liblgs_b200.so loads on a CPU-only box and exports exactly what include/lgs_c.h declares."""
     from lidar_graph_slam_b200 import _lib
