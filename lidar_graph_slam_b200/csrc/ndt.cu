@@ -496,40 +496,7 @@ void pose_to_matrix(const double x[6], float* T) {
   ndtopt::pose_to_matrix(x, t, T);
 }
 
-// p = [translation, eulerAngles(0,1,2)] of an Affine3f (NDT:103-111): rotation() is the polar factor
-// U V^T of the linear part (f32 Jacobi SVD), then Eigen's eulerAngles branch convention.
-void matrix_to_pose(const float* T, double p[6]) {
-  float L[9], U[9], S[3], V[9], UVt[9], R[9];
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) L[r * 3 + c] = T[c * 4 + r];
-  m::svd_jacobi<3, float>(L, U, S, V);
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) UVt[i * 3 + j] = (U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1]) + U[i * 3 + 2] * V[j * 3 + 2];
-  float det = UVt[0] * (UVt[4] * UVt[8] - UVt[5] * UVt[7]) - UVt[1] * (UVt[3] * UVt[8] - UVt[5] * UVt[6]) +
-              UVt[2] * (UVt[3] * UVt[7] - UVt[4] * UVt[6]);
-  float sgn = det < 0.0f ? -1.0f : 1.0f;
-  for (int r = 0; r < 3; r++) U[r * 3 + 2] *= sgn;
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) R[i * 3 + j] = (U[i * 3] * V[j * 3] + U[i * 3 + 1] * V[j * 3 + 1]) + U[i * 3 + 2] * V[j * 3 + 2];
-  const float pi = static_cast<float>(M_PI);
-  float r0 = std::atan2(R[1 * 3 + 2], R[2 * 3 + 2]);
-  float c2 = std::sqrt(R[0] * R[0] + R[1] * R[1]);
-  float r1;
-  if (r0 > 0.0f) {
-    r0 -= pi;
-    r1 = std::atan2(-R[2], -c2);
-  } else {
-    r1 = std::atan2(-R[2], c2);
-  }
-  float s1 = std::sin(r0), c1 = std::cos(r0);
-  float r2 = std::atan2(s1 * R[2 * 3 + 0] - c1 * R[1 * 3 + 0], c1 * R[1 * 3 + 1] - s1 * R[2 * 3 + 1]);
-  p[0] = T[12];
-  p[1] = T[13];
-  p[2] = T[14];
-  p[3] = -r0;
-  p[4] = -r1;
-  p[5] = -r2;
-}
+using ndtopt::matrix_to_pose;  // NDT:103-111 (ndt_opt.cuh)
 
 void compute_gauss(lgs_ndt* n) {  // NDT:86-93
   double c1 = 10 * (1 - n->outlier_ratio);

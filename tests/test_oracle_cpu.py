@@ -538,6 +538,90 @@ def test_ndt_hessian_has_two_triangles_and_counts_do_not_depend_on_the_summation
         assert np.array_equal(a.final_transformation, b.final_transformation)
 
 
+def _drive_machine_with_oracle_evaluations(L, h, o, guess, n_in, step=0.1, eps=0.01, max_iter=64):
+    """One align: csrc/ndt_opt.cuh's state machine (host build) decides, the oracle evaluates."""
+    import ctypes as C
+    g16 = np.asarray(guess, np.float32).ravel(order="F").copy()
+    L.mh_begin(h, g16.ctypes.data_as(C.c_void_p), C.c_double(step), C.c_double(eps), C.c_int(max_iter), C.c_double(n_in))
+    T16, pose, mode = np.zeros(16, np.float32), np.zeros(6), C.c_int(0)
+    evaluations = 0
+    while True:
+        L.mh_command(h, T16.ctypes.data_as(C.c_void_p), pose.ctypes.data_as(C.c_void_p), C.byref(mode))
+        score, g, H = o.derivatives(T16.reshape(4, 4, order="F"), pose, mode.value)
+        sums = np.zeros(48)
+        if mode.value == 2:
+            sums[:21] = H[np.triu_indices(6)]
+        else:
+            sums[0], sums[1:7] = score, g
+            if mode.value == 0:
+                sums[7:28] = H[np.triu_indices(6)]
+                sums[28:43] = H[np.tril_indices(6, -1)]
+        evaluations += 1
+        assert evaluations < 2000
+        if not L.mh_advance(h, sums.ctypes.data_as(C.c_void_p)):
+            break
+    counts, tp = np.zeros(5, np.int32), C.c_double(0)
+    L.mh_result(h, T16.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), C.byref(tp))
+    return T16.reshape(4, 4, order="F").copy(), [int(c) for c in counts], tp.value
+
+
+def test_ndt_state_machine_on_the_host_walks_the_oracles_path(oracle, velodyne_pair, tmp_path):
+    """The optimiser that runs INSIDE ndt_align_kernel (csrc/ndt_opt.cuh: Newton step by block elimination with refinement,
+    More-Thuente search, restated sinf / cosf, per-entry transform, exit rules), compiled for the host and fed with the oracle's
+    derivative evaluations: over random guesses on the bundled pair, at two resolutions and with DIRECT1 / 7 / 26, it takes the
+    oracle's iterations, evaluations, trials and computeHessian calls and ends on the oracle's 16 floats.  (On the GPU the same
+    source is driven by the CUDA evaluations; this is the part of that parity that needs no GPU.)"""
+    import ctypes as C
+    import subprocess
+    lib = str(tmp_path / "libndt_machine_host.so")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "lidar_graph_slam_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "ndt_machine_host.cpp"), "-o", lib])
+    L = C.CDLL(lib)
+    L.mh_create.restype = C.c_void_p
+    for f in (L.mh_destroy, L.mh_begin, L.mh_command, L.mh_result):
+        f.restype = None
+    L.mh_destroy.argtypes = [C.c_void_p]
+    L.mh_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+    L.mh_command.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mh_advance.argtypes = [C.c_void_p, C.c_void_p]
+    L.mh_advance.restype = C.c_int
+    L.mh_result.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    h = L.mh_create()
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.3)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.4)["points"]
+    rel = velodyne_pair["relative"].astype(np.float64)
+    rng = np.random.default_rng(31)
+    aligns, iterations = 0, set()
+    for res, method, eps, step in ((1.0, 2, 0.01, 0.1), (2.0, 2, 0.01, 0.1), (1.0, 1, 0.001, 0.5), (1.5, 3, 0.05, 0.05)):
+        o = oracle.NDT()
+        o.setResolution(res)
+        o.setTransformationEpsilon(eps)
+        o.setMaximumIterations(40)
+        o.setStepSize(step)
+        o.setNeighborhoodSearchMethod(method)
+        o.setInputTarget(td)
+        o.setInputSource(sd)
+        for k in range(6):
+            d = np.eye(4)
+            scale = 3.0 if k == 5 else 1.0
+            ang = rng.uniform(-1, 1, 3) * np.radians([1.0, 1.0, 4.0]) * scale
+            cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+            d[:3, :3] = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ \
+                np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+            d[:3, 3] = rng.uniform(-1, 1, 3) * np.array([0.6, 0.6, 0.1]) * scale
+            guess = np.eye(4, dtype=np.float32) if k == 0 else (d @ rel).astype(np.float32)
+            T, counts, tp = _drive_machine_with_oracle_evaluations(L, h, o, guess, float(len(sd)), step=step, eps=eps, max_iter=40)
+            o.align(guess)  # after the machine's run: the derivative hook does not disturb the oracle's state, its own align does
+            want = [o.nr_iterations, int(o.converged), o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"]]
+            assert counts == want, (res, method, k, counts, want)
+            assert np.array_equal(T, o.final_transformation), (res, method, k)
+            assert tp == pytest.approx(o.trans_probability, rel=1e-12)
+            aligns += 1
+            iterations.add(o.nr_iterations)
+    L.mh_destroy(h)
+    assert aligns == 24 and len(iterations) >= 6
+
+
 def test_c_abi_exports_every_declared_symbol():
     """liblgs_b200.so loads on a CPU-only box and exports exactly what include/lgs_c.h declares."""
     from lidar_graph_slam_b200 import _lib
