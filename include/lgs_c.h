@@ -166,6 +166,10 @@ int lgs_ndt_create(lgs_ctx* ctx, lgs_ndt** out);
 void lgs_ndt_destroy(lgs_ndt* ndt);
 int lgs_ndt_set_resolution(lgs_ndt* ndt, float resolution);             /* NDT.h:132-142 setResolution */
 int lgs_ndt_set_step_size(lgs_ndt* ndt, double step_size);              /* NDT.h:162-166 setStepSize */
+/* Parity mode (no counterpart in the reference): solve every Newton step (NDT:127-129) with the restated JacobiSVD instead of
+ * the block elimination.  The align then repeats the reference's arithmetic step by step (bit-identical transforms on every
+ * fuzzed problem) at about twice the time per align; off by default.  LGS_NDT_EXACT_SOLVE=1 in the environment does the same. */
+int lgs_ndt_set_exact_newton_step(lgs_ndt* ndt, int32_t on);
 int lgs_ndt_set_transformation_epsilon(lgs_ndt* ndt, double eps);       /* pcl::Registration::setTransformationEpsilon, LSM:58 */
 int lgs_ndt_set_maximum_iterations(lgs_ndt* ndt, int32_t n);            /* pcl::Registration::setMaximumIterations, LSM:66 */
 int lgs_ndt_set_outlier_ratio(lgs_ndt* ndt, double ratio);              /* NDT.h:180-184 setOutlierRatio */

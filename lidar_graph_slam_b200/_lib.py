@@ -81,6 +81,7 @@ SYMBOLS = {
     "lgs_ndt_set_maximum_iterations": (_i32, [_vp, _i32]),
     "lgs_ndt_set_outlier_ratio": (_i32, [_vp, _f64]),
     "lgs_ndt_set_search_method": (_i32, [_vp, _i32]),
+    "lgs_ndt_set_exact_newton_step": (_i32, [_vp, _i32]),
     "lgs_ndt_set_target": (_i32, [_vp, _vp, _i64, _i32]),
     "lgs_ndt_set_source": (_i32, [_vp, _vp, _i64, _i32]),
     "lgs_ndt_set_target_dev": (_i32, [_vp, _vp, _i64]),

@@ -352,6 +352,11 @@ class NormalDistributionsTransform(_Registration):
     def setTransformationEpsilon(self, e): check(self._L.lgs_ndt_set_transformation_epsilon(self._h, float(e)))
     def setMaximumIterations(self, n): check(self._L.lgs_ndt_set_maximum_iterations(self._h, int(n)))
     def setNeighborhoodSearchMethod(self, m): check(self._L.lgs_ndt_set_search_method(self._h, int(m)))
+
+    def setExactNewtonStep(self, on):
+        """Parity mode: every Newton step through the restated JacobiSVD of the reference instead of the block elimination."""
+        check(self._L.lgs_ndt_set_exact_newton_step(self._h, 1 if on else 0))
+
     def setNumThreads(self, n): pass  # OpenMP knob of the reference (NDT.h:113-115); meaningless on the GPU
 
     @staticmethod

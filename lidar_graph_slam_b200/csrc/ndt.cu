@@ -428,6 +428,7 @@ struct lgs_ndt {
   float resolution = 1.0f;
   double step_size = 0.1, outlier_ratio = 0.55, trans_eps = 0.1;
   int max_iter = 35;
+  bool exact_newton_step = false;  // lgs_ndt_set_exact_newton_step
   int search = LGS_NDT_DIRECT7;
   // clouds
   DevBuf target, source, out_cloud;
@@ -970,10 +971,16 @@ struct AlignOutcome {
 
 // the optimiser stepped by the host: one kernel launch per evaluation (small or empty inputs, profiling of the
 // per-evaluation kernels, LGS_NDT_DEVICE_ALIGN=0)
+// parity mode: the reference's JacobiSVD for every Newton step (setter, or LGS_NDT_EXACT_SOLVE=1 read at every align)
+bool exact_solve_requested(const lgs_ndt* n) {
+  const char* e = getenv("LGS_NDT_EXACT_SOLVE");
+  return n->exact_newton_step || (e && e[0] && e[0] != '0');
+}
+
 int align_host_stepped(lgs_ndt* n, const double p0[6], const float T0[16], AlignOutcome* out) {
   ndtopt::Machine m;
   ndtopt::Command c;
-  m.begin(p0, T0, n->step_size, n->trans_eps, n->max_iter, static_cast<double>(n->n_source), &c);
+  m.begin(p0, T0, n->step_size, n->trans_eps, n->max_iter, static_cast<double>(n->n_source), &c, exact_solve_requested(n) ? 1 : 0);
   n->evals = n->hess_recomputes = 0;
   while (true) {
     command_to_params(c, &n->P);
@@ -1026,7 +1033,7 @@ int align_on_device(lgs_ndt* n, const double p0[6], const float T0[16], AlignOut
   args.trans_eps = n->trans_eps;
   args.n_in = static_cast<double>(n->n_source);
   args.max_iter = n->max_iter;
-  args.pad = 0;
+  args.exact_solve = exact_solve_requested(n) ? 1 : 0;
   Mailbox mb;
   LGS_TRY(mailbox_next(ctx, &mb));
   LGS_CUDA(cudaMemsetAsync(n->align_dev.p, 0, 48, st));  // seq, the arrival counter, the trace words
@@ -1126,6 +1133,7 @@ int lgs_ndt_set_resolution(lgs_ndt* n, float r) {  // NDT.h:132-142: re-init onl
   return LGS_OK;
 }
 int lgs_ndt_set_step_size(lgs_ndt* n, double s) { LGS_REQUIRE(n, "null"); n->step_size = s; return LGS_OK; }
+int lgs_ndt_set_exact_newton_step(lgs_ndt* n, int32_t on) { LGS_REQUIRE(n, "null"); n->exact_newton_step = on != 0; return LGS_OK; }
 int lgs_ndt_set_transformation_epsilon(lgs_ndt* n, double e) { LGS_REQUIRE(n, "null"); n->trans_eps = e; return LGS_OK; }
 int lgs_ndt_set_maximum_iterations(lgs_ndt* n, int32_t it) { LGS_REQUIRE(n, "null"); n->max_iter = it; return LGS_OK; }
 int lgs_ndt_set_outlier_ratio(lgs_ndt* n, double o) { LGS_REQUIRE(n, "null"); n->outlier_ratio = o; return LGS_OK; }

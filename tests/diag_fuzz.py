@@ -138,7 +138,8 @@ def fuzz_ndt(case, large=False):
         a = (r.iterations, bool(r.converged), r.evaluations, r.line_search_trials, r.hessian_recomputes)
         b = (o.nr_iterations, bool(o.converged), o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"])
         t_err, r_err = pose_error(o.final_transformation, g.getFinalTransformation())
-        if a != b or not (t_err < 1e-6 and r_err < 1e-6):
+        bitwise = os.environ.get("LGS_FUZZ_BITWISE") and not np.array_equal(o.final_transformation, g.getFinalTransformation())
+        if a != b or not (t_err < 1e-6 and r_err < 1e-6) or bitwise:  # LGS_FUZZ_BITWISE: with LGS_NDT_EXACT_SOLVE=1 the 16 floats are the oracle's
             report(case, tag, "align %s vs %s  pose diff %.3e m %.3e rad" % (a, b, t_err, r_err))
             out = os.path.join(ROOT, "gpurun_out")
             if os.path.isdir(out):  # input of tests/diag_ndt_eval_diff.py --case

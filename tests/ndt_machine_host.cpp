@@ -21,11 +21,11 @@ void* mh_create() { return new Host(); }
 void mh_destroy(void* h) { delete static_cast<Host*>(h); }
 
 // NDT:95-119: the pose of the guess and the first command
-void mh_begin(void* hp, const float* guess16, double step_size, double trans_eps, int max_iter, double n_in) {
+void mh_begin(void* hp, const float* guess16, double step_size, double trans_eps, int max_iter, double n_in, int exact_solve) {
   Host* h = static_cast<Host*>(hp);
   double p0[6];
   matrix_to_pose(guess16, p0);
-  h->m.begin(p0, guess16, step_size, trans_eps, max_iter, n_in, &h->c);
+  h->m.begin(p0, guess16, step_size, trans_eps, max_iter, n_in, &h->c, exact_solve);
   h->first = true;
 }
 

@@ -852,6 +852,29 @@ def test_fuzzed_clouds_and_parameters_against_the_oracle():
     assert out.returncode == 0 and "140 cases x 3 fuzzers, 0 disagreements" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
 
 
+def test_ndt_exact_newton_step_mode_is_bit_identical_to_the_oracle(api, oracle, velodyne_pair):
+    """Parity mode (lgs_ndt_set_exact_newton_step / LGS_NDT_EXACT_SOLVE=1): every Newton step of the device-resident align goes
+    through the JacobiSVD restatement instead of the block elimination.  Then the whole align repeats the reference's arithmetic
+    and the final transform is the oracle's bit for bit - on the bundled pair through the setter, and on 60 fuzzed problems
+    (where the default mode ends one f32 ulp away in ~1.5 % of the aligns) through the environment switch."""
+    import subprocess
+    import sys
+    td = oracle.voxel_grid(velodyne_pair["target"], 0.2)["points"]
+    sd = oracle.voxel_grid(velodyne_pair["source"], 0.3)["points"]
+    g, o = _ndt_pair(api, oracle, td, sd, res=1.0, eps=0.01, it=64)
+    g.setExactNewtonStep(True)
+    for guess in _random_guesses(velodyne_pair["relative"], 7, 6):
+        g.align(guess)
+        o.align(guess)
+        r = g.result
+        assert (r.iterations, bool(r.converged), r.evaluations, r.line_search_trials, r.hessian_recomputes) == \
+            (o.nr_iterations, o.converged, o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"])
+        assert np.array_equal(g.getFinalTransformation(), o.final_transformation)
+    env = dict(os.environ, LGS_NDT_EXACT_SOLVE="1", LGS_FUZZ_BITWISE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "diag_fuzz.py"), "60", "31"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "0 disagreements" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+
+
 def _random_guesses(rel, seed, count, yaw_deg=4.0, xy=0.6):
     rng = np.random.default_rng(seed)
     out = []

@@ -538,11 +538,11 @@ def test_ndt_hessian_has_two_triangles_and_counts_do_not_depend_on_the_summation
         assert np.array_equal(a.final_transformation, b.final_transformation)
 
 
-def _drive_machine_with_oracle_evaluations(L, h, o, guess, n_in, step=0.1, eps=0.01, max_iter=64):
+def _drive_machine_with_oracle_evaluations(L, h, o, guess, n_in, step=0.1, eps=0.01, max_iter=64, exact=0):
     """One align: csrc/ndt_opt.cuh's state machine (host build) decides, the oracle evaluates."""
     import ctypes as C
     g16 = np.asarray(guess, np.float32).ravel(order="F").copy()
-    L.mh_begin(h, g16.ctypes.data_as(C.c_void_p), C.c_double(step), C.c_double(eps), C.c_int(max_iter), C.c_double(n_in))
+    L.mh_begin(h, g16.ctypes.data_as(C.c_void_p), C.c_double(step), C.c_double(eps), C.c_int(max_iter), C.c_double(n_in), C.c_int(exact))
     T16, pose, mode = np.zeros(16, np.float32), np.zeros(6), C.c_int(0)
     evaluations = 0
     while True:
@@ -570,7 +570,8 @@ def test_ndt_state_machine_on_the_host_walks_the_oracles_path(oracle, velodyne_p
     More-Thuente search, restated sinf / cosf, per-entry transform, exit rules), compiled for the host and fed with the oracle's
     derivative evaluations: over random guesses on the bundled pair, at two resolutions and with DIRECT1 / 7 / 26, it takes the
     oracle's iterations, evaluations, trials and computeHessian calls and ends on the oracle's 16 floats.  (On the GPU the same
-    source is driven by the CUDA evaluations; this is the part of that parity that needs no GPU.)"""
+    source is driven by the CUDA evaluations; this is the part of that parity that needs no GPU.)  Then 40 fuzzed problems in
+    both solver modes."""
     import ctypes as C
     import subprocess
     lib = str(tmp_path / "libndt_machine_host.so")
@@ -581,7 +582,7 @@ def test_ndt_state_machine_on_the_host_walks_the_oracles_path(oracle, velodyne_p
     for f in (L.mh_destroy, L.mh_begin, L.mh_command, L.mh_result):
         f.restype = None
     L.mh_destroy.argtypes = [C.c_void_p]
-    L.mh_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+    L.mh_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
     L.mh_command.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mh_advance.argtypes = [C.c_void_p, C.c_void_p]
     L.mh_advance.restype = C.c_int
@@ -618,8 +619,54 @@ def test_ndt_state_machine_on_the_host_walks_the_oracles_path(oracle, velodyne_p
             assert tp == pytest.approx(o.trans_probability, rel=1e-12)
             aligns += 1
             iterations.add(o.nr_iterations)
-    L.mh_destroy(h)
     assert aligns == 24 and len(iterations) >= 6
+    # Fuzzed problems (clusters, walls, duplicated points: Hessians with cond up to 1e8).  The default Newton step (block
+    # elimination) keeps the oracle's counts and stays within 1e-4 m of its transform; in parity mode (exact_solve: the
+    # JacobiSVD restatement for every step) the transform is the oracle's, bit for bit.
+    rng = np.random.default_rng(2)
+    flips = 0
+    for case in range(40):
+        kind = case % 3
+        nt = int(rng.integers(300, 6000))
+        if kind == 0:
+            c = rng.uniform(-25, 25, (max(2, nt // 200), 3)) * np.array([1, 1, 0.15])
+            pts = c[rng.integers(0, len(c), nt)] + rng.normal(0, 0.4, (nt, 3))
+        elif kind == 1:
+            pts = rng.uniform(-20, 20, (nt, 3))
+            w = rng.integers(0, 3, nt)
+            pts[w == 0, 2] = -1.5
+            pts[w == 1, 0] = np.round(pts[w == 1, 0] / 10) * 10
+        else:
+            base = rng.uniform(-10, 10, (max(1, nt // 8), 3))
+            pts = base[rng.integers(0, len(base), nt)]
+        tgt = np.zeros((nt, 4), np.float32)
+        tgt[:, :3] = pts
+        ns = int(rng.integers(50, min(nt, 2000) + 1))
+        src = tgt[rng.choice(nt, ns, replace=False)].copy()
+        yaw = rng.uniform(-1, 1) * np.radians(3)
+        Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+        src[:, :3] = ((src[:, :3] - rng.uniform(-0.4, 0.4, 3)) @ Rz + rng.normal(0, 0.02, (ns, 3))).astype(np.float32)
+        res, method = float(rng.choice([0.5, 1.0, 2.0])), int(rng.choice([1, 2, 3]))
+        eps, it, step = float(rng.choice([0.01, 0.001])), int(rng.choice([5, 30, 64])), float(rng.choice([0.1, 0.5]))
+        o = oracle.NDT()
+        o.setResolution(res)
+        o.setTransformationEpsilon(eps)
+        o.setMaximumIterations(it)
+        o.setStepSize(step)
+        o.setNeighborhoodSearchMethod(method)
+        o.setInputTarget(tgt)
+        o.setInputSource(src)
+        guess = np.eye(4, dtype=np.float32)
+        guess[:3, 3] = rng.uniform(-0.3, 0.3, 3) * np.array([1, 1, 0.1])
+        fast = _drive_machine_with_oracle_evaluations(L, h, o, guess, float(ns), step=step, eps=eps, max_iter=it)
+        exact = _drive_machine_with_oracle_evaluations(L, h, o, guess, float(ns), step=step, eps=eps, max_iter=it, exact=1)
+        o.align(guess)
+        want = [o.nr_iterations, int(o.converged), o.stats["derivative_evals"], o.stats["line_search_trials"], o.stats["hessian_recomputes"]]
+        assert exact[1] == want and np.array_equal(exact[0], o.final_transformation), (case, exact[1], want)
+        assert fast[1] == want and np.abs(fast[0] - o.final_transformation).max() < 1e-4, (case, fast[1], want)
+        flips += not np.array_equal(fast[0], o.final_transformation)
+    assert flips <= 4  # the elimination differs from the SVD by ~cond * 1e-16: now and then one f32 ulp of one entry
+    L.mh_destroy(h)
 
 
 def test_c_abi_exports_every_declared_symbol():
